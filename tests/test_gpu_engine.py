@@ -1,0 +1,208 @@
+"""GPU: the reference's own vector-engine tests, replayed through the CUDA engine via the C-ABI, plus the
+semantics checklist of SURVEY.md section 8c (edge cases the reference code defines but does not test)."""
+import threading
+
+import numpy as np
+import pytest
+
+import wax_b200
+from wax_b200 import CUDAVectorEngine, VectorMetric, VectorSearchSession
+
+from helpers import EngineModel, load_json
+from test_oracle import METRICS, _run_kat_steps
+
+pytestmark = pytest.mark.gpu
+M = {"cosine": VectorMetric.cosine, "dot": VectorMetric.dot, "l2": VectorMetric.l2}
+
+
+@pytest.mark.parametrize("case", [c for c in load_json("reference_kats.json")["cases"] if c["steps"]],
+                         ids=lambda c: c["name"])
+def test_reference_kats_through_cuda_engine(case):
+    def search(eng, query, k, case):
+        if case.get("session"):
+            return VectorSearchSession(eng).search(query, k)          # VectorSearchSession.swift:70-76
+        if case.get("normalize_query"):
+            query = wax_b200.normalize_l2(query)
+        return eng.search(query, k)
+
+    def roundtrip(eng):
+        blob = eng.serialize()
+        assert blob
+        fresh = CUDAVectorEngine(eng.metric, eng.dimensions)
+        fresh.deserialize(blob)
+        return fresh
+
+    eng = _run_kat_steps(case, lambda: CUDAVectorEngine(M[case["metric"]], case["dims"]), search, roundtrip)
+    if case.get("pool_reuse"):       # MetalVectorEnginePoolTests.swift:7-20
+        a1, r1 = eng.debug_buffer_pool_stats()
+        eng.search([1.0, 0.0], 1)
+        a2, r2 = eng.debug_buffer_pool_stats()
+        assert a2 == a1 and r2 >= r1 + 1
+
+
+def test_search_after_add_correctness():
+    """MetalVectorEngineBenchmark.swift:131-172."""
+    dims, k = 128, 5
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    for i in range(100):
+        v = np.full(dims, i / 100.0, np.float32); v[0] = 1.0
+        eng.add(i, v)
+    q = np.full(dims, 0.5, np.float32)
+    assert len(eng.search(q, k)) == k
+    for i in range(100, 200):
+        v = np.full(dims, i / 200.0, np.float32); v[0] = 0.5
+        eng.add(i, v)
+    r2 = eng.search(q, k)
+    assert len(r2) == k and any(100 <= i < 200 for i, _ in r2)
+
+
+def test_empty_engine_returns_empty_without_validation():
+    eng = CUDAVectorEngine(VectorMetric.cosine, 4)
+    assert eng.search([1, 0, 0, 0], 10) == []
+    assert eng.search([1, 0], 10) == []          # `guard vectorCount > 0` precedes validate (:448-449)
+    eng.remove(5)                                # remove on empty: no-op (:425)
+    assert eng.count == 0
+
+
+def test_dimension_mismatch_is_encoding_error():
+    eng = CUDAVectorEngine(VectorMetric.cosine, 4)
+    eng.add(1, [1, 0, 0, 0])
+    with pytest.raises(wax_b200.EncodingError, match="vector dimension mismatch: expected 4, got 3"):
+        eng.search([1, 0, 0], 1)
+    with pytest.raises(wax_b200.EncodingError):
+        eng.add(2, [1, 0, 0])
+    with pytest.raises(wax_b200.EncodingError):
+        eng.add_batch([2, 3], [[1, 0, 0, 0], [1, 0, 0]])
+    with pytest.raises(wax_b200.EncodingError, match="frameIds.count != vectors.count"):
+        eng.add_batch([2, 3], [[1, 0, 0, 0]])
+    eng.add_batch([], [])                        # empty batch: no-op (:360)
+    assert eng.count == 1
+
+
+def test_topk_clamp_and_min_k_n():
+    eng = CUDAVectorEngine(VectorMetric.dot, 8)
+    rng = np.random.default_rng(0)
+    eng.add_batch(list(range(50)), rng.standard_normal((50, 8)).astype(np.float32))
+    q = rng.standard_normal(8).astype(np.float32)
+    assert len(eng.search(q, 0)) == 1 and len(eng.search(q, -7)) == 1   # clamp to 1 (:843)
+    assert len(eng.search(q, 10)) == 10
+    assert len(eng.search(q, 50_000)) == 50                             # clamp to 10000 then min(k, N)
+    full = eng.search(q, 10_000)
+    assert [i for i, _ in full[:10]] == [i for i, _ in eng.search(q, 10)]
+    assert all(a[1] >= b[1] for a, b in zip(full, full[1:]))            # best first
+
+
+@pytest.mark.parametrize("metric", list(VectorMetric))
+def test_mutations_match_reference_semantics(oracle, metric):
+    """Upsert overwrites in place, new ids append, remove keeps relative order (MetalVectorEngine.swift:330-444):
+    checked by replaying a random op sequence on the list model and comparing full results + the raw rows."""
+    dims = 12
+    rng = np.random.default_rng(1 + metric.value)
+    eng, model = CUDAVectorEngine(metric, dims), EngineModel(oracle, metric.value, dims)
+    pool = list(range(100, 140))
+    for step in range(120):
+        op = rng.integers(0, 10)
+        if op < 5:
+            i, v = int(rng.choice(pool)), rng.standard_normal(dims).astype(np.float32)
+            eng.add(i, v); model.add(i, v)
+        elif op < 8:
+            n = int(rng.integers(1, 9))
+            ids = [int(x) for x in rng.choice(pool, n)]            # duplicates inside a batch allowed
+            vs = rng.standard_normal((n, dims)).astype(np.float32)
+            eng.add_batch(ids, vs); model.add_batch(ids, list(vs))
+        else:
+            i = int(rng.choice(pool + [999]))                      # 999: unknown id -> no-op
+            eng.remove(i); model.remove(i)
+        assert eng.count == len(model.ids)
+        if step % 10 == 9 and model.ids:
+            q = rng.standard_normal(dims).astype(np.float32)
+            got, exp = eng.search(q, 15), model.search(q, 15)
+            assert [g[0] for g in got] == [e[0] for e in exp]
+            assert np.array_equal(np.float32([g[1] for g in got]), np.float32([e[1] for e in exp]))
+            assert np.array_equal(eng.read_rows(0, eng.count), model.corpus())
+
+
+def test_serialize_is_byte_identical_to_the_mv2v_layout(oracle):
+    rng = np.random.default_rng(5)
+    for metric in VectorMetric:
+        eng = CUDAVectorEngine(metric, 6)
+        vec = rng.standard_normal((9, 6)).astype(np.float32)
+        ids = [int(x) for x in rng.integers(0, 2**63, 9, dtype=np.uint64)]
+        eng.add_batch(ids, vec)
+        blob = eng.serialize()
+        assert blob == oracle.mv2v_encode(metric.value, vec, ids)      # MetalVectorEngine.swift:682-714
+        other = CUDAVectorEngine(metric, 6)
+        other.deserialize(blob)
+        assert other.count == 9 and other.serialize() == blob
+        q = rng.standard_normal(6).astype(np.float32)
+        assert other.search(q, 9) == eng.search(q, 9)
+    empty = CUDAVectorEngine(VectorMetric.cosine, 5)
+    assert empty.serialize() == oracle.mv2v_encode(0, np.zeros((0, 5), np.float32), [])
+    empty2 = CUDAVectorEngine(VectorMetric.cosine, 5)
+    empty2.deserialize(empty.serialize())
+    assert empty2.count == 0
+
+
+def test_deserialize_rejects_malformed_blobs(oracle):
+    vec = np.array([[1.0, -2.0], [0.5, 0.25]], np.float32)
+    blob = oracle.mv2v_encode(0, vec, [7, 9])
+    eng = CUDAVectorEngine(VectorMetric.cosine, 2)
+
+    def corrupt(i, b):
+        x = bytearray(blob); x[i] = b; return bytes(x)
+    cases = [(blob[:20], "too small"), (corrupt(0, 0x58), "magic mismatch"), (corrupt(4, 2), "version"),
+             (corrupt(6, 1), "encoding"), (corrupt(7, 1), "Metric mismatch"), (corrupt(8, 3), "Dimension mismatch"),
+             (corrupt(30, 1), "reserved bytes must be zero"), (corrupt(20, 17), "Vector data length mismatch"),
+             (corrupt(52, 8), "FrameId data length mismatch"), (blob + b"\x00", "length mismatch")]
+    for bad, reason in cases:
+        with pytest.raises(wax_b200.InvalidToc, match=reason):
+            eng.deserialize(bad)
+        assert oracle.mv2v_decode(bad, 0, 2)[0] != 0            # the oracle rejects the same blobs
+    eng.deserialize(blob)
+    assert eng.count == 2 and eng.search([1.0, -2.0], 1)[0][0] == 7
+
+
+def test_stage_for_commit_follows_the_dirty_flag():
+    class FakeWax:
+        def __init__(self): self.calls = []
+        def stage_vec_index_for_next_commit(self, **kw): self.calls.append(kw)
+    wax, eng = FakeWax(), CUDAVectorEngine(VectorMetric.cosine, 2)
+    eng.stage_for_commit(wax)
+    assert wax.calls == []                       # not dirty -> nothing staged (:819)
+    eng.add(3, [1.0, 0.0])
+    eng.stage_for_commit(wax); eng.stage_for_commit(wax)
+    assert len(wax.calls) == 1 and wax.calls[0]["vector_count"] == 1 and wax.calls[0]["dimension"] == 2
+    assert wax.calls[0]["bytes"][:4] == b"MV2V" and wax.calls[0]["similarity"] == 0
+
+
+def test_concurrent_searches_are_reentrant(oracle):
+    eng = CUDAVectorEngine(VectorMetric.cosine, 64)
+    eng.fill_synthetic(3, 20_000)
+    qs = oracle.synth_rows(4, 0, 16, 64)
+    expected = [eng.search(q, 10) for q in qs]
+    errors = []
+
+    def work(t):
+        try:
+            for rep in range(20):
+                i = (t + rep) % len(qs)
+                if eng.search(qs[i], 10) != expected[i]:
+                    errors.append((t, rep))
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+    threads = [threading.Thread(target=work, args=(t,)) for t in range(8)]
+    [t.start() for t in threads]; [t.join() for t in threads]
+    assert not errors
+    allocs, reuses = eng.debug_buffer_pool_stats()
+    assert allocs <= 9 and reuses > 0
+
+
+def test_growth_from_initial_reserve(oracle):
+    eng = CUDAVectorEngine(VectorMetric.l2, 3)           # initialReserve 64, doubling (:19, :857-871)
+    rows = oracle.synth_rows(8, 0, 1000, 3, normalize=False)
+    for start in range(0, 1000, 37):
+        eng.add_batch(list(range(start, min(start + 37, 1000))), rows[start:start + 37])
+    assert eng.count == 1000 and np.array_equal(eng.read_rows(0, 1000), rows)
+    r, _, s = oracle.search(oracle.L2, rows, rows[500], 5, mode=oracle.ACC_F32_TREE)
+    got = eng.search(rows[500], 5)
+    assert [g[0] for g in got] == r.tolist() and got[0][0] == 500 and got[0][1] == 0.0

@@ -1,0 +1,51 @@
+"""CPU: host-side logic of the mirror (no device needed) checked against the oracle."""
+import numpy as np
+import pytest
+
+import wax_b200
+from wax_b200 import sharded
+
+
+def test_normalize_matches_oracle(oracle):
+    for seed in range(5):
+        v = oracle.synth_row(40 + seed, 0, 384, False) * np.float32(seed + 0.5)
+        assert (wax_b200.normalize_l2(v).view(np.uint32) == oracle.normalize_l2(v).view(np.uint32)).all()
+        assert wax_b200.is_normalized_l2(v) == oracle.is_normalized_l2(v)
+    assert wax_b200.is_normalized_l2([1.0, 0.0, 0.0]) and not wax_b200.is_normalized_l2([2.0, 0.0, 0.0])
+    assert not wax_b200.is_normalized_l2([])
+    assert wax_b200.normalize_l2([0.0, 0.0]).tolist() == [0.0, 0.0]
+
+
+def test_metric_score_matches_oracle(oracle):
+    for m in wax_b200.VectorMetric:
+        for d in (0.0, 0.25, -3.5, 1e-7, float("nan"), float("inf")):
+            assert m.score(d) == oracle.score_from_distance(m.value, d)
+        assert (sharded.score_from_distance(m.value, np.array([0.25, np.nan], np.float32)).tolist()
+                == [m.score(0.25), 0.0])
+
+
+def test_shard_ranges_partition_the_corpus():
+    for total in (0, 1, 7, 10_000_000, 100_000_000):
+        for world in (1, 2, 3, 8):
+            spans = [sharded.shard_range(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
+
+
+def test_merge_candidates_total_order():
+    c = np.zeros(7, sharded.CAND_DTYPE)
+    c["distance"] = [0.5, 0.1, 0.5, 0.1, 0.9, 0.0, 0.1]
+    c["row"] = [10, 30, 5, 20, 1, 99, 25]
+    c["frame_id"] = c["row"] + 1000
+    c["valid"] = [1, 1, 1, 1, 1, 0, 1]            # the 0.0 entry is padding
+    best = sharded.merge_candidates(c, 4)
+    assert best["row"].tolist() == [20, 25, 30, 5]
+    assert sharded.merge_candidates(c[5:6], 4).size == 0
+
+
+def test_engine_argument_errors_are_wax_errors():
+    with pytest.raises(wax_b200.InvalidToc):
+        wax_b200.CUDAVectorEngine(wax_b200.VectorMetric.cosine, 0)
+    with pytest.raises(wax_b200.CapacityExceeded):
+        wax_b200.CUDAVectorEngine(wax_b200.VectorMetric.cosine, 1_000_001)

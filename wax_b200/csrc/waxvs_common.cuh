@@ -1,0 +1,173 @@
+// waxvs_common.cuh -- shared device helpers for the B200 (sm_100a) vector-scan kernels.
+//
+// Ordering key.  Every candidate is a 64-bit key  (orderable(distance) << 32) | local_row  so that the
+// total order (distance ascending, row ascending) -- the order the oracle fixes, see
+// oracle/wax_oracle.h -- is one unsigned compare.  The reference leaves ties unspecified
+// (TopKReduction.metal:84-101, MetalVectorEngine.swift:671,678); non-finite distances are dropped
+// (MetalVectorEngine.swift:597) and are represented here by WAXVS_KEY_NONE.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#define WAXVS_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+#define WAXVS_UKEY_NONE 0xFFFFFFFFu
+#define WAXVS_FULL_MASK 0xFFFFFFFFu
+
+namespace waxvs {
+
+enum Metric : int { kCosine = 0, kDot = 1, kL2 = 2 };
+
+// float -> uint32 whose unsigned order equals the float order (for non-NaN inputs).
+__device__ __forceinline__ uint32_t orderable_u32(float f) {
+    uint32_t u = __float_as_uint(f);
+    return u ^ ((u & 0x80000000u) ? 0xFFFFFFFFu : 0x80000000u);
+}
+__device__ __forceinline__ float from_orderable_u32(uint32_t k) {
+    uint32_t u = k ^ ((k & 0x80000000u) ? 0x80000000u : 0xFFFFFFFFu);
+    return __uint_as_float(u);
+}
+__host__ __device__ __forceinline__ bool finite_f32(float f) {
+#ifdef __CUDA_ARCH__
+    return (__float_as_uint(f) & 0x7F800000u) != 0x7F800000u;
+#else
+    union { float f; uint32_t u; } x; x.f = f;
+    return (x.u & 0x7F800000u) != 0x7F800000u;
+#endif
+}
+__device__ __forceinline__ uint64_t make_key(float d, uint32_t row) {
+    return (static_cast<uint64_t>(orderable_u32(d)) << 32) | row;
+}
+
+// ---- USearch metric epilogues (oracle/wax_oracle.c finish_f32; USearch 2.23.0 index_plugins.hpp) ----
+// All IEEE round-to-nearest: __fsqrt_rn / __fdiv_rn are bit-identical to the host's sqrtf and '/'.
+__device__ __forceinline__ float finish_cos(float ab, float a2, float sqrt_a2, float b2) {
+    float d;
+    const bool az = (a2 == 0.0f), bz = (b2 == 0.0f);
+    if (az || bz) d = (az && bz) ? 0.0f : 1.0f;
+    else d = __fsub_rn(1.0f, __fdiv_rn(ab, __fmul_rn(sqrt_a2, __fsqrt_rn(b2))));
+    return __fadd_rn(d, 0.0f);  // -0 -> +0
+}
+__device__ __forceinline__ float finish_dot(float ab) { return __fadd_rn(__fsub_rn(1.0f, ab), 0.0f); }
+__device__ __forceinline__ float finish_l2(float l2) { return __fadd_rn(l2, 0.0f); }
+
+// ---- warp helpers -------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_butterfly_sum(float v) {
+    // xor butterfly 16,8,4,2,1: the order oracle tree_reduce128() mirrors.
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) v = __fadd_rn(v, __shfl_xor_sync(WAXVS_FULL_MASK, v, off));
+    return v;
+}
+
+__device__ __forceinline__ uint64_t shfl_u64(uint64_t v, int src) {
+    uint32_t lo = __shfl_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(v), src);
+    uint32_t hi = __shfl_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(v >> 32), src);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int delta) {
+    uint32_t lo = __shfl_up_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(v), delta);
+    uint32_t hi = __shfl_up_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(v >> 32), delta);
+    return (static_cast<uint64_t>(hi) << 32) | lo;
+}
+
+// Reduce-scatter over the warp: on entry every lane holds R partial sums (one per row of the step); on
+// exit v[0] of lane L is the full 32-lane sum for row (L >> (5 - log2 R)).  Each addition pairs the same
+// two lanes as the plain xor butterfly (16,8,4,2,1), so the result is bit-identical to it, at
+// (R - 1 + 5 - log2 R) shuffles per R rows instead of 5R.
+template <int R>
+__device__ __forceinline__ void warp_reduce_scatter(float (&v)[R], int lane) {
+    static_assert(R == 1 || R == 2 || R == 4 || R == 8 || R == 16, "R must be a power of two <= 16");
+    int off = 16;
+#pragma unroll
+    for (int half = R / 2; half >= 1; half >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int j = 0; j < half; ++j) {
+            const float send = upper ? v[j] : v[j + half];
+            const float keep = upper ? v[j + half] : v[j];
+            v[j] = __fadd_rn(keep, __shfl_xor_sync(WAXVS_FULL_MASK, send, off));
+        }
+    }
+#pragma unroll
+    for (; off >= 1; off >>= 1) v[0] = __fadd_rn(v[0], __shfl_xor_sync(WAXVS_FULL_MASK, v[0], off));
+}
+
+// ---- per-warp sorted top-k list (k <= 32): lane i holds the i-th best key ---------------------------------
+struct WarpTopK {
+    uint64_t key;     // this lane's entry (WAXVS_KEY_NONE beyond k)
+    uint64_t thresh;  // key of entry k-1 (warp-uniform): only strictly smaller keys enter
+    __device__ __forceinline__ void init() { key = WAXVS_KEY_NONE; thresh = WAXVS_KEY_NONE; }
+    // x is warp-uniform and x < thresh.
+    __device__ __forceinline__ void insert(uint64_t x, int lane, int k) {
+        const int pos = __popc(__ballot_sync(WAXVS_FULL_MASK, key < x));
+        const uint64_t up = shfl_up_u64(key, 1);
+        if (lane == pos) key = x;
+        else if (lane > pos) key = up;
+        if (lane >= k) key = WAXVS_KEY_NONE;
+        thresh = shfl_u64(key, k - 1);
+    }
+    // Merge a sorted list held one-entry-per-lane by `other` (entries beyond its length are KEY_NONE).
+    __device__ __forceinline__ void merge_sorted(uint64_t other, int lane, int k) {
+        for (int i = 0; i < k; ++i) {
+            const uint64_t x = shfl_u64(other, i);
+            if (x >= thresh) break;  // sorted: the rest are worse (KEY_NONE never passes)
+            insert(x, lane, k);
+        }
+    }
+};
+
+// ---- mbarrier / bulk-copy (TMA 1-D) PTX ---------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait_parity(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    uint32_t done;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(addr), "r"(parity)
+            : "memory");
+    } while (!done);
+}
+// global -> shared bulk copy (SASS: UBLKCP), completion counted in bytes on `bar`.
+__device__ __forceinline__ void bulk_copy_g2s(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                              uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s_hint(void *smem_dst, const void *gmem_src, uint32_t bytes,
+                                                   uint64_t *bar, uint64_t policy) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, "
+        "[%3], %4;" ::"r"(smem_u32(smem_dst)),
+        "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar)), "l"(policy)
+        : "memory");
+}
+__device__ __forceinline__ uint64_t l2_policy_evict_first() {
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ uint64_t ld_cg_u64(const uint64_t *p) {
+    uint64_t v;
+    asm volatile("ld.global.cg.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+}  // namespace waxvs

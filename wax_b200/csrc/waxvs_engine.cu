@@ -1,0 +1,913 @@
+// waxvs_engine.cu -- host side of libwaxvs_cuda.so: the engine object behind include/wax_vs_cuda.h.
+//
+// What it mirrors (all /root/reference paths): the state and behaviour of
+//   actor MetalVectorEngine            Sources/WaxVectorSearch/MetalVectorEngine.swift:17-893
+// with USearchVectorEngine's metric coverage (USearchVectorEngine.swift:44-67) -- the corpus matrix resident
+// on the device (here: HBM, row-major fp32), a frameIds side array, a pool of per-search scratch contexts
+// (the transient buffer pool, :84-121), upsert/ordered-remove mutation semantics (:330-444), the MV2V
+// encoding=2 blob (:682-815) -- re-designed for a discrete 180 GB GPU: id->row hash instead of the O(N)
+// firstIndex(of:) scan, explicit pinned staging, one fused kernel launch per query.
+//
+// There is NO CPU fallback in this file or anywhere in the product path: without a CUDA device every entry
+// point that needs one returns WAX_VS_ERR_CUDA.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <shared_mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/wax_vs_cuda.h"
+#include "waxvs_common.cuh"
+#include "waxvs_scan.cuh"
+#include "waxvs_select.cuh"
+#include "waxvs_synth.cuh"
+
+using namespace waxvs;
+
+// ---------------------------------------------------------------------------------------------------------
+// errors
+static thread_local char g_last_error[512] = "";
+
+static int32_t fail(int32_t code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof g_last_error, fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CUDA_TRY(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t _e = (expr);                                                                  \
+        if (_e != cudaSuccess)                                                                    \
+            return fail(WAX_VS_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(_e));         \
+    } while (0)
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { prev = -1; }
+        if (prev != dev) ok = (cudaSetDevice(dev) == cudaSuccess);
+    }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// id -> row: open addressing, linear probing.  Replaces frameIds.firstIndex(of:) (MetalVectorEngine.swift:334,385,426).
+struct IdMap {
+    std::vector<uint64_t> keys;
+    std::vector<uint32_t> vals;
+    size_t mask = 0, used = 0;
+    static uint64_t mix(uint64_t x) {
+        x ^= x >> 30; x *= 0xbf58476d1ce4e5b9ull; x ^= x >> 27; x *= 0x94d049bb133111ebull; x ^= x >> 31;
+        return x;
+    }
+    void reset(size_t expect) {
+        size_t cap = 64;
+        while (cap < expect * 2 + 16) cap <<= 1;
+        keys.assign(cap, 0);
+        vals.assign(cap, 0xFFFFFFFFu);
+        mask = cap - 1;
+        used = 0;
+    }
+    uint32_t find(uint64_t id) const {
+        if (vals.empty()) return 0xFFFFFFFFu;
+        for (size_t i = mix(id) & mask;; i = (i + 1) & mask) {
+            if (vals[i] == 0xFFFFFFFFu) return 0xFFFFFFFFu;
+            if (keys[i] == id) return vals[i];
+        }
+    }
+    void put(uint64_t id, uint32_t row) {
+        if (vals.empty() || (used + 1) * 2 > keys.size()) grow();
+        for (size_t i = mix(id) & mask;; i = (i + 1) & mask) {
+            if (vals[i] == 0xFFFFFFFFu) { keys[i] = id; vals[i] = row; ++used; return; }
+            if (keys[i] == id) { vals[i] = row; return; }
+        }
+    }
+    void grow() {
+        std::vector<uint64_t> ok; std::vector<uint32_t> ov;
+        ok.swap(keys); ov.swap(vals);
+        reset(std::max<size_t>(used * 2, 32));
+        for (size_t i = 0; i < ov.size(); ++i) if (ov[i] != 0xFFFFFFFFu) put(ok[i], ov[i]);
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------
+struct Tuning {
+    int variant = 0;      // 0 auto, 1 TMA-staged, 2 direct LDG
+    int rows_per_step = 0;  // 0 auto
+    int stages = 0;       // 0 auto
+    int warps = 0;        // 0 auto
+    int grid = 0;         // 0 = one CTA per SM
+    int l2_hint = 0;
+    int ldg_ctas_per_sm = 4;
+};
+
+// Per-search scratch: the analogue of TransientBuffers (MetalVectorEngine.swift:36-41, :84-117).
+struct SearchCtx {
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    float *d_queries = nullptr; size_t d_queries_cap = 0;        // floats
+    wax_vs_candidate *d_out = nullptr; size_t d_out_cap = 0;      // candidates
+    float *h_queries = nullptr; size_t h_queries_cap = 0;        // pinned
+    wax_vs_candidate *h_out = nullptr; size_t h_out_cap = 0;      // pinned
+    uint64_t *d_block_keys = nullptr; size_t block_keys_cap = 0;  // u64
+    uint32_t *d_ticket = nullptr;
+    uint32_t *d_dist_keys = nullptr; size_t dist_keys_cap = 0;    // large-k path
+    SelectState *d_select = nullptr;
+    uint64_t *d_sel_keys = nullptr;                               // 16384 u64
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+struct wax_vs_engine {
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 0;
+    uint32_t dims = 0;
+    uint8_t similarity = 0;
+
+    float *d_corpus = nullptr;
+    uint64_t cap_rows = 0, n_rows = 0;
+
+    // frame ids: implicit (id_base + row) after fill_synthetic until the first mutation, else explicit.
+    bool ids_identity = true;
+    uint64_t id_base = 0;
+    std::vector<uint64_t> ids;
+    IdMap map;
+    bool map_valid = true;
+    uint64_t *d_ids = nullptr; size_t d_ids_cap = 0; bool d_ids_dirty = true;
+    std::mutex ids_mu;
+
+    std::shared_mutex rw;  // readers: search / serialize; writer: mutators (AsyncReadWriteLock, :56-80)
+    std::mutex pool_mu;
+    std::vector<SearchCtx *> pool;
+    std::unordered_map<void *, SearchCtx *> stream_ctx;  // wax_vs_search_device: one ctx per caller stream
+    uint64_t pool_allocs = 0, pool_reuses = 0;
+    Tuning tune;
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// scratch contexts
+static void ctx_free(SearchCtx *c) {
+    if (!c) return;
+    if (c->d_queries) cudaFree(c->d_queries);
+    if (c->d_out) cudaFree(c->d_out);
+    if (c->h_queries) cudaFreeHost(c->h_queries);
+    if (c->h_out) cudaFreeHost(c->h_out);
+    if (c->d_block_keys) cudaFree(c->d_block_keys);
+    if (c->d_ticket) cudaFree(c->d_ticket);
+    if (c->d_dist_keys) cudaFree(c->d_dist_keys);
+    if (c->d_select) cudaFree(c->d_select);
+    if (c->d_sel_keys) cudaFree(c->d_sel_keys);
+    if (c->ev0) cudaEventDestroy(c->ev0);
+    if (c->ev1) cudaEventDestroy(c->ev1);
+    if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
+    delete c;
+}
+
+static int32_t ctx_new(wax_vs_engine *e, SearchCtx **out, bool with_stream) {
+    SearchCtx *c = new (std::nothrow) SearchCtx();
+    if (!c) return fail(WAX_VS_ERR_CUDA, "out of host memory");
+    auto bail = [&](int32_t rc) { ctx_free(c); return rc; };
+    if (with_stream) {
+        if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess)
+            return bail(fail(WAX_VS_ERR_CUDA, "cudaStreamCreate failed"));
+        c->own_stream = true;
+    }
+    c->block_keys_cap = static_cast<size_t>(std::max(e->sm_count * 8, 2048)) * 32;
+    if (cudaMalloc(&c->d_block_keys, c->block_keys_cap * sizeof(uint64_t)) != cudaSuccess ||
+        cudaMalloc(&c->d_ticket, sizeof(uint32_t)) != cudaSuccess ||
+        cudaMemset(c->d_ticket, 0, sizeof(uint32_t)) != cudaSuccess ||
+        cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
+        return bail(fail(WAX_VS_ERR_CUDA, "failed to allocate search scratch: %s",
+                         cudaGetErrorString(cudaGetLastError())));
+    *out = c;
+    return WAX_VS_OK;
+}
+
+static int32_t ctx_acquire(wax_vs_engine *e, SearchCtx **out) {
+    {
+        std::lock_guard<std::mutex> g(e->pool_mu);
+        if (!e->pool.empty()) {
+            *out = e->pool.back();
+            e->pool.pop_back();
+            ++e->pool_reuses;
+            return WAX_VS_OK;
+        }
+        ++e->pool_allocs;
+    }
+    return ctx_new(e, out, true);
+}
+static void ctx_release(wax_vs_engine *e, SearchCtx *c) {
+    std::lock_guard<std::mutex> g(e->pool_mu);
+    e->pool.push_back(c);
+}
+
+template <typename T>
+static int32_t ensure_dev(T **p, size_t *cap, size_t need, const char *what) {
+    if (need <= *cap) return WAX_VS_OK;
+    if (*p) { cudaFree(*p); *p = nullptr; *cap = 0; }
+    if (cudaMalloc(p, need * sizeof(T)) != cudaSuccess)
+        return fail(WAX_VS_ERR_CUDA, "failed to allocate %s (%zu bytes): %s", what, need * sizeof(T),
+                    cudaGetErrorString(cudaGetLastError()));
+    *cap = need;
+    return WAX_VS_OK;
+}
+template <typename T>
+static int32_t ensure_pinned(T **p, size_t *cap, size_t need, const char *what) {
+    if (need <= *cap) return WAX_VS_OK;
+    if (*p) { cudaFreeHost(*p); *p = nullptr; *cap = 0; }
+    if (cudaMallocHost(p, need * sizeof(T)) != cudaSuccess)
+        return fail(WAX_VS_ERR_CUDA, "failed to allocate pinned %s (%zu bytes): %s", what, need * sizeof(T),
+                    cudaGetErrorString(cudaGetLastError()));
+    *cap = need;
+    return WAX_VS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// kernel dispatch
+struct TmaConfig { int C, R, warps, stages; size_t smem; };
+
+static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
+    const uint32_t d = e->dims;
+    if (d % 128u != 0) return false;
+    const int C = static_cast<int>(d / 128u);
+    if (!(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 8)) return false;
+    const bool wide = (C >= 6);
+    int R = e->tune.rows_per_step ? e->tune.rows_per_step : (wide ? 2 : 4);
+    if (wide) { if (R != 2 && R != 4) R = 2; } else { if (R != 4 && R != 8) R = 4; }
+    int warps = e->tune.warps ? e->tune.warps : 8;
+    warps = std::max(1, std::min(16, warps));
+    const size_t budget = e->smem_optin ? e->smem_optin : 232448;
+    const size_t stage_bytes = static_cast<size_t>(R) * d * 4;
+    auto smem_for = [&](int st) { return static_cast<size_t>(warps) * st * (stage_bytes + 8) + static_cast<size_t>(warps) * 256; };
+    int stages = e->tune.stages;
+    if (stages <= 0) {
+        stages = 8;
+        while (stages > 2 && smem_for(stages) > budget) --stages;
+    }
+    if (stages < 1 || smem_for(stages) > budget) return false;
+    cfg->C = C; cfg->R = R; cfg->warps = warps; cfg->stages = stages; cfg->smem = smem_for(stages);
+    return true;
+}
+
+template <int C, int R, int M, bool E>
+static cudaError_t launch_tma_inst(const ScanParams &p, int grid, const TmaConfig &cfg, cudaStream_t s) {
+    cudaError_t err = cudaFuncSetAttribute(scan_tma_kernel<C, R, M, E>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
+    if (err != cudaSuccess) return err;
+    scan_tma_kernel<C, R, M, E><<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
+    return cudaGetLastError();
+}
+template <int C, int R>
+static cudaError_t launch_tma_cr(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, bool emit,
+                                 cudaStream_t s) {
+    switch (metric * 2 + (emit ? 1 : 0)) {
+        case 0: return launch_tma_inst<C, R, kCosine, false>(p, grid, cfg, s);
+        case 1: return launch_tma_inst<C, R, kCosine, true>(p, grid, cfg, s);
+        case 2: return launch_tma_inst<C, R, kDot, false>(p, grid, cfg, s);
+        case 3: return launch_tma_inst<C, R, kDot, true>(p, grid, cfg, s);
+        case 4: return launch_tma_inst<C, R, kL2, false>(p, grid, cfg, s);
+        default: return launch_tma_inst<C, R, kL2, true>(p, grid, cfg, s);
+    }
+}
+static cudaError_t launch_tma(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, bool emit,
+                              cudaStream_t s) {
+#define WAXVS_CASE(Cv, Rv) if (cfg.C == Cv && cfg.R == Rv) return launch_tma_cr<Cv, Rv>(p, grid, cfg, metric, emit, s)
+    WAXVS_CASE(1, 4); WAXVS_CASE(1, 8); WAXVS_CASE(2, 4); WAXVS_CASE(2, 8);
+    WAXVS_CASE(3, 4); WAXVS_CASE(3, 8); WAXVS_CASE(4, 4); WAXVS_CASE(4, 8);
+    WAXVS_CASE(6, 2); WAXVS_CASE(6, 4); WAXVS_CASE(8, 2); WAXVS_CASE(8, 4);
+#undef WAXVS_CASE
+    return cudaErrorInvalidValue;
+}
+static cudaError_t launch_ldg(const ScanParams &p, int grid, int metric, bool emit, cudaStream_t s) {
+    switch (metric * 2 + (emit ? 1 : 0)) {
+        case 0: scan_ldg_kernel<kCosine, false><<<grid, 256, 0, s>>>(p); break;
+        case 1: scan_ldg_kernel<kCosine, true><<<grid, 256, 0, s>>>(p); break;
+        case 2: scan_ldg_kernel<kDot, false><<<grid, 256, 0, s>>>(p); break;
+        case 3: scan_ldg_kernel<kDot, true><<<grid, 256, 0, s>>>(p); break;
+        case 4: scan_ldg_kernel<kL2, false><<<grid, 256, 0, s>>>(p); break;
+        default: scan_ldg_kernel<kL2, true><<<grid, 256, 0, s>>>(p); break;
+    }
+    return cudaGetLastError();
+}
+
+// Enqueue one query's scan + top-k on `stream`.  k_eff <= 10000.  Adds the number of kernels launched.
+static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_query, uint32_t k_eff,
+                              uint64_t row_offset, wax_vs_candidate *d_out, const uint64_t *d_ids,
+                              cudaStream_t stream, uint64_t *launches) {
+    if (e->n_rows == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out, 0, static_cast<size_t>(k_eff) * sizeof(wax_vs_candidate), stream));
+        return WAX_VS_OK;
+    }
+    ScanParams p{};
+    p.corpus = e->d_corpus; p.query = d_query;
+    p.n_rows = static_cast<uint32_t>(e->n_rows); p.dims = e->dims; p.k = k_eff;
+    p.block_keys = c->d_block_keys; p.ticket = c->d_ticket; p.out = d_out;
+    p.frame_ids = d_ids; p.id_base = e->id_base; p.row_offset = row_offset;
+    p.use_l2_hint = e->tune.l2_hint ? 1u : 0u;
+
+    const bool emit = k_eff > 32;
+    if (emit) {
+        int32_t rc = ensure_dev(&c->d_dist_keys, &c->dist_keys_cap, static_cast<size_t>(e->n_rows), "distance keys");
+        if (rc) return rc;
+        if (!c->d_select) CUDA_TRY(cudaMalloc(&c->d_select, sizeof(SelectState)));
+        if (!c->d_sel_keys) CUDA_TRY(cudaMalloc(&c->d_sel_keys, 16384 * sizeof(uint64_t)));
+        p.dist_keys = c->d_dist_keys;
+    }
+
+    TmaConfig cfg{};
+    bool use_tma = (e->tune.variant != 2) && pick_tma_config(e, &cfg);
+    if (e->tune.variant == 1 && !use_tma)
+        return fail(WAX_VS_ERR_UNSUPPORTED, "TMA-staged kernel does not support dims=%u", e->dims);
+    int grid;
+    const int grid_cap = static_cast<int>(c->block_keys_cap / 32);
+    if (use_tma) {
+        p.stages = static_cast<uint32_t>(cfg.stages);
+        const uint64_t steps = (e->n_rows + cfg.R - 1) / cfg.R;
+        const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count;
+        grid = static_cast<int>(std::min<uint64_t>(max_grid, (steps + cfg.warps - 1) / cfg.warps));
+        grid = std::max(std::min(grid, grid_cap), 1);
+        CUDA_TRY(launch_tma(p, grid, cfg, e->similarity, emit, stream));
+    } else {
+        const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count * e->tune.ldg_ctas_per_sm;
+        grid = static_cast<int>(std::min<uint64_t>(max_grid, (e->n_rows + 7) / 8));
+        grid = std::max(std::min(grid, grid_cap), 1);
+        CUDA_TRY(launch_ldg(p, grid, e->similarity, emit, stream));
+    }
+    ++*launches;
+
+    if (emit) {
+        const uint32_t n = static_cast<uint32_t>(e->n_rows);
+        const int sgrid = std::max(1, std::min<int>(e->sm_count * 4, static_cast<int>((n + 511) / 512)));
+        select_init_kernel<<<1, 256, 0, stream>>>(c->d_select, k_eff);
+        for (int pass = 0; pass < kSelectPasses; ++pass) {
+            select_hist_kernel<<<sgrid, 512, 0, stream>>>(c->d_dist_keys, n, c->d_select, pass);
+            select_scan_kernel<<<1, 1024, 0, stream>>>(c->d_select, pass);
+        }
+        select_compact_kernel<<<sgrid, 512, 0, stream>>>(c->d_dist_keys, n, c->d_select, c->d_sel_keys, 16384);
+        uint32_t pow2 = 64;
+        while (pow2 < k_eff) pow2 <<= 1;
+        static bool sort_attr = false;
+        if (!sort_attr) {
+            CUDA_TRY(cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+            sort_attr = true;
+        }
+        select_sort_kernel<<<1, 1024, pow2 * sizeof(uint64_t), stream>>>(c->d_select, c->d_sel_keys, pow2, p);
+        CUDA_TRY(cudaGetLastError());
+        *launches += 3 + 2 * kSelectPasses;
+    }
+    return WAX_VS_OK;
+}
+
+static uint32_t clamp_topk(int64_t k) {  // MetalVectorEngine.swift:842-846
+    if (k < 1) return 1;
+    if (k > WAX_VS_MAX_RESULTS) return WAX_VS_MAX_RESULTS;
+    return static_cast<uint32_t>(k);
+}
+
+// VectorMetric.score(fromDistance:) (VectorMetric.swift:32-43)
+static float score_from_distance(uint8_t sim, float d) {
+    if (!finite_f32(d)) return 0.0f;
+    return sim == WAX_VS_COSINE ? 1.0f - d : -d;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// corpus storage
+static int32_t set_capacity(wax_vs_engine *e, uint64_t rows) {
+    if (rows <= e->cap_rows) return WAX_VS_OK;
+    float *n = nullptr;
+    const size_t bytes = static_cast<size_t>(rows) * e->dims * sizeof(float);
+    if (cudaMalloc(&n, bytes) != cudaSuccess)
+        return fail(WAX_VS_ERR_CUDA, "Failed to resize vectors buffer (%zu bytes): %s", bytes,
+                    cudaGetErrorString(cudaGetLastError()));
+    if (e->n_rows) {
+        cudaError_t err = cudaMemcpy(n, e->d_corpus, static_cast<size_t>(e->n_rows) * e->dims * sizeof(float),
+                                     cudaMemcpyDeviceToDevice);
+        if (err != cudaSuccess) { cudaFree(n); return fail(WAX_VS_ERR_CUDA, "corpus copy failed: %s", cudaGetErrorString(err)); }
+    }
+    if (e->d_corpus) cudaFree(e->d_corpus);
+    e->d_corpus = n;
+    e->cap_rows = rows;
+    return WAX_VS_OK;
+}
+
+// reserveIfNeeded (MetalVectorEngine.swift:857-871): doubling from 64.
+static int32_t grow_for(wax_vs_engine *e, uint64_t required) {
+    if (required > 0xFFFFFFFFull)
+        return fail(WAX_VS_ERR_CAPACITY, "capacity exceeded: limit %llu, requested %llu", 0xFFFFFFFFull,
+                    static_cast<unsigned long long>(required));
+    if (required <= e->cap_rows) return WAX_VS_OK;
+    uint64_t next = e->cap_rows ? e->cap_rows : 64;
+    while (next < required) next = std::min<uint64_t>(next * 2, 0xFFFFFFFFull);
+    return set_capacity(e, next);
+}
+
+static void materialize_ids(wax_vs_engine *e) {
+    if (!e->ids_identity) return;
+    e->ids.resize(e->n_rows);
+    for (uint64_t r = 0; r < e->n_rows; ++r) e->ids[r] = e->id_base + r;
+    e->ids_identity = false;
+    e->map_valid = false;
+    e->d_ids_dirty = true;
+}
+static void ensure_map(wax_vs_engine *e) {
+    if (e->map_valid) return;
+    e->map.reset(e->ids.size());
+    for (size_t r = 0; r < e->ids.size(); ++r) e->map.put(e->ids[r], static_cast<uint32_t>(r));
+    e->map_valid = true;
+}
+static int32_t sync_device_ids(wax_vs_engine *e, const uint64_t **out) {
+    std::lock_guard<std::mutex> g(e->ids_mu);
+    if (e->ids_identity) { *out = nullptr; return WAX_VS_OK; }
+    if (e->d_ids_dirty) {
+        int32_t rc = ensure_dev(&e->d_ids, &e->d_ids_cap, std::max<size_t>(e->ids.size(), 1), "frame ids");
+        if (rc) return rc;
+        if (!e->ids.empty())
+            CUDA_TRY(cudaMemcpy(e->d_ids, e->ids.data(), e->ids.size() * sizeof(uint64_t), cudaMemcpyHostToDevice));
+        e->d_ids_dirty = false;
+    }
+    *out = e->d_ids;
+    return WAX_VS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// C-ABI
+extern "C" {
+
+const char *wax_vs_last_error(void) { return g_last_error; }
+const char *wax_vs_version(void) { return "waxvs_cuda 0.1 sm_100a (fused scan+top-k; TMA bulk staging)"; }
+
+int32_t wax_vs_device_count(int32_t *out) {
+    if (!out) return fail(WAX_VS_ERR_NULL, "out is NULL");
+    int n = 0;
+    cudaError_t err = cudaGetDeviceCount(&n);
+    if (err != cudaSuccess) { *out = 0; cudaGetLastError(); return fail(WAX_VS_ERR_CUDA, "CUDA device not available: %s", cudaGetErrorString(err)); }
+    *out = n;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_create(uint32_t dimensions, uint8_t similarity, const int32_t *devices, int32_t n_devices,
+                      wax_vs_engine **out) {
+    if (!out) return fail(WAX_VS_ERR_NULL, "out is NULL");
+    *out = nullptr;
+    if (dimensions == 0) return fail(WAX_VS_ERR_ARGUMENT, "dimensions must be > 0");  // :154-156
+    if (dimensions > WAX_VS_MAX_DIMENSIONS)                                           // :157-162
+        return fail(WAX_VS_ERR_CAPACITY, "capacity exceeded: limit %d, requested %u", WAX_VS_MAX_DIMENSIONS, dimensions);
+    if (similarity > 2) return fail(WAX_VS_ERR_ARGUMENT, "vec similarity must be 0..2 (got %u)", similarity);
+    if (n_devices > 1)
+        return fail(WAX_VS_ERR_UNSUPPORTED, "one engine drives one device; shard with one engine per rank (wax_vs_search_device)");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) {
+        cudaGetLastError();
+        return fail(WAX_VS_ERR_CUDA, "CUDA device not available");  // "Metal device not available" :167-169
+    }
+    int dev = 0;
+    if (devices && n_devices == 1) dev = devices[0];
+    else if (cudaGetDevice(&dev) != cudaSuccess) dev = 0;
+    if (dev < 0 || dev >= count) return fail(WAX_VS_ERR_ARGUMENT, "device ordinal %d out of range (0..%d)", dev, count - 1);
+
+    wax_vs_engine *e = new (std::nothrow) wax_vs_engine();
+    if (!e) return fail(WAX_VS_ERR_CUDA, "out of host memory");
+    e->device = dev; e->dims = dimensions; e->similarity = similarity;
+    DeviceGuard g(dev);
+    int v = 0;
+    if (!g.ok || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+        delete e;
+        return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", dev);
+    }
+    e->sm_count = v;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) == cudaSuccess) e->smem_optin = static_cast<size_t>(v);
+    int32_t rc = set_capacity(e, 64);  // initialReserve (:19, :225-229)
+    if (rc) { delete e; return rc; }
+    *out = e;
+    return WAX_VS_OK;
+}
+
+void wax_vs_destroy(wax_vs_engine *e) {
+    if (!e) return;
+    {
+        std::unique_lock<std::shared_mutex> w(e->rw);
+        DeviceGuard g(e->device);
+        cudaDeviceSynchronize();
+        for (SearchCtx *c : e->pool) ctx_free(c);
+        for (auto &kv : e->stream_ctx) ctx_free(kv.second);
+        if (e->d_corpus) cudaFree(e->d_corpus);
+        if (e->d_ids) cudaFree(e->d_ids);
+    }
+    delete e;
+}
+
+int32_t wax_vs_dimensions(const wax_vs_engine *e, uint32_t *out) {
+    if (!e || !out) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    *out = e->dims;
+    return WAX_VS_OK;
+}
+int32_t wax_vs_similarity(const wax_vs_engine *e, uint8_t *out) {
+    if (!e || !out) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    *out = e->similarity;
+    return WAX_VS_OK;
+}
+int32_t wax_vs_count(wax_vs_engine *e, uint64_t *out) {
+    if (!e || !out) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    *out = e->n_rows;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_reserve(wax_vs_engine *e, uint64_t rows) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    if (rows > 0xFFFFFFFFull)
+        return fail(WAX_VS_ERR_CAPACITY, "capacity exceeded: limit %llu, requested %llu", 0xFFFFFFFFull,
+                    static_cast<unsigned long long>(rows));
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    return set_capacity(e, rows);
+}
+
+int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const float *rows, uint64_t n,
+                         uint32_t vector_len) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    if (n == 0) return WAX_VS_OK;  // guard !frameIds.isEmpty (:360)
+    if (!frame_ids || !rows) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (vector_len != e->dims)     // :367-370
+        return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, vector_len);
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    int32_t rc = grow_for(e, e->n_rows + n);  // maxNewCount (:379-380)
+    if (rc) return rc;
+    materialize_ids(e);
+    ensure_map(e);
+
+    // Resolve the destination row of every batch item in order (the sequential loop at :384-398).
+    std::vector<uint32_t> target(n);
+    const uint64_t n0 = e->n_rows;
+    bool pure_append = true;
+    for (uint64_t i = 0; i < n; ++i) {
+        uint32_t row = e->map.find(frame_ids[i]);
+        if (row == 0xFFFFFFFFu) {
+            row = static_cast<uint32_t>(e->n_rows);
+            e->ids.push_back(frame_ids[i]);
+            e->map.put(frame_ids[i], row);
+            ++e->n_rows;
+        }
+        target[i] = row;
+        if (row != n0 + i) pure_append = false;
+    }
+    e->d_ids_dirty = true;
+    const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
+    if (pure_append) {
+        CUDA_TRY(cudaMemcpy(e->d_corpus + n0 * e->dims, rows, n * row_bytes, cudaMemcpyHostToDevice));
+        return WAX_VS_OK;
+    }
+    // Overwrites present: a later item for the same row wins; earlier ones are dropped.
+    {
+        std::unordered_map<uint32_t, uint64_t> last;
+        last.reserve(n * 2);
+        for (uint64_t i = 0; i < n; ++i) last[target[i]] = i;
+        for (uint64_t i = 0; i < n; ++i) if (last[target[i]] != i) target[i] = 0xFFFFFFFFu;
+    }
+    float *d_stage = nullptr; uint32_t *d_target = nullptr;
+    if (cudaMalloc(&d_stage, n * row_bytes) != cudaSuccess || cudaMalloc(&d_target, n * sizeof(uint32_t)) != cudaSuccess) {
+        if (d_stage) cudaFree(d_stage);
+        return fail(WAX_VS_ERR_CUDA, "failed to allocate upsert staging: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    cudaError_t err = cudaMemcpy(d_stage, rows, n * row_bytes, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(d_target, target.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) {
+        scatter_rows_kernel<<<static_cast<unsigned>(n), 256>>>(e->d_corpus, d_stage, d_target, n, e->dims);
+        err = cudaGetLastError();
+        if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    }
+    cudaFree(d_stage); cudaFree(d_target);
+    if (err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "upsert failed: %s", cudaGetErrorString(err));
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_add(wax_vs_engine *e, uint64_t frame_id, const float *vector, uint32_t vector_len) {
+    return wax_vs_add_batch(e, &frame_id, vector, 1, vector_len);
+}
+
+int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    if (e->n_rows == 0) return WAX_VS_OK;  // :425
+    uint64_t index;
+    if (e->ids_identity) {
+        if (frame_id < e->id_base || frame_id - e->id_base >= e->n_rows) return WAX_VS_OK;
+        index = frame_id - e->id_base;
+        materialize_ids(e);
+    } else {
+        ensure_map(e);
+        const uint32_t r = e->map.find(frame_id);
+        if (r == 0xFFFFFFFFu) return WAX_VS_OK;  // :426
+        index = r;
+    }
+    DeviceGuard g(e->device);
+    const uint64_t after = e->n_rows - 1 - index;  // countAfter (:431)
+    if (after > 0) {
+        // memmove of the tail (:433-437) through a bounce buffer, ascending chunks (dst < src).
+        const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
+        const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(after, (256ull << 20) / row_bytes));
+        float *bounce = nullptr;
+        CUDA_TRY(cudaMalloc(&bounce, chunk_rows * row_bytes));
+        cudaError_t err = cudaSuccess;
+        for (uint64_t done = 0; done < after && err == cudaSuccess; done += chunk_rows) {
+            const uint64_t m = std::min(chunk_rows, after - done);
+            err = cudaMemcpy(bounce, e->d_corpus + (index + 1 + done) * e->dims, m * row_bytes, cudaMemcpyDeviceToDevice);
+            if (err == cudaSuccess)
+                err = cudaMemcpy(e->d_corpus + (index + done) * e->dims, bounce, m * row_bytes, cudaMemcpyDeviceToDevice);
+        }
+        cudaFree(bounce);
+        if (err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "remove failed: %s", cudaGetErrorString(err));
+    }
+    e->ids.erase(e->ids.begin() + static_cast<std::ptrdiff_t>(index));  // :440
+    --e->n_rows;
+    e->map_valid = false;
+    e->d_ids_dirty = true;
+    return WAX_VS_OK;
+}
+
+// ---- search ---------------------------------------------------------------------------------------------------
+static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_queries, uint32_t query_len,
+                           int64_t top_k, uint64_t *out_ids, float *out_scores, uint32_t out_stride,
+                           uint32_t *out_n) {
+    if (!e || !out_n) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    if (e->n_rows == 0) {  // guard vectorCount > 0 else { return [] } (:448) -- before validation, as the reference
+        for (uint32_t i = 0; i < n_queries; ++i) out_n[i] = 0;
+        return WAX_VS_OK;
+    }
+    if (n_queries == 0) return WAX_VS_OK;
+    if (!queries) return fail(WAX_VS_ERR_NULL, "query is NULL");
+    if (query_len != e->dims)  // validate (:449, :830-833)
+        return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, query_len);
+    const uint32_t limit = clamp_topk(top_k);
+    const uint32_t k_eff = static_cast<uint32_t>(std::min<uint64_t>(limit, e->n_rows));  // topKCount (:451)
+    if (!out_ids || !out_scores) return fail(WAX_VS_ERR_NULL, "output buffer is NULL");
+    if (out_stride < k_eff)
+        return fail(WAX_VS_ERR_BUFFER, "output buffers hold %u entries, need %u", out_stride, k_eff);
+
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_acquire(e, &c);
+    if (rc) return rc;
+    struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); } } rel{e, c};
+
+    const size_t qfloats = static_cast<size_t>(n_queries) * e->dims;
+    const size_t ncand = static_cast<size_t>(n_queries) * k_eff;
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, qfloats, "query buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, qfloats, "query staging"))) return rc;
+    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, ncand, "result buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_out, &c->h_out_cap, ncand, "result staging"))) return rc;
+
+    memcpy(c->h_queries, queries, qfloats * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    uint64_t launches = 0;
+    for (uint32_t qi = 0; qi < n_queries; ++qi) {
+        rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
+                            c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, ncand * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+
+    // row -> frameId and distance -> score on the host, as MetalVectorEngine.swift:595-603 does.
+    for (uint32_t qi = 0; qi < n_queries; ++qi) {
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < k_eff; ++i) {
+            const wax_vs_candidate &cd = c->h_out[static_cast<size_t>(qi) * k_eff + i];
+            if (!cd.valid) continue;
+            const uint64_t row = cd.row;
+            out_ids[static_cast<size_t>(qi) * out_stride + m] = e->ids_identity ? e->id_base + row : e->ids[row];
+            out_scores[static_cast<size_t>(qi) * out_stride + m] = score_from_distance(e->similarity, cd.distance);
+            ++m;
+        }
+        out_n[qi] = m;
+    }
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_search(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k,
+                      uint64_t *out_ids, float *out_scores, uint32_t out_cap, uint32_t *out_n) {
+    return search_host(e, query, 1, query_len, top_k, out_ids, out_scores, out_cap, out_n);
+}
+
+int32_t wax_vs_search_batch(wax_vs_engine *e, const float *queries, uint32_t n_queries, uint32_t query_len,
+                            int64_t top_k, uint64_t *out_ids, float *out_scores, uint32_t out_stride,
+                            uint32_t *out_n) {
+    return search_host(e, queries, n_queries, query_len, top_k, out_ids, out_scores, out_stride, out_n);
+}
+
+int32_t wax_vs_search_device(wax_vs_engine *e, const float *d_queries, uint32_t n_queries, int64_t top_k,
+                             uint64_t row_offset, wax_vs_candidate *d_candidates, void *cuda_stream) {
+    if (!e || !d_queries || !d_candidates) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    const uint32_t k_eff = clamp_topk(top_k);
+    SearchCtx *c = nullptr;
+    {
+        std::lock_guard<std::mutex> pg(e->pool_mu);
+        auto it = e->stream_ctx.find(cuda_stream);
+        if (it != e->stream_ctx.end()) c = it->second;
+    }
+    if (!c) {
+        int32_t rc = ctx_new(e, &c, false);
+        if (rc) return rc;
+        c->stream = static_cast<cudaStream_t>(cuda_stream);
+        std::lock_guard<std::mutex> pg(e->pool_mu);
+        e->stream_ctx[cuda_stream] = c;
+        ++e->pool_allocs;
+    }
+    const uint64_t *d_ids = nullptr;
+    int32_t rc = sync_device_ids(e, &d_ids);
+    if (rc) return rc;
+    uint64_t launches = 0;
+    for (uint32_t qi = 0; qi < n_queries; ++qi) {
+        rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
+                            d_candidates + static_cast<size_t>(qi) * k_eff, d_ids,
+                            static_cast<cudaStream_t>(cuda_stream), &launches);
+        if (rc) return rc;
+    }
+    return WAX_VS_OK;
+}
+
+// ---- persistence ---------------------------------------------------------------------------------------------
+static uint64_t mv2v_length(const wax_vs_engine *e) {
+    return 36ull + e->n_rows * e->dims * 4ull + 8ull + e->n_rows * 8ull;
+}
+
+int32_t wax_vs_serialized_length(wax_vs_engine *e, uint64_t *out) {
+    if (!e || !out) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    *out = mv2v_length(e);
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_serialize(wax_vs_engine *e, uint8_t *dst, uint64_t cap, uint64_t *out_len) {
+    if (!e || !dst) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    const uint64_t need = mv2v_length(e);
+    if (out_len) *out_len = need;
+    if (cap < need) return fail(WAX_VS_ERR_BUFFER, "serialize needs %llu bytes, buffer has %llu",
+                                static_cast<unsigned long long>(need), static_cast<unsigned long long>(cap));
+    DeviceGuard g(e->device);
+    uint8_t *p = dst;
+    const uint8_t magic[4] = {0x4D, 0x56, 0x32, 0x56};  // "MV2V" (:686)
+    memcpy(p, magic, 4); p += 4;
+    const uint16_t version = 1; memcpy(p, &version, 2); p += 2;  // :687-688
+    *p++ = 2;                                                     // encoding (:689)
+    *p++ = e->similarity;                                         // :690
+    memcpy(p, &e->dims, 4); p += 4;                               // :691-692
+    memcpy(p, &e->n_rows, 8); p += 8;                             // :693-694
+    const uint64_t vbytes = e->n_rows * e->dims * 4ull;
+    memcpy(p, &vbytes, 8); p += 8;                                // :697-699
+    memset(p, 0, 8); p += 8;                                      // reserved (:700)
+    if (vbytes) CUDA_TRY(cudaMemcpy(p, e->d_corpus, vbytes, cudaMemcpyDeviceToHost));  // :703-705
+    p += vbytes;
+    const uint64_t ibytes = e->n_rows * 8ull;
+    memcpy(p, &ibytes, 8); p += 8;                                // :707-709
+    if (e->ids_identity) {
+        for (uint64_t i = 0; i < e->n_rows; ++i) { const uint64_t id = e->id_base + i; memcpy(p + i * 8, &id, 8); }
+    } else if (ibytes) {
+        memcpy(p, e->ids.data(), ibytes);                         // :710
+    }
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_deserialize(wax_vs_engine *e, const uint8_t *src, uint64_t len) {
+    if (!e || !src) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    // Reason strings follow MetalVectorEngine.deserialize (:716-815) / VectorSerializer.decodeVecSegment (:84-157).
+    if (len < 36) return fail(WAX_VS_ERR_FORMAT, "Metal segment too small: %llu bytes", static_cast<unsigned long long>(len));
+    const uint8_t magic[4] = {0x4D, 0x56, 0x32, 0x56};
+    if (memcmp(src, magic, 4) != 0) return fail(WAX_VS_ERR_FORMAT, "Metal segment magic mismatch");
+    uint16_t version; memcpy(&version, src + 4, 2);
+    if (version != 1) return fail(WAX_VS_ERR_FORMAT, "Unsupported Metal segment version %u", version);
+    if (src[6] != 2) return fail(WAX_VS_ERR_FORMAT, "Unsupported Metal segment encoding %u", src[6]);
+    if (src[7] > 2 || src[7] != e->similarity)
+        return fail(WAX_VS_ERR_FORMAT, "Metric mismatch: expected %u, got %u", e->similarity, src[7]);
+    uint32_t dims; memcpy(&dims, src + 8, 4);
+    if (dims != e->dims) return fail(WAX_VS_ERR_FORMAT, "Dimension mismatch: expected %u, got %u", e->dims, dims);
+    uint64_t count, vbytes; memcpy(&count, src + 12, 8); memcpy(&vbytes, src + 20, 8);
+    for (int i = 0; i < 8; ++i)
+        if (src[28 + i] != 0) return fail(WAX_VS_ERR_FORMAT, "Metal segment reserved bytes must be zero");
+    if (count > 0xFFFFFFFFull) return fail(WAX_VS_ERR_CAPACITY, "capacity exceeded: limit %llu, requested %llu", 0xFFFFFFFFull, static_cast<unsigned long long>(count));
+    if (vbytes != count * static_cast<uint64_t>(dims) * 4ull) return fail(WAX_VS_ERR_FORMAT, "Vector data length mismatch");
+    if (len < 36 + vbytes + 8) return fail(WAX_VS_ERR_FORMAT, "Metal segment missing frameId length");
+    uint64_t ibytes; memcpy(&ibytes, src + 36 + vbytes, 8);
+    if (ibytes != count * 8ull) return fail(WAX_VS_ERR_FORMAT, "FrameId data length mismatch");
+    if (len != 36 + vbytes + 8 + ibytes)
+        return fail(WAX_VS_ERR_FORMAT, "vec segment length mismatch: expected %llu, got %llu",
+                    static_cast<unsigned long long>(36 + vbytes + 8 + ibytes), static_cast<unsigned long long>(len));
+    DeviceGuard g(e->device);
+    int32_t rc = set_capacity(e, std::max<uint64_t>(count, 64));  // reservedCapacity = max(...) (:791-792)
+    if (rc) return rc;
+    if (vbytes) CUDA_TRY(cudaMemcpy(e->d_corpus, src + 36, vbytes, cudaMemcpyHostToDevice));  // :794-799
+    e->n_rows = count;
+    e->ids.resize(count);
+    if (count) memcpy(e->ids.data(), src + 36 + vbytes + 8, ibytes);  // :809-811
+    e->ids_identity = false;
+    e->map_valid = false;
+    e->d_ids_dirty = true;
+    return WAX_VS_OK;
+}
+
+// ---- instrumentation ------------------------------------------------------------------------------------------
+int32_t wax_vs_debug_pool_stats(wax_vs_engine *e, uint64_t *allocations, uint64_t *reuses) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    std::lock_guard<std::mutex> g(e->pool_mu);
+    if (allocations) *allocations = e->pool_allocs;
+    if (reuses) *reuses = e->pool_reuses;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_debug_fill_synthetic(wax_vs_engine *e, uint64_t seed, uint64_t first_row, uint64_t rows,
+                                    uint64_t id_base, int32_t normalize) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    if (rows > 0xFFFFFFFFull) return fail(WAX_VS_ERR_CAPACITY, "capacity exceeded: limit %llu, requested %llu", 0xFFFFFFFFull, static_cast<unsigned long long>(rows));
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    e->n_rows = 0;
+    int32_t rc = set_capacity(e, std::max<uint64_t>(rows, 64));
+    if (rc) return rc;
+    if (rows) {
+        const unsigned blocks = static_cast<unsigned>((rows + 255) / 256);
+        synth_fill_kernel<<<blocks, 256>>>(e->d_corpus, rows, e->dims, seed, first_row, normalize);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaDeviceSynchronize());
+    }
+    e->n_rows = rows;
+    e->ids.clear(); e->ids.shrink_to_fit();
+    e->ids_identity = true; e->id_base = id_base;
+    e->map = IdMap(); e->map_valid = true;
+    e->d_ids_dirty = true;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_debug_read_rows(wax_vs_engine *e, uint64_t first, uint64_t n, float *dst) {
+    if (!e || !dst) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    if (first + n > e->n_rows) return fail(WAX_VS_ERR_ARGUMENT, "row range out of bounds");
+    DeviceGuard g(e->device);
+    if (n) CUDA_TRY(cudaMemcpy(dst, e->d_corpus + first * e->dims, n * e->dims * sizeof(float), cudaMemcpyDeviceToHost));
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_debug_time_search(wax_vs_engine *e, uint32_t n_queries, int64_t top_k, uint64_t seed,
+                                 uint32_t warmup, uint32_t iters, float *out_ms_total, uint64_t *out_launches) {
+    if (!e || !out_ms_total) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (n_queries == 0) n_queries = 1;
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    DeviceGuard g(e->device);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_acquire(e, &c);
+    if (rc) return rc;
+    struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); } } rel{e, c};
+    const uint32_t k_eff = clamp_topk(top_k);
+    const size_t qfloats = static_cast<size_t>(n_queries) * e->dims;
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, qfloats, "query buffer"))) return rc;
+    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, static_cast<size_t>(n_queries) * k_eff, "result buffer"))) return rc;
+    // n_queries distinct unit queries (generator stream `seed`); step i searches query i mod n_queries.
+    synth_fill_kernel<<<(n_queries + 255) / 256, 256, 0, c->stream>>>(c->d_queries, n_queries, e->dims, seed, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    uint64_t launches = 0;
+    for (uint32_t it = 0; it < warmup + iters; ++it) {
+        if (it == warmup) { launches = 0; CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); }
+        const uint32_t qi = it % n_queries;
+        rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
+                            c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(out_ms_total, c->ev0, c->ev1));
+    if (out_launches) *out_launches = launches;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value) {
+    if (!e || !key) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    const int v = static_cast<int>(value);
+    if (!strcmp(key, "variant")) e->tune.variant = v;
+    else if (!strcmp(key, "rows_per_step")) e->tune.rows_per_step = v;
+    else if (!strcmp(key, "stages")) e->tune.stages = v;
+    else if (!strcmp(key, "warps")) e->tune.warps = v;
+    else if (!strcmp(key, "grid")) e->tune.grid = v;
+    else if (!strcmp(key, "l2_hint")) e->tune.l2_hint = v;
+    else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
+    else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);
+    return WAX_VS_OK;
+}
+
+}  // extern "C"

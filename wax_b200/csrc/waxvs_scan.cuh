@@ -1,0 +1,304 @@
+// waxvs_scan.cuh -- the fused single-pass scan: query L2-norm + distance + top-k in ONE launch.
+//
+// Replaces, for the CUDA engine, the reference's two-dispatch pipeline
+//   cosineDistanceKernelSIMD8/SIMD4  (Shaders/CosineDistance.metal:233-328, :152-229)  -> N*4 B distances
+//   topKReduceDistances/Entries loop (Shaders/TopKReduction.metal:103-167; MetalVectorEngine.swift:511-575)
+// and the host-side query normalisation (VectorSearchSession.swift:70-76).  The corpus is the only HBM
+// stream: no distance array, no second pass.
+//
+// Data layout: corpus row-major [n_rows][dims] fp32 in HBM (as MetalVectorEngine.swift:134,345-349).
+//
+// Work split (HBM-bound, ~1 flop/byte -- deliberately NOT a GEMM):
+//   * persistent grid, one CTA per SM; every warp owns a private ring of `stages` shared-memory tiles of
+//     R rows and streams "steps" (R consecutive rows = R*dims*4 contiguous bytes) with 1-D TMA bulk copies
+//     (cp.async.bulk -> SASS UBLKCP) completing on the warp's own mbarriers -- no block-wide barrier in
+//     the main loop, (stages-1)*R*dims*4 bytes in flight per warp;
+//   * a lane reads its 16-byte chunks (lane + 32c) of a row with conflict-free LDS.128, FMAs them against
+//     the query chunks it keeps in registers into 4 accumulators per quantity (element i -> accumulator
+//     i mod 128: the order oracle ACC_F32_TREE mirrors, so results are bit-exact against it);
+//   * R rows are reduced together with a shuffle reduce-scatter (warp_reduce_scatter) and finished by the
+//     lane that owns the row (IEEE sqrt/div, USearch zero-norm rules);
+//   * each warp keeps a sorted k<=32 list in registers; a row is compared against the list's k-th key
+//     (one 64-bit compare) and inserted by shuffles only when it wins (rare after warm-up);
+//   * per-CTA merge in shared memory, per-grid merge by the last CTA to finish (atomic ticket): still the
+//     same launch.
+#pragma once
+#include "waxvs_common.cuh"
+#include "../../include/wax_vs_cuda.h"
+
+namespace waxvs {
+
+struct ScanParams {
+    const float *corpus;        // [n_rows][dims]
+    const float *query;         // [dims]
+    uint32_t n_rows;
+    uint32_t dims;
+    uint32_t k;                 // entries to produce (<= 32 for the fused list kernels)
+    uint32_t stages;            // ring depth per warp (TMA kernels)
+    uint64_t *block_keys;       // [grid][32] scratch
+    uint32_t *ticket;           // zero on entry, zero again on exit
+    wax_vs_candidate *out;      // [k] results, best first
+    uint32_t *dist_keys;        // emit mode: [n_rows] orderable distance keys (WAXVS_UKEY_NONE = dropped)
+    const uint64_t *frame_ids;  // device ids or nullptr (then id = id_base + row)
+    uint64_t id_base;
+    uint64_t row_offset;        // added to the reported row (shard offset)
+    uint32_t use_l2_hint;       // 1: evict-first policy on the corpus stream
+};
+
+__device__ __forceinline__ void write_candidate(const ScanParams &p, int slot, uint64_t key) {
+    wax_vs_candidate c;
+    if (key == WAXVS_KEY_NONE) {
+        c.distance = 0.0f; c.valid = 0; c.row = 0; c.frame_id = 0;
+    } else {
+        const uint32_t row = static_cast<uint32_t>(key);
+        c.distance = from_orderable_u32(static_cast<uint32_t>(key >> 32));
+        c.valid = 1;
+        c.row = p.row_offset + row;
+        c.frame_id = p.frame_ids ? p.frame_ids[row] : p.id_base + row;
+    }
+    p.out[slot] = c;
+}
+
+// CTA merge + grid merge + output.  Called by every thread of the CTA after the scan loop.
+// lists: shared [warps][32] u64.
+__device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK &tk, uint64_t *lists, int warp,
+                                            int lane, int warps) {
+    const int k = static_cast<int>(p.k);
+    __shared__ uint32_t s_last;
+    lists[warp * 32 + lane] = tk.key;
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < warps; ++w) tk.merge_sorted(lists[w * 32 + lane], lane, k);
+        p.block_keys[static_cast<size_t>(blockIdx.x) * 32 + lane] = tk.key;
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    tk.init();
+    for (uint32_t b = warp; b < gridDim.x; b += warps)
+        tk.merge_sorted(ld_cg_u64(p.block_keys + static_cast<size_t>(b) * 32 + lane), lane, k);
+    __syncthreads();  // everyone is done reading lists from the CTA merge
+    lists[warp * 32 + lane] = tk.key;
+    __syncthreads();
+    if (warp == 0) {
+        for (int w = 1; w < warps; ++w) tk.merge_sorted(lists[w * 32 + lane], lane, k);
+        if (lane < k) write_candidate(p, lane, tk.key);
+        if (lane == 0) *p.ticket = 0u;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// TMA-staged kernel for dims == 128*C.
+//   R      rows per step (power of two)
+//   EMIT   false: fused top-k (k <= 32);  true: write orderable distance keys for the large-k select path
+template <int C, int R, int METRIC, bool EMIT>
+__global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
+    constexpr int D4 = 32 * C;  // float4 per row
+    constexpr uint32_t ROW_BYTES = 512u * C;
+    constexpr uint32_t STAGE_BYTES = ROW_BYTES * R;
+    constexpr int LANES_PER_ROW = 32 / R;
+
+    extern __shared__ __align__(128) unsigned char smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const uint32_t stages = p.stages;
+    unsigned char *ring = smem + static_cast<size_t>(warp) * stages * STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(warps) * stages * STAGE_BYTES) +
+                     warp * stages;
+    uint64_t *lists = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(warps) * stages * STAGE_BYTES) +
+                      warps * stages;
+
+    // ---- query chunks in registers + fused |q|^2 (the in-kernel L2 normalisation of the query) ----
+    float4 q[C];
+    const float4 *q4 = reinterpret_cast<const float4 *>(p.query);
+#pragma unroll
+    for (int c = 0; c < C; ++c) q[c] = __ldg(q4 + lane + 32 * c);
+    float a2 = 0.0f, sqrt_a2 = 0.0f;
+    if (METRIC == kCosine) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            s0 = __fmaf_rn(q[c].x, q[c].x, s0); s1 = __fmaf_rn(q[c].y, q[c].y, s1);
+            s2 = __fmaf_rn(q[c].z, q[c].z, s2); s3 = __fmaf_rn(q[c].w, q[c].w, s3);
+        }
+        a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
+        sqrt_a2 = __fsqrt_rn(a2);
+    }
+
+    const uint32_t total_warps = gridDim.x * warps;
+    const uint32_t gwarp = blockIdx.x * warps + warp;
+    const uint32_t n_steps = (p.n_rows + R - 1) / R;
+    uint64_t policy = 0;
+    if (p.use_l2_hint) policy = l2_policy_evict_first();
+
+    auto issue = [&](uint32_t step, uint32_t s) {
+        const uint32_t row0 = step * R;
+        const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
+        const uint32_t bytes = rows * ROW_BYTES;
+        mbar_arrive_expect_tx(&bars[s], bytes);
+        const float *src = p.corpus + static_cast<size_t>(row0) * (128u * C);
+        if (p.use_l2_hint) bulk_copy_g2s_hint(ring + s * STAGE_BYTES, src, bytes, &bars[s], policy);
+        else bulk_copy_g2s(ring + s * STAGE_BYTES, src, bytes, &bars[s]);
+    };
+
+    if (lane == 0) {
+        for (uint32_t s = 0; s < stages; ++s) mbar_init(&bars[s], 1);
+        mbar_fence_init();
+    }
+    __syncwarp();
+    if (lane == 0) {
+        for (uint32_t s = 0; s < stages; ++s) {
+            const uint32_t step = gwarp + s * total_warps;
+            if (step < n_steps) issue(step, s);
+        }
+    }
+
+    WarpTopK tk;
+    tk.init();
+    const int k = static_cast<int>(p.k);
+
+    uint32_t s = 0, parity = 0;
+    for (uint32_t step = gwarp; step < n_steps; step += total_warps) {
+        mbar_wait_parity(&bars[s], parity);
+        const float4 *tile = reinterpret_cast<const float4 *>(ring + s * STAGE_BYTES);
+
+        float sum0[R], sum1[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            float a0 = 0.f, a1 = 0.f, a2_ = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                const float4 v = tile[r * D4 + lane + 32 * c];
+                if (METRIC == kL2) {
+                    const float dx = __fsub_rn(q[c].x, v.x), dy = __fsub_rn(q[c].y, v.y);
+                    const float dz = __fsub_rn(q[c].z, v.z), dw = __fsub_rn(q[c].w, v.w);
+                    a0 = __fmaf_rn(dx, dx, a0); a1 = __fmaf_rn(dy, dy, a1);
+                    a2_ = __fmaf_rn(dz, dz, a2_); a3 = __fmaf_rn(dw, dw, a3);
+                } else {
+                    a0 = __fmaf_rn(q[c].x, v.x, a0); a1 = __fmaf_rn(q[c].y, v.y, a1);
+                    a2_ = __fmaf_rn(q[c].z, v.z, a2_); a3 = __fmaf_rn(q[c].w, v.w, a3);
+                    if (METRIC == kCosine) {
+                        b0 = __fmaf_rn(v.x, v.x, b0); b1 = __fmaf_rn(v.y, v.y, b1);
+                        b2 = __fmaf_rn(v.z, v.z, b2); b3 = __fmaf_rn(v.w, v.w, b3);
+                    }
+                }
+            }
+            sum0[r] = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2_, a3));
+            sum1[r] = __fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3));
+        }
+        __syncwarp();  // every lane has consumed this stage: safe to refill it
+        if (lane == 0) {
+            const uint32_t next = step + stages * total_warps;
+            if (next < n_steps) issue(next, s);
+        }
+        if (++s == stages) { s = 0; parity ^= 1u; }
+
+        warp_reduce_scatter<R>(sum0, lane);
+        if (METRIC == kCosine) warp_reduce_scatter<R>(sum1, lane);
+
+        const uint32_t my_row = step * R + (lane / LANES_PER_ROW);
+        float d;
+        if (METRIC == kCosine) d = finish_cos(sum0[0], a2, sqrt_a2, sum1[0]);
+        else if (METRIC == kDot) d = finish_dot(sum0[0]);
+        else d = finish_l2(sum0[0]);
+        const bool leader = (lane % LANES_PER_ROW) == 0;
+        const bool ok = (my_row < p.n_rows) && finite_f32(d);
+
+        if (EMIT) {
+            if (leader && my_row < p.n_rows) p.dist_keys[my_row] = ok ? orderable_u32(d) : WAXVS_UKEY_NONE;
+        } else {
+            const uint64_t key = ok ? make_key(d, my_row) : WAXVS_KEY_NONE;
+            uint32_t m = __ballot_sync(WAXVS_FULL_MASK, leader && key < tk.thresh);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const uint64_t x = shfl_u64(key, src);
+                if (x < tk.thresh) tk.insert(x, lane, k);
+            }
+        }
+    }
+
+    if (!EMIT) finish_topk(p, tk, lists, warp, lane, warps);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Generic kernel: any dims (including dims % 4 != 0 and rows too large for a shared-memory tile).
+// One warp per row, coalesced direct global loads (LDG.128 when dims % 4 == 0), same accumulation order.
+template <int METRIC, bool EMIT>
+__global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
+    __shared__ uint64_t lists[8 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
+    const uint32_t dims = p.dims;
+    const bool vec4 = (dims % 4u) == 0u;
+    const uint32_t d4 = dims / 4u;
+
+    float a2 = 0.0f, sqrt_a2 = 0.0f;
+    if (METRIC == kCosine) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (uint32_t base = 4u * lane; base < dims; base += 128u) {
+            const float x = __ldg(p.query + base);
+            const float y = (base + 1 < dims) ? __ldg(p.query + base + 1) : 0.0f;
+            const float z = (base + 2 < dims) ? __ldg(p.query + base + 2) : 0.0f;
+            const float w = (base + 3 < dims) ? __ldg(p.query + base + 3) : 0.0f;
+            s0 = __fmaf_rn(x, x, s0);
+            if (base + 1 < dims) s1 = __fmaf_rn(y, y, s1);
+            if (base + 2 < dims) s2 = __fmaf_rn(z, z, s2);
+            if (base + 3 < dims) s3 = __fmaf_rn(w, w, s3);
+        }
+        a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
+        sqrt_a2 = __fsqrt_rn(a2);
+    }
+
+    WarpTopK tk;
+    tk.init();
+    const int k = static_cast<int>(p.k);
+    const uint32_t total_warps = gridDim.x * warps;
+
+    for (uint32_t row = blockIdx.x * warps + warp; row < p.n_rows; row += total_warps) {
+        const float *v = p.corpus + static_cast<size_t>(row) * dims;
+        float a0 = 0.f, a1 = 0.f, a2_ = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        auto acc = [&](float qx, float vx, float &a, float &b) {
+            if (METRIC == kL2) { const float dd = __fsub_rn(qx, vx); a = __fmaf_rn(dd, dd, a); }
+            else {
+                a = __fmaf_rn(qx, vx, a);
+                if (METRIC == kCosine) b = __fmaf_rn(vx, vx, b);
+            }
+        };
+        if (vec4) {
+            const float4 *v4 = reinterpret_cast<const float4 *>(v);
+            const float4 *q4 = reinterpret_cast<const float4 *>(p.query);
+#pragma unroll 4
+            for (uint32_t c = lane; c < d4; c += 32u) {
+                const float4 x = __ldg(v4 + c);
+                const float4 y = __ldg(q4 + c);
+                acc(y.x, x.x, a0, b0); acc(y.y, x.y, a1, b1); acc(y.z, x.z, a2_, b2); acc(y.w, x.w, a3, b3);
+            }
+        } else {
+            for (uint32_t base = 4u * lane; base < dims; base += 128u) {
+                acc(__ldg(p.query + base), __ldg(v + base), a0, b0);
+                if (base + 1 < dims) acc(__ldg(p.query + base + 1), __ldg(v + base + 1), a1, b1);
+                if (base + 2 < dims) acc(__ldg(p.query + base + 2), __ldg(v + base + 2), a2_, b2);
+                if (base + 3 < dims) acc(__ldg(p.query + base + 3), __ldg(v + base + 3), a3, b3);
+            }
+        }
+        const float s0 = warp_butterfly_sum(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2_, a3)));
+        float d;
+        if (METRIC == kCosine) {
+            const float s1 = warp_butterfly_sum(__fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3)));
+            d = finish_cos(s0, a2, sqrt_a2, s1);
+        } else if (METRIC == kDot) d = finish_dot(s0);
+        else d = finish_l2(s0);
+        const bool ok = finite_f32(d);
+        if (EMIT) {
+            if (lane == 0) p.dist_keys[row] = ok ? orderable_u32(d) : WAXVS_UKEY_NONE;
+        } else if (ok) {
+            const uint64_t key = make_key(d, row);
+            if (key < tk.thresh) tk.insert(key, lane, k);
+        }
+    }
+    if (!EMIT) finish_topk(p, tk, lists, warp, lane, warps);
+}
+
+}  // namespace waxvs

@@ -1,0 +1,60 @@
+// waxvs_synth.cuh -- on-device synthetic corpus, the bit-exact twin of oracle wax_oracle_synth_row().
+// Value distribution follows the reference's benchmark embedder (FNV-1a -> 64-bit LCG -> [-1,1] ->
+// L2-normalise; Tests/WaxIntegrationTests/RAGBenchmarkSupport.swift:130-156).  Needed because the
+// BASELINE corpora (10 M / 100 M x 384 fp32 = 15 / 154 GB) cannot be staged through a host.
+#pragma once
+#include "waxvs_common.cuh"
+
+namespace waxvs {
+
+__host__ __device__ inline uint64_t synth_state0(uint64_t seed, uint64_t row) {
+    uint64_t h = 14695981039346656037ull;
+    for (int i = 0; i < 8; ++i) { h ^= (seed >> (8 * i)) & 0xff; h *= 1099511628211ull; }
+    for (int i = 0; i < 8; ++i) { h ^= (row >> (8 * i)) & 0xff; h *= 1099511628211ull; }
+    h ^= h >> 30; h *= 0xbf58476d1ce4e5b9ull;
+    h ^= h >> 27; h *= 0x94d049bb133111ebull;
+    h ^= h >> 31;
+    return h;
+}
+
+// One thread per row (the LCG is sequential along a row).  Two passes over the LCG: |x|^2 first (fma
+// chain, same order as the oracle), then scaled stores.
+__global__ void __launch_bounds__(256) synth_fill_kernel(float *dst, uint64_t n_rows, uint32_t dims,
+                                                         uint64_t seed, uint64_t first_row, int normalize) {
+    const uint64_t r = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    if (r >= n_rows) return;
+    const uint64_t s0 = synth_state0(seed, first_row + r);
+    float inv = 1.0f;
+    if (normalize) {
+        uint64_t st = s0;
+        float s = 0.0f;
+        for (uint32_t i = 0; i < dims; ++i) {
+            st = st * 6364136223846793005ull + 1442695040888963407ull;
+            const float x = __fmul_rn(__ll2float_rn(static_cast<long long>(st)), 0x1p-63f);
+            s = __fmaf_rn(x, x, s);
+        }
+        if (s > 0.0f) inv = __fdiv_rn(1.0f, __fsqrt_rn(s));
+    }
+    uint64_t st = s0;
+    float *out = dst + r * dims;
+    for (uint32_t i = 0; i < dims; ++i) {
+        st = st * 6364136223846793005ull + 1442695040888963407ull;
+        const float x = __fmul_rn(__ll2float_rn(static_cast<long long>(st)), 0x1p-63f);
+        out[i] = normalize ? __fmul_rn(x, inv) : x;
+    }
+}
+
+// Order-preserving row scatter used by add_batch when a batch overwrites existing rows:
+// staging row i -> corpus row target[i] (target == UINT32_MAX: superseded by a later duplicate, skip).
+__global__ void __launch_bounds__(256) scatter_rows_kernel(float *corpus, const float *staging,
+                                                           const uint32_t *target, uint64_t n, uint32_t dims) {
+    const uint64_t row = blockIdx.x;
+    if (row >= n) return;
+    const uint32_t t = target[row];
+    if (t == 0xFFFFFFFFu) return;
+    const float *src = staging + row * dims;
+    float *dst = corpus + static_cast<uint64_t>(t) * dims;
+    for (uint32_t i = threadIdx.x; i < dims; i += blockDim.x) dst[i] = src[i];
+}
+
+}  // namespace waxvs

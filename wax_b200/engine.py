@@ -1,0 +1,308 @@
+"""Host-side mirror of Wax's `VectorSearchEngine` surface over the CUDA C-ABI.
+
+The reference's host language is Swift, which this image cannot compile; `swift/CUDAVectorEngine.swift`
+(uncompiled) is the literal binding.  This module is the same surface in Python so the
+parity tests read like the reference's own tests (Tests/WaxIntegrationTests/VectorSearchEngineTests.swift):
+
+    protocol VectorSearchEngine            Sources/WaxVectorSearch/VectorSearchEngine.swift:10-18
+    enum VectorMetric                      Sources/WaxVectorSearch/VectorMetric.swift:5-54
+    actor MetalVectorEngine (public API)   Sources/WaxVectorSearch/MetalVectorEngine.swift:144-146,153,330-446,682-828
+    WaxVectorSearchSession.search          Sources/Wax/VectorSearchSession.swift:70-76
+    VectorMath.normalizeL2/isNormalizedL2  Sources/Wax/Utilities/VectorMath.swift:15-33,123-127
+    WaxError cases                         encodingError / capacityExceeded / invalidToc
+
+Everything numeric happens in libwaxvs_cuda.so; nothing here computes a distance.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import enum
+import threading
+from typing import Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+# ---- WaxError (the cases the vector engines throw) ---------------------------------------------------------
+class WaxError(Exception):
+    pass
+
+
+class EncodingError(WaxError):      # WaxError.encodingError(reason:)
+    pass
+
+
+class CapacityExceeded(WaxError):   # WaxError.capacityExceeded(limit:requested:)
+    pass
+
+
+class InvalidToc(WaxError):         # WaxError.invalidToc(reason:)
+    pass
+
+
+def _raise(rc: int) -> None:
+    reason = L.last_error()
+    if rc == L.ERR_DIMENSION:
+        raise EncodingError(reason)
+    if rc == L.ERR_CAPACITY:
+        raise CapacityExceeded(reason)
+    raise InvalidToc(f"{reason} (rc={rc})")
+
+
+def _check(rc: int) -> None:
+    if rc != L.OK:
+        _raise(rc)
+
+
+# ---- VectorMetric (VectorMetric.swift:5-54) -----------------------------------------------------------------
+class VectorMetric(enum.Enum):
+    cosine = 0
+    dot = 1
+    l2 = 2
+
+    def to_vec_similarity(self) -> int:          # toVecSimilarity (:45-54); VecSimilarity raw value
+        return self.value
+
+    def score(self, from_distance: float) -> float:  # score(fromDistance:) (:32-43)
+        d = np.float32(from_distance)
+        if not np.isfinite(d):
+            return 0.0
+        return float(np.float32(1) - d) if self is VectorMetric.cosine else float(-d)
+
+
+class VectorEnginePreference(enum.Enum):     # VectorSearchEngine.swift:4-8 (metalPreferred -> the GPU engine)
+    auto = 0
+    gpu_preferred = 1
+    cpu_only = 2
+
+
+# ---- VectorMath (host-side query preparation only) -------------------------------------------------------------
+def normalize_l2(vector: Sequence[float]) -> np.ndarray:
+    """VectorMath.normalizeL2 (VectorMath.swift:15-33): x * (1/|x|); empty or zero vectors unchanged."""
+    v = np.ascontiguousarray(vector, dtype=np.float32)
+    if v.size == 0:
+        return v
+    s = np.float32(0)
+    for x in v:                       # vDSP_svesq: plain fp32 sum of squares
+        s = np.float32(s + x * x)
+    m = np.float32(np.sqrt(s))
+    if not m > 0:
+        return v
+    return (v * np.float32(np.float32(1) / m)).astype(np.float32)
+
+
+def is_normalized_l2(vector: Sequence[float], tolerance: float = 1e-3) -> bool:
+    """VectorMath.isNormalizedL2 (VectorMath.swift:123-127)."""
+    v = np.ascontiguousarray(vector, dtype=np.float32)
+    if v.size == 0:
+        return False
+    s = np.float32(0)
+    for x in v:
+        s = np.float32(s + x * x)
+    return bool(abs(np.float32(np.sqrt(s)) - np.float32(1)) <= np.float32(tolerance))
+
+
+def _as_rows(vectors, dims: int) -> np.ndarray:
+    rows = [np.asarray(v, dtype=np.float32).reshape(-1) for v in vectors] if not isinstance(vectors, np.ndarray) \
+        else None
+    if rows is not None:
+        for v in rows:
+            if v.size != dims:  # MetalVectorEngine.swift:367-370
+                raise EncodingError(f"vector dimension mismatch: expected {dims}, got {v.size}")
+        return np.ascontiguousarray(np.stack(rows) if rows else np.zeros((0, dims), np.float32))
+    arr = np.ascontiguousarray(vectors, dtype=np.float32)
+    if arr.ndim != 2 or arr.shape[1] != dims:
+        got = arr.shape[1] if arr.ndim == 2 else arr.size
+        raise EncodingError(f"vector dimension mismatch: expected {dims}, got {got}")
+    return arr
+
+
+class CUDAVectorEngine:
+    """Drop-in for MetalVectorEngine / USearchVectorEngine behind `VectorSearchEngine`.
+
+    Thread-safety mirrors the actor + AsyncReadWriteLock: searches may run concurrently, mutators are
+    exclusive (enforced inside the library).
+    """
+
+    @staticmethod
+    def is_available() -> bool:                      # MetalVectorEngine.isAvailable (:144-146)
+        n = C.c_int32(0)
+        return L.lib().wax_vs_device_count(C.byref(n)) == L.OK and n.value > 0
+
+    def __init__(self, metric: VectorMetric = VectorMetric.cosine, dimensions: int = 0,
+                 device: Optional[int] = None):     # init(metric:dimensions:) (:153)
+        if dimensions <= 0:
+            raise InvalidToc("dimensions must be > 0")
+        if dimensions > L.MAX_DIMENSIONS:
+            raise CapacityExceeded(f"capacity exceeded: limit {L.MAX_DIMENSIONS}, requested {dimensions}")
+        self.metric = metric
+        self.dimensions = int(dimensions)
+        self._dirty = False
+        self._h = C.c_void_p()
+        devs = (C.c_int32 * 1)(device) if device is not None else None
+        _check(L.lib().wax_vs_create(self.dimensions, metric.to_vec_similarity(), devs,
+                                     1 if device is not None else 0, C.byref(self._h)))
+        self._closed = False
+        self._lock = threading.Lock()
+
+    # -- lifetime
+    def close(self) -> None:
+        if not getattr(self, "_closed", True):
+            self._closed = True
+            L.lib().wax_vs_destroy(self._h)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    @property
+    def handle(self) -> C.c_void_p:
+        return self._h
+
+    @property
+    def count(self) -> int:
+        n = C.c_uint64(0)
+        _check(L.lib().wax_vs_count(self._h, C.byref(n)))
+        return n.value
+
+    # -- VectorSearchEngine protocol
+    def search(self, vector: Sequence[float], top_k: int) -> List[Tuple[int, float]]:
+        """search(vector:topK:) -> [(frameId, score)] best first."""
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        n_rows = self.count
+        cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(n_rows, 1)))
+        ids = np.zeros(cap, np.uint64)
+        scores = np.zeros(cap, np.float32)
+        n = C.c_uint32(0)
+        _check(L.lib().wax_vs_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k),
+                                     ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                     scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
+        return [(int(ids[i]), float(scores[i])) for i in range(n.value)]
+
+    def search_batch(self, vectors, top_k: int) -> List[List[Tuple[int, float]]]:
+        qs = _as_rows(vectors, self.dimensions) if len(vectors) else np.zeros((0, self.dimensions), np.float32)
+        b = qs.shape[0]
+        if b == 0:
+            return []
+        n_rows = self.count
+        cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(n_rows, 1)))
+        ids = np.zeros((b, cap), np.uint64)
+        scores = np.zeros((b, cap), np.float32)
+        ns = np.zeros(b, np.uint32)
+        _check(L.lib().wax_vs_search_batch(self._h, qs.ctypes.data_as(C.POINTER(C.c_float)), b, qs.shape[1],
+                                           int(top_k), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           scores.ctypes.data_as(C.POINTER(C.c_float)), cap,
+                                           ns.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(b)]
+
+    def add(self, frame_id: int, vector: Sequence[float]) -> None:
+        v = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        _check(L.lib().wax_vs_add(self._h, int(frame_id), v.ctypes.data_as(C.POINTER(C.c_float)), v.size))
+        self._dirty = True
+
+    def add_batch(self, frame_ids: Sequence[int], vectors) -> None:
+        ids = np.ascontiguousarray(frame_ids, dtype=np.uint64).reshape(-1)
+        if ids.size == 0:                         # guard !frameIds.isEmpty (:360)
+            return
+        if ids.size != len(vectors):              # :361-363
+            raise EncodingError("addBatch: frameIds.count != vectors.count")
+        rows = _as_rows(vectors, self.dimensions)
+        _check(L.lib().wax_vs_add_batch(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                        rows.ctypes.data_as(C.POINTER(C.c_float)), ids.size, rows.shape[1]))
+        self._dirty = True
+
+    def add_batch_streaming(self, frame_ids: Sequence[int], vectors, chunk_size: int = 256) -> None:
+        """addBatchStreaming (:404-421)."""
+        if len(frame_ids) == 0:
+            return
+        if len(frame_ids) != len(vectors):
+            raise EncodingError("addBatchStreaming: frameIds.count != vectors.count")
+        if len(frame_ids) <= chunk_size:
+            return self.add_batch(frame_ids, vectors)
+        for start in range(0, len(frame_ids), chunk_size):
+            self.add_batch(frame_ids[start:start + chunk_size], vectors[start:start + chunk_size])
+
+    def remove(self, frame_id: int) -> None:
+        before = self.count
+        _check(L.lib().wax_vs_remove(self._h, int(frame_id)))
+        if self.count != before:
+            self._dirty = True
+
+    def reserve(self, rows: int) -> None:
+        _check(L.lib().wax_vs_reserve(self._h, int(rows)))
+
+    # -- persistence (MV2V encoding = 2)
+    def serialize(self) -> bytes:
+        n = C.c_uint64(0)
+        _check(L.lib().wax_vs_serialized_length(self._h, C.byref(n)))
+        buf = np.zeros(n.value, np.uint8)
+        out = C.c_uint64(0)
+        _check(L.lib().wax_vs_serialize(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint8)), buf.size, C.byref(out)))
+        return buf[: out.value].tobytes()
+
+    def deserialize(self, data: bytes) -> None:
+        buf = np.frombuffer(bytes(data), np.uint8)
+        ptr = buf.ctypes.data_as(C.POINTER(C.c_uint8)) if buf.size else C.cast(C.c_char_p(b""), C.POINTER(C.c_uint8))
+        _check(L.lib().wax_vs_deserialize(self._h, ptr, buf.size))
+        self._dirty = False
+
+    def stage_for_commit(self, into) -> None:
+        """stageForCommit(into:) (:818-828): `into` needs stage_vec_index_for_next_commit(bytes, vector_count,
+        dimension, similarity) -- the Wax store itself is out of scope."""
+        if not self._dirty:
+            return
+        into.stage_vec_index_for_next_commit(bytes=self.serialize(), vector_count=self.count,
+                                             dimension=self.dimensions,
+                                             similarity=self.metric.to_vec_similarity())
+        self._dirty = False
+
+    # -- instrumentation
+    def debug_buffer_pool_stats(self) -> Tuple[int, int]:
+        a, r = C.c_uint64(0), C.c_uint64(0)
+        _check(L.lib().wax_vs_debug_pool_stats(self._h, C.byref(a), C.byref(r)))
+        return a.value, r.value
+
+    def fill_synthetic(self, seed: int, rows: int, first_row: int = 0, id_base: int = 0,
+                       normalize: bool = True) -> None:
+        _check(L.lib().wax_vs_debug_fill_synthetic(self._h, seed, first_row, rows, id_base, int(normalize)))
+        self._dirty = True
+
+    def read_rows(self, first: int, n: int) -> np.ndarray:
+        out = np.empty((n, self.dimensions), np.float32)
+        _check(L.lib().wax_vs_debug_read_rows(self._h, first, n, out.ctypes.data_as(C.POINTER(C.c_float))))
+        return out
+
+    def time_search(self, top_k: int, iters: int, warmup: int = 3, n_queries: int = 1, seed: int = 7):
+        """Kernel-only timing (CUDA events on the launching stream). Returns (ms_total, launches)."""
+        ms, launches = C.c_float(0), C.c_uint64(0)
+        _check(L.lib().wax_vs_debug_time_search(self._h, n_queries, int(top_k), seed, warmup, iters,
+                                                C.byref(ms), C.byref(launches)))
+        return ms.value, launches.value
+
+    def set_option(self, key: str, value: int) -> None:
+        _check(L.lib().wax_vs_debug_set_option(self._h, key.encode(), int(value)))
+
+
+class VectorSearchSession:
+    """The score-preserving entry `WaxVectorSearchSession.search` (VectorSearchSession.swift:70-76):
+    cosine queries that are not unit length (tolerance 1e-3) are normalised on the host first."""
+
+    def __init__(self, engine: CUDAVectorEngine):
+        self.engine = engine
+        self.metric = engine.metric
+
+    def search(self, vector: Sequence[float], top_k: int):
+        q = np.ascontiguousarray(vector, dtype=np.float32)
+        if self.metric is VectorMetric.cosine and q.size and not is_normalized_l2(q):
+            q = normalize_l2(q)
+        return self.engine.search(q, top_k)

@@ -1,0 +1,149 @@
+"""Row-sharded vector search across GPUs: one process (rank) per GPU, one CUDA engine per rank.
+
+Design (BASELINE.json north_star): contiguous row ranges per rank, the query
+replicated, the identical fused kernel on every shard, ONE all-gather of the per-shard top-k candidates
+(k x 24 B per rank -- NCCL over NVLink when the group's backend is nccl) and a final host-side merge under
+the same total order (distance ascending, GLOBAL row ascending), so results do not depend on the shard
+count.  Nothing else is exchanged.
+
+The reference has no distributed code at all ("none exist"); this is the only
+parallelism the build adds.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+CAND_DTYPE = np.dtype([("distance", "<f4"), ("valid", "<u4"), ("row", "<u8"), ("frame_id", "<u8")])
+assert CAND_DTYPE.itemsize == 24
+
+
+def shard_range(total_rows: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Contiguous shard [lo, hi): rows r*N/R .. (r+1)*N/R (global row = lo + local row)."""
+    lo = (total_rows * rank) // world_size
+    hi = (total_rows * (rank + 1)) // world_size
+    return lo, hi
+
+
+def clamp_topk(top_k: int) -> int:
+    """clampTopK (MetalVectorEngine.swift:842-846)."""
+    return 1 if top_k < 1 else min(int(top_k), 10_000)
+
+
+def merge_candidates(gathered: np.ndarray, top_k: int) -> np.ndarray:
+    """Host-side R-way merge: `gathered` is any array of CAND_DTYPE records (all ranks' lists);
+    returns the best `top_k` valid ones ordered by (distance, global row)."""
+    flat = gathered.reshape(-1)
+    flat = flat[flat["valid"] != 0]
+    if flat.size == 0:
+        return flat
+    order = np.lexsort((flat["row"], flat["distance"]))  # primary: distance, secondary: row
+    return flat[order[:top_k]]
+
+
+def score_from_distance(similarity: int, d: np.ndarray) -> np.ndarray:
+    """VectorMetric.score(fromDistance:) (VectorMetric.swift:32-43), vectorised, fp32."""
+    d = d.astype(np.float32)
+    s = (np.float32(1) - d) if similarity == 0 else -d
+    return np.where(np.isfinite(d), s, np.float32(0)).astype(np.float32)
+
+
+class ShardedVectorEngine:
+    """`VectorSearchEngine.search` over a corpus row-sharded across the ranks of a torch.distributed group.
+
+    local_search: optional injection point used by the CPU (gloo) tests of the host-side logic -- a callable
+    (query ndarray, k) -> ndarray[CAND_DTYPE] of length k.  In production it is None and the local step is
+    wax_vs_search_device on the rank's GPU.
+    """
+
+    def __init__(self, metric, dimensions: int, total_rows: int = 0, group=None,
+                 local_search: Optional[Callable[[np.ndarray, int], np.ndarray]] = None, device=None):
+        import torch
+        import torch.distributed as dist
+        self._torch, self._dist = torch, dist
+        self.group = group
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        self.world_size = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.metric = metric
+        self.dimensions = int(dimensions)
+        self.total_rows = int(total_rows)
+        self.row_lo, self.row_hi = shard_range(self.total_rows, self.world_size, self.rank)
+        self._local_search = local_search
+        self.engine = None
+        self._bufs = {}
+        if local_search is None:
+            from .engine import CUDAVectorEngine
+            self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+            self.engine = CUDAVectorEngine(metric, dimensions, device=self.device.index)
+        else:
+            self.device = torch.device("cpu")
+
+    # -- corpus
+    def fill_synthetic(self, seed: int, normalize: bool = True) -> None:
+        """Each rank generates its own shard on device; frameId = global row."""
+        self.engine.fill_synthetic(seed, self.row_hi - self.row_lo, first_row=self.row_lo, id_base=self.row_lo,
+                                   normalize=normalize)
+
+    # -- search
+    def _buffers(self, k: int):
+        torch = self._torch
+        key = k
+        if key not in self._bufs:
+            local = torch.zeros(k * 24, dtype=torch.uint8, device=self.device)
+            gathered = torch.zeros(self.world_size * k * 24, dtype=torch.uint8, device=self.device)
+            host = torch.zeros(self.world_size * k * 24, dtype=torch.uint8,
+                               pin_memory=(self.device.type == "cuda"))
+            self._bufs[key] = (local, gathered, host)
+        return self._bufs[key]
+
+    def search_async(self, d_query, top_k: int):
+        """Enqueue local scan + all-gather + D2H on the current stream; returns a handle for finish()."""
+        torch, dist = self._torch, self._dist
+        k = clamp_topk(top_k)
+        local, gathered, host = self._buffers(k)
+        if self._local_search is not None:
+            cands = np.ascontiguousarray(self._local_search(np.asarray(d_query, np.float32), k), dtype=CAND_DTYPE)
+            local.copy_(torch.from_numpy(cands.view(np.uint8).reshape(-1).copy()))
+        else:
+            from . import _lib as L
+            stream = torch.cuda.current_stream(self.device)
+            rc = L.lib().wax_vs_search_device(self.engine.handle, C.c_void_p(d_query.data_ptr()), 1, k,
+                                              self.row_lo, C.c_void_p(local.data_ptr()),
+                                              C.c_void_p(stream.cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"wax_vs_search_device rc={rc}: {L.last_error()}")
+        if self.world_size > 1:
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+        else:
+            gathered.copy_(local)
+        host.copy_(gathered, non_blocking=True)
+        ev = None
+        if self.device.type == "cuda":
+            ev = torch.cuda.Event()
+            ev.record()
+        return (host, ev, k)
+
+    def finish(self, handle) -> List[Tuple[int, float]]:
+        host, ev, k = handle
+        if ev is not None:
+            ev.synchronize()
+        cands = host.numpy().view(CAND_DTYPE)
+        k_eff = min(k, self.total_rows) if self.total_rows else k
+        best = merge_candidates(cands, k_eff)
+        scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
+        return [(int(best["frame_id"][i]), float(scores[i])) for i in range(best.size)]
+
+    def search(self, vector: Sequence[float], top_k: int) -> List[Tuple[int, float]]:
+        torch = self._torch
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        if q.size != self.dimensions:
+            from .engine import EncodingError
+            raise EncodingError(f"vector dimension mismatch: expected {self.dimensions}, got {q.size}")
+        if self.total_rows == 0:
+            return []
+        if self._local_search is not None:
+            return self.finish(self.search_async(q, top_k))
+        d_q = torch.from_numpy(q).to(self.device, non_blocking=False)
+        return self.finish(self.search_async(d_q, top_k))
