@@ -90,3 +90,19 @@ def test_product_package_never_touches_the_oracle():
     assert "oracle" not in needed
     undefined = subprocess.run(["nm", "-D", "--undefined-only", str(build.build())], capture_output=True, text=True).stdout
     assert "wax_oracle" not in undefined
+
+
+def test_header_is_valid_c_and_cxx_mirror_links(tmp_path):
+    """gcc -std=c11 on a C probe and g++ -std=c++17 on the C++ mirror probe, linked against the built .so."""
+    from wax_b200 import build
+    lib = build.build()
+    env_rpath = f"-Wl,-rpath,{lib.parent}"
+    c_exe, cpp_exe = tmp_path / "c_probe", tmp_path / "cpp_probe"
+    subprocess.run(["gcc", "-std=c11", "-Wall", "-Werror", f"-I{ROOT / 'include'}", str(ROOT / "tests" / "c_abi_probe.c"),
+                    f"-L{lib.parent}", "-lwaxvs_cuda", env_rpath, "-o", str(c_exe)], check=True, capture_output=True)
+    out = subprocess.run([str(c_exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "sm_100a" in out.stdout, (out.returncode, out.stdout, out.stderr)
+    subprocess.run(["g++", "-std=c++17", "-Wall", str(ROOT / "tests" / "cpp_mirror_probe.cpp"), f"-L{lib.parent}",
+                    "-lwaxvs_cuda", env_rpath, "-o", str(cpp_exe)], check=True, capture_output=True)
+    out = subprocess.run([str(cpp_exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "dimensions must be > 0" in out.stdout, (out.returncode, out.stdout, out.stderr)

@@ -1,0 +1,93 @@
+// cuda_vector_engine.hpp -- header-only C++17 mirror of Wax's `VectorSearchEngine` over the C-ABI
+// (for C++ hosts; the Swift actor in swift/ and the Python mirror in wax_b200/engine.py bind the same entry
+// points).  Member names follow the protocol (Sources/WaxVectorSearch/VectorSearchEngine.swift:10-18) and
+// MetalVectorEngine's public surface (MetalVectorEngine.swift:144-146,153,330-446,682-815).
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "../../include/wax_vs_cuda.h"
+
+namespace wax {
+
+enum class VectorMetric : uint8_t { cosine = WAX_VS_COSINE, dot = WAX_VS_DOT, l2 = WAX_VS_L2 };
+
+// WaxError cases thrown on this path.
+struct WaxError : std::runtime_error { using std::runtime_error::runtime_error; };
+struct EncodingError : WaxError { using WaxError::WaxError; };
+struct CapacityExceeded : WaxError { using WaxError::WaxError; };
+struct InvalidToc : WaxError { using WaxError::WaxError; };
+
+class CUDAVectorEngine {
+public:
+    using Hit = std::pair<uint64_t, float>;  // (frameId, score)
+
+    static bool isAvailable() {
+        int32_t n = 0;
+        return wax_vs_device_count(&n) == WAX_VS_OK && n > 0;
+    }
+    CUDAVectorEngine(VectorMetric metric, uint32_t dimensions) : metric_(metric), dimensions_(dimensions) {
+        check(wax_vs_create(dimensions, static_cast<uint8_t>(metric), nullptr, 0, &h_));
+    }
+    ~CUDAVectorEngine() { wax_vs_destroy(h_); }
+    CUDAVectorEngine(const CUDAVectorEngine &) = delete;
+    CUDAVectorEngine &operator=(const CUDAVectorEngine &) = delete;
+
+    uint32_t dimensions() const { return dimensions_; }
+    uint64_t count() const { uint64_t n = 0; check(wax_vs_count(h_, &n)); return n; }
+
+    std::vector<Hit> search(const std::vector<float> &vector, int64_t topK) const {
+        const int64_t lim = topK < 1 ? 1 : (topK > WAX_VS_MAX_RESULTS ? WAX_VS_MAX_RESULTS : topK);
+        std::vector<uint64_t> ids(static_cast<size_t>(lim));
+        std::vector<float> scores(static_cast<size_t>(lim));
+        uint32_t n = 0;
+        check(wax_vs_search(h_, vector.data(), static_cast<uint32_t>(vector.size()), topK, ids.data(), scores.data(),
+                            static_cast<uint32_t>(lim), &n));
+        std::vector<Hit> out(n);
+        for (uint32_t i = 0; i < n; ++i) out[i] = {ids[i], scores[i]};
+        return out;
+    }
+    void add(uint64_t frameId, const std::vector<float> &vector) {
+        check(wax_vs_add(h_, frameId, vector.data(), static_cast<uint32_t>(vector.size())));
+    }
+    void addBatch(const std::vector<uint64_t> &frameIds, const std::vector<std::vector<float>> &vectors) {
+        if (frameIds.empty()) return;
+        if (frameIds.size() != vectors.size()) throw EncodingError("addBatch: frameIds.count != vectors.count");
+        std::vector<float> flat;
+        flat.reserve(vectors.size() * dimensions_);
+        for (const auto &v : vectors) {
+            if (v.size() != dimensions_)
+                throw EncodingError("vector dimension mismatch: expected " + std::to_string(dimensions_) + ", got " +
+                                    std::to_string(v.size()));
+            flat.insert(flat.end(), v.begin(), v.end());
+        }
+        check(wax_vs_add_batch(h_, frameIds.data(), flat.data(), frameIds.size(), dimensions_));
+    }
+    void remove(uint64_t frameId) { check(wax_vs_remove(h_, frameId)); }
+    std::vector<uint8_t> serialize() const {
+        uint64_t len = 0;
+        check(wax_vs_serialized_length(h_, &len));
+        std::vector<uint8_t> blob(len);
+        check(wax_vs_serialize(h_, blob.data(), len, &len));
+        return blob;
+    }
+    void deserialize(const std::vector<uint8_t> &blob) { check(wax_vs_deserialize(h_, blob.data(), blob.size())); }
+    wax_vs_engine *handle() const { return h_; }
+
+private:
+    static void check(int32_t rc) {
+        if (rc == WAX_VS_OK) return;
+        const std::string reason = wax_vs_last_error();
+        if (rc == WAX_VS_ERR_DIMENSION) throw EncodingError(reason);
+        if (rc == WAX_VS_ERR_CAPACITY) throw CapacityExceeded(reason);
+        throw InvalidToc(reason);
+    }
+    VectorMetric metric_;
+    uint32_t dimensions_;
+    wax_vs_engine *h_ = nullptr;
+};
+
+}  // namespace wax
