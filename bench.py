@@ -221,6 +221,7 @@ def run_single(args):
     value = args.steps / (ms_total / 1e3)
 
     peak, peak_src = measured_peak()
+    read_ceiling = eng.stream_read_gbs(5)                # plain LDG.128 read of the same bytes, same box
     alg_bytes = args.rows * DIMS * 4                     # N*D*4 algorithmic bytes per launch
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
     traffic = None
@@ -239,6 +240,8 @@ def run_single(args):
         "config": workload_config(args, 1),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "peak_source": peak_src,
+                     "stream_read_ceiling_gbs": read_ceiling, "frac_of_read_ceiling": achieved / read_ceiling if read_ceiling else None,
+                     "nominal_hbm_gbs": 7700.0, "frac_of_nominal": achieved / 7700.0,
                      "kernel": "scan_tma_kernel<C=3,cosine> (fused scan+top-k, 1 launch per query)",
                      "algorithmic_bytes_per_launch": alg_bytes},
         "e2e": {"value": args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": DIMS * 4,

@@ -171,6 +171,10 @@ int32_t wax_vs_debug_time_search(wax_vs_engine *engine, uint32_t n_queries, int6
                                  uint32_t warmup, uint32_t iters, float *out_ms_total,
                                  uint64_t *out_launches);
 
+/* Streaming-read ceiling on the same box: a plain coalesced LDG.128 read of the live corpus bytes, best of
+   `iters` (milliseconds, and the bytes read).  Context for the roofline fraction. */
+int32_t wax_vs_debug_stream_read(wax_vs_engine *engine, uint32_t iters, float *out_best_ms, uint64_t *out_bytes);
+
 /* Tuning knobs for experiments ("variant", "ctas_per_sm", ...).  Unknown key -> WAX_VS_ERR_ARGUMENT. */
 int32_t wax_vs_debug_set_option(wax_vs_engine *engine, const char *key, int64_t value);
 

@@ -895,6 +895,36 @@ int32_t wax_vs_debug_time_search(wax_vs_engine *e, uint32_t n_queries, int64_t t
     return WAX_VS_OK;
 }
 
+int32_t wax_vs_debug_stream_read(wax_vs_engine *e, uint32_t iters, float *out_best_ms, uint64_t *out_bytes) {
+    if (!e || !out_best_ms || !out_bytes) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    DeviceGuard g(e->device);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_acquire(e, &c);
+    if (rc) return rc;
+    struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); } } rel{e, c};
+    const uint64_t bytes = e->n_rows * e->dims * sizeof(float) / 16 * 16;
+    *out_bytes = bytes;
+    *out_best_ms = 0.0f;
+    if (bytes == 0) return WAX_VS_OK;
+    float best = 1e30f;
+    for (uint32_t it = 0; it < iters + 2; ++it) {
+        CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+        stream_read_kernel<<<e->sm_count * 4, 512, 0, c->stream>>>(reinterpret_cast<const uint4 *>(e->d_corpus),
+                                                                     bytes / 16, c->d_ticket + 0);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
+        if (it >= 2 && ms < best) best = ms;
+    }
+    CUDA_TRY(cudaMemsetAsync(c->d_ticket, 0, sizeof(uint32_t), c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    *out_best_ms = best;
+    return WAX_VS_OK;
+}
+
 int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value) {
     if (!e || !key) return fail(WAX_VS_ERR_NULL, "NULL argument");
     std::unique_lock<std::shared_mutex> w(e->rw);

@@ -289,6 +289,12 @@ class CUDAVectorEngine:
                                                 C.byref(ms), C.byref(launches)))
         return ms.value, launches.value
 
+    def stream_read_gbs(self, iters: int = 5) -> float:
+        """Plain coalesced read of the corpus bytes: the box's streaming-read ceiling in GB/s."""
+        ms, nbytes = C.c_float(0), C.c_uint64(0)
+        _check(L.lib().wax_vs_debug_stream_read(self._h, iters, C.byref(ms), C.byref(nbytes)))
+        return nbytes.value / (ms.value * 1e6) if ms.value > 0 else 0.0
+
     def set_option(self, key: str, value: int) -> None:
         _check(L.lib().wax_vs_debug_set_option(self._h, key.encode(), int(value)))
 
