@@ -171,6 +171,17 @@ int32_t wax_vs_debug_time_search(wax_vs_engine *engine, uint32_t n_queries, int6
                                  uint32_t warmup, uint32_t iters, float *out_ms_total,
                                  uint64_t *out_launches);
 
+/* Batched-path instrumentation: how many queries were answered by the tensor-core nomination path with a
+   completed exactness proof, and how many had to be re-run on the exact single-query path. */
+int32_t wax_vs_debug_batch_stats(wax_vs_engine *engine, uint64_t *tensor_queries, uint64_t *fallback_queries);
+
+/* Device-only timing of the batched path (n_queries synthetic unit queries per step, everything resident):
+   total milliseconds of `iters` steps (CUDA events on the launching stream), kernel launches in the bracket and
+   the number of queries of the last step whose proof did not complete (they would be re-run exactly). */
+int32_t wax_vs_debug_time_search_batch(wax_vs_engine *engine, uint32_t n_queries, int64_t top_k, uint64_t seed,
+                                       uint32_t warmup, uint32_t iters, float *out_ms_total,
+                                       uint64_t *out_launches, uint32_t *out_unproven);
+
 /* Streaming-read ceiling on the same box: a plain coalesced LDG.128 read of the live corpus bytes, best of
    `iters` (milliseconds, and the bytes read).  Context for the roofline fraction. */
 int32_t wax_vs_debug_stream_read(wax_vs_engine *engine, uint32_t iters, float *out_best_ms, uint64_t *out_bytes);

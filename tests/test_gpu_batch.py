@@ -1,0 +1,94 @@
+"""GPU: the batched path (tcgen05 TF32 nomination + exact fp32 re-score + completeness proof) must return
+EXACTLY what the single-query path returns -- same ids, same score bits -- and must actually be the tensor path
+(the instrumentation counts queries answered with a completed proof vs. re-run exactly)."""
+import numpy as np
+import pytest
+
+from wax_b200 import CUDAVectorEngine, VectorMetric
+
+pytestmark = pytest.mark.gpu
+
+
+def _engine(oracle, metric, n, dims, seed, normalize=True):
+    eng = CUDAVectorEngine(metric, dims)
+    eng.fill_synthetic(seed, n, normalize=normalize)
+    return eng
+
+
+def _single(eng, qs, k):
+    eng.set_option("batch_tensor", 0)
+    out = [eng.search(q, k) for q in qs]
+    eng.set_option("batch_tensor", 1)
+    return out
+
+
+@pytest.mark.parametrize("dims,n,b,k", [(384, 100_003, 5, 10), (384, 100_003, 129, 10), (384, 50_000, 300, 72),
+                                        (768, 30_001, 64, 100), (128, 70_000, 17, 32), (32, 9_999, 8, 1),
+                                        (384, 255, 6, 10), (384, 257, 6, 10), (384, 1, 4, 10), (1024, 20_000, 33, 10)])
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+def test_batch_equals_single_query_path(oracle, metric, dims, n, b, k):
+    eng = _engine(oracle, metric, n, dims, seed=900 + dims, normalize=(metric is VectorMetric.cosine))
+    qs = oracle.synth_rows(901 + b, 0, b, dims, normalize=True)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, k)
+    t1, f1 = eng.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == b, "the batch did not go through the tensor path"
+    exp = _single(eng, qs, k)
+    assert got == exp
+    # random data: the proof completes for (nearly) every query -- otherwise the tensor path is not doing its job
+    if n >= 1000:
+        assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"
+    # and the single-query path is itself bit-exact against the oracle (spot check one query)
+    corpus = eng.read_rows(0, n)
+    r, d, s = oracle.search(metric.value, corpus, qs[0], k, mode=oracle.ACC_F32_TREE, threads=4)
+    assert [g[0] for g in got[0]] == r.tolist()
+    assert np.array_equal(np.float32([g[1] for g in got[0]]).view(np.uint32), s.view(np.uint32))
+
+
+def test_batch_with_near_duplicates_stays_exact(oracle):
+    """Adversarial for TF32: thousands of rows within 1e-5 of the query's best match.  The proof cannot complete
+    (TF32 cannot separate them), so those queries are re-run exactly -- results still identical."""
+    dims, n = 384, 20_000
+    rng = np.random.default_rng(3)
+    base = oracle.synth_row(77, 0, dims, True)
+    corpus = oracle.synth_rows(78, 0, n, dims)
+    corpus[:3000] = base + rng.standard_normal((3000, dims)).astype(np.float32) * np.float32(1e-6)
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.add_batch(list(range(n)), corpus)
+    qs = np.stack([base, oracle.synth_row(79, 0, dims, True), base * np.float32(2.5), corpus[5000]])
+    got = eng.search_batch(qs, 10)
+    assert got == _single(eng, qs, 10)
+    r, _, s = oracle.search(oracle.COSINE, corpus, qs[0], 10, mode=oracle.ACC_F32_TREE, threads=4)
+    assert [g[0] for g in got[0]] == r.tolist()
+    assert eng.batch_stats()[1] >= 1          # at least the adversarial queries fell back
+
+
+def test_batch_edge_rows_and_mutation_invalidates_norm_cache(oracle):
+    dims = 384
+    corpus = oracle.synth_rows(80, 0, 4000, dims)
+    corpus[7] = 0.0
+    corpus[8, 5] = np.nan
+    corpus[9, 6] = np.inf
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.add_batch(list(range(4000)), corpus)
+    qs = oracle.synth_rows(81, 0, 6, dims)
+    assert eng.search_batch(qs, 10) == _single(eng, qs, 10)
+    # mutate: scale a row by 1000 (norm changes a lot) and append rows; cached norms must be rebuilt
+    eng.add(11, corpus[11] * np.float32(1000.0))
+    eng.add_batch([5000, 5001], np.stack([qs[0], qs[1] * np.float32(3.0)]))
+    eng.remove(3)
+    got = eng.search_batch(qs, 10)
+    assert got == _single(eng, qs, 10)
+    assert got[0][0][0] == 5000 and got[1][0][0] == 5001
+    assert 8 not in [i for i, _ in eng.search_batch(qs, 4000)[0]]
+
+
+def test_ineligible_batches_use_the_loop(oracle):
+    eng = _engine(oracle, VectorMetric.l2, 5000, 384, seed=5)
+    qs = oracle.synth_rows(82, 0, 9, 384)
+    t0, f0 = eng.batch_stats()
+    assert eng.search_batch(qs, 10) == [eng.search(q, 10) for q in qs]     # l2: not on the tensor path
+    eng2 = _engine(oracle, VectorMetric.cosine, 5000, 100, seed=6)         # dims % 32 != 0
+    qs2 = oracle.synth_rows(83, 0, 9, 100)
+    assert eng2.search_batch(qs2, 10) == [eng2.search(q, 10) for q in qs2]
+    assert eng.batch_stats() == (t0, f0) and eng2.batch_stats() == (0, 0)

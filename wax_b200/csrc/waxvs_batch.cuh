@@ -1,0 +1,451 @@
+// waxvs_batch.cuh -- batched queries (BASELINE configs 3 and 5): a genuine dense contraction, so it runs on the
+// 5th-gen tensor cores.  score'[b][n] = sum_d Q[b][d] * V[n][d] as a skinny GEMM with tcgen05.mma kind::tf32:
+//
+//   A (M = 128 queries)  : TMA 2-D box [128 x 32 floats], 128-byte swizzle, K-major          (16 KB / k-block)
+//   B (N = 256 rows)     : TMA 2-D box [256 x 32 floats] of the row-major corpus, K-major     (32 KB / k-block)
+//   D                    : fp32 accumulators in TMEM, 128 lanes x 256 columns, double buffered (all 512 columns)
+//   warp roles           : warps 0-3 epilogue (thread t owns query t = TMEM lane t), warp 4 TMA producer,
+//                          warp 5 TMEM allocator + single-thread MMA issuer;  smem ring of 4 k-block stages.
+//
+// The score matrix (B x N, 40 GB at 1024 x 10 M) is never written: each epilogue thread scans its query's 256
+// accumulator columns straight out of TMEM (tcgen05.ld), scales by the row's cached 1/|v| (cosine) and keeps
+// the k' best (score', row) pairs of its row slice in a private max-heap (inserts are rare: O(k' ln(N/k'))).
+//
+// TF32 keeps 10 mantissa bits, which is not enough for the parity bar (scores within 1e-4, identical order),
+// so the tensor-core pass only NOMINATES candidates: batch_finish_kernel merges the slices' lists per query,
+// re-scores the k' nominees EXACTLY in fp32 with the very same accumulation order as the single-query kernels
+// (bit-identical results), and proves nothing was missed: every row that was not nominated has
+// score' <= tau, hence exact score <= tau + eps with eps the TF32 worst-case bound
+// (|a_t b_t - ab| <= 2^-9 |ab| termwise  =>  |err| <= 2^-9 |q||v|); if the exact k-th score does not clear
+// tau + eps the query is flagged and the host re-runs it on the exact single-query path.  Results are
+// therefore always identical to the non-batched path; the tensor cores only buy speed.
+//
+// The reference has no batched search at all (VectorSearchEngine.swift:13 takes one vector); this is the
+// "batched-query case where it is a genuine dense contraction" of BASELINE.json's north_star.
+#pragma once
+#include <cuda.h>
+
+#include "waxvs_common.cuh"
+#include "waxvs_scan.cuh"
+
+namespace waxvs {
+
+constexpr int kBatchM = 128;            // queries per CTA  (UMMA M)
+constexpr int kBatchN = 256;            // corpus rows per tile (UMMA N)
+constexpr int kBatchKBlock = 32;        // floats per k-block = one 128-byte swizzle atom
+constexpr int kBatchStages = 4;
+constexpr uint32_t kBatchABytes = kBatchM * 128u;   // 16 KB
+constexpr uint32_t kBatchBBytes = kBatchN * 128u;   // 32 KB
+constexpr uint32_t kBatchStageBytes = kBatchABytes + kBatchBBytes;
+constexpr uint32_t kBatchSmemBytes = kBatchStages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kBatchThreads = 192;
+constexpr float kTf32Eps = 1.25f * 0x1p-9f;
+
+struct BatchParams {
+    uint32_t n_rows, dims, n_queries;
+    uint32_t groups;        // ceil(n_queries / 128)
+    uint32_t slices;        // row slices; CTA b -> (group b % groups, slice b / groups)
+    uint32_t tiles_total;   // ceil(n_rows / 256)
+    uint32_t kprime;        // nominees kept per (slice, query)
+    int metric;             // kCosine or kDot
+    const float *row_scale; // [n_rows] 1/|v| (cosine) or nullptr
+    uint64_t *heaps;        // [slices*groups][128][kprime]
+};
+
+// ---- PTX wrappers (tcgen05 / TMA tensor) ---------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0,
+                                            int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem desc] * B[smem desc], kind::tf32, one CTA.
+__device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// 32 lanes x 32 columns of 32-bit accumulators -> 32 registers (thread = lane, register j = column j).
+__device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+          "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+          "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+          "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, K-major, 128-byte swizzle (canonical layout ((8,n),2):((8,SBO),1) in 16-byte
+// units; rows 128 B apart, 8-row groups SBO = 1024 B apart).  Field layout: cute::UMMA::SmemDescriptor.
+__device__ __forceinline__ uint64_t umma_desc_k_sw128(const void *smem_tile) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_u32(smem_tile) >> 4) & 0x3FFFu);  // start address  [0,14)
+    d |= static_cast<uint64_t>(1) << 16;                               // LBO (unused for swizzled K-major) [16,30)
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;                       // SBO [32,46)
+    d |= static_cast<uint64_t>(1) << 46;                               // descriptor version (Blackwell) [46,48)
+    d |= static_cast<uint64_t>(2) << 61;                               // layout type SWIZZLE_128B [61,64)
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 256.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m128_n256() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+}
+
+// ---- per-thread nominee heap (max-heap on the ordering key: root = worst nominee) ----------------------------
+// key = (orderable(-score') << 32) | row  -- smaller is better, exactly like the exact keys.
+__device__ __forceinline__ uint64_t nominee_key(float score, uint32_t row) {
+    return (static_cast<uint64_t>(orderable_u32(-score)) << 32) | row;
+}
+__device__ __forceinline__ float nominee_score(uint64_t key) { return -from_orderable_u32(static_cast<uint32_t>(key >> 32)); }
+
+__device__ __forceinline__ float heap_replace_root(uint64_t *heap, uint32_t n, uint64_t x) {
+    uint32_t i = 0;
+    for (;;) {
+        const uint32_t l = 2 * i + 1;
+        if (l >= n) break;
+        const uint32_t r = l + 1;
+        const uint64_t kl = heap[l];
+        const uint64_t kr = (r < n) ? heap[r] : 0ull;
+        const uint32_t c = (kr > kl) ? r : l;
+        const uint64_t kc = (kr > kl) ? kr : kl;
+        if (kc <= x) break;
+        heap[i] = kc;
+        i = c;
+    }
+    heap[i] = x;
+    const uint64_t root = heap[0];
+    return root == WAXVS_KEY_NONE ? -INFINITY : nominee_score(root);
+}
+
+// ---- row norms (cached per corpus version) --------------------------------------------------------------------
+// One warp per row, same accumulation order as the scan kernels.  inv_norm = 1/sqrt(sum v^2) (0 for a zero
+// row); max_norm_bits = max over finite rows of sqrt(sum v^2) as float bits (positive floats order as uints).
+__global__ void __launch_bounds__(256) row_norms_kernel(const float *corpus, uint32_t n_rows, uint32_t dims,
+                                                        float *inv_norm, uint32_t *max_norm_bits) {
+    const int lane = threadIdx.x & 31;
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    const bool vec4 = (dims % 4u) == 0u;
+    float local_max = 0.0f;
+    for (uint32_t row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; row < n_rows; row += warps) {
+        const float *v = corpus + static_cast<size_t>(row) * dims;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+        if (vec4) {
+            const float4 *v4 = reinterpret_cast<const float4 *>(v);
+            for (uint32_t c = lane; c < dims / 4u; c += 32u) {
+                const float4 x = __ldg(v4 + c);
+                b0 = __fmaf_rn(x.x, x.x, b0); b1 = __fmaf_rn(x.y, x.y, b1);
+                b2 = __fmaf_rn(x.z, x.z, b2); b3 = __fmaf_rn(x.w, x.w, b3);
+            }
+        } else {
+            for (uint32_t base = 4u * lane; base < dims; base += 128u) {
+                const float x = __ldg(v + base); b0 = __fmaf_rn(x, x, b0);
+                if (base + 1 < dims) { const float y = __ldg(v + base + 1); b1 = __fmaf_rn(y, y, b1); }
+                if (base + 2 < dims) { const float z = __ldg(v + base + 2); b2 = __fmaf_rn(z, z, b2); }
+                if (base + 3 < dims) { const float w = __ldg(v + base + 3); b3 = __fmaf_rn(w, w, b3); }
+            }
+        }
+        const float s = warp_butterfly_sum(__fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3)));
+        const float nrm = __fsqrt_rn(s);
+        if (lane == 0) inv_norm[row] = (s == 0.0f) ? 0.0f : __fdiv_rn(1.0f, nrm);
+        if (finite_f32(nrm)) local_max = fmaxf(local_max, nrm);
+    }
+    if (lane == 0 && local_max > 0.0f) atomicMax(max_norm_bits, __float_as_uint(local_max));
+}
+
+// ---- the tensor-core kernel ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kBatchThreads, 1)
+batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                  const BatchParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *stages = smem;                                            // [stage][A 16 KB | B 32 KB], 1024-aligned
+    float *scale_smem = reinterpret_cast<float *>(smem + kBatchStages * kBatchStageBytes);   // [2][256]
+    uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kBatchN);                 // [stages]
+    uint64_t *empty = full + kBatchStages;                                                   // [stages]
+    uint64_t *tmem_full = empty + kBatchStages;                                              // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t group = blockIdx.x % p.groups, slice = blockIdx.x / p.groups;
+    if (slice >= p.slices) return;                    // surplus CTAs (grid is a multiple of groups anyway)
+    const uint32_t tile_lo = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * slice / p.slices);
+    const uint32_t tile_hi = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * (slice + 1) / p.slices);
+    const uint32_t num_kb = p.dims / kBatchKBlock;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmap_q);
+        tma_prefetch_desc(&tmap_c);
+        for (int s = 0; s < kBatchStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        mbar_fence_init();
+    }
+    if (warp == 5) {  // whole warp: allocate all 512 TMEM columns (2 accumulator buffers of 256)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                     "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = tile_lo; tile < tile_hi; ++tile) {
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_parity(&empty[stage], phase ^ 1u);
+                    mbar_arrive_expect_tx(&full[stage], kBatchStageBytes);
+                    uint8_t *a = stages + stage * kBatchStageBytes;
+                    tma_load_2d(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                                static_cast<int32_t>(group * kBatchM));
+                    tma_load_2d(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                                static_cast<int32_t>(tile * kBatchN));
+                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer (one thread) =====
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_tf32_m128_n256();
+            uint32_t stage = 0, phase = 0, t = 0;
+            for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
+                const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+                mbar_wait_parity(&tmem_empty[acc], acc_phase ^ 1u);   // epilogue has drained this buffer
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * kBatchN;
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    mbar_wait_parity(&full[stage], phase);            // TMA bytes have landed
+                    tcgen05_fence_after();
+                    const uint8_t *a = stages + stage * kBatchStageBytes;
+                    const uint64_t da = umma_desc_k_sw128(a), db = umma_desc_k_sw128(a + kBatchABytes);
+#pragma unroll
+                    for (uint32_t j = 0; j < kBatchKBlock / 8; ++j)   // UMMA K = 8 tf32 = 32 bytes = +2 in the address field
+                        umma_tf32_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
+                    tcgen05_commit(&empty[stage]);                    // frees the smem stage when the MMAs retire
+                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                }
+                tcgen05_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+            }
+        }
+    } else {
+        // ===== epilogue: thread t <-> query group*128 + t <-> TMEM lane t =====
+        const uint32_t tid = threadIdx.x;                              // 0..127
+        const uint32_t q = group * kBatchM + tid;
+        const bool q_valid = q < p.n_queries;
+        uint64_t *heap = p.heaps + (static_cast<size_t>(blockIdx.x) * kBatchM + tid) * p.kprime;
+        for (uint32_t i = 0; i < p.kprime; ++i) heap[i] = WAXVS_KEY_NONE;
+        float tau = -INFINITY;
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        uint32_t t = 0;
+        for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
+            const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+            const uint32_t row0 = tile * kBatchN;
+            float *sc = scale_smem + acc * kBatchN;
+            if (p.row_scale) {
+#pragma unroll
+                for (uint32_t h = 0; h < 2; ++h) {
+                    const uint32_t r = row0 + tid + h * 128u;
+                    sc[tid + h * 128u] = (r < p.n_rows) ? __ldg(p.row_scale + r) : 0.0f;
+                }
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");            // scales visible; previous use of sc[] finished
+            mbar_wait_parity(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t rows_here = min(static_cast<uint32_t>(kBatchN), p.n_rows - row0);
+#pragma unroll 1
+            for (uint32_t chunk = 0; chunk < kBatchN / 32; ++chunk) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + lane_base + acc * kBatchN + chunk * 32u, v);
+                if (chunk * 32u >= rows_here) continue;               // warp-uniform
+#pragma unroll
+                for (uint32_t j = 0; j < 32; ++j) {
+                    const uint32_t col = chunk * 32u + j;
+                    float s = __uint_as_float(v[j]);
+                    if (p.row_scale) s *= sc[col];
+                    if (s > tau && col < rows_here && q_valid) tau = heap_replace_root(heap, p.kprime, nominee_key(s, row0 + col));
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
+// ---- exact re-score + proof ------------------------------------------------------------------------------------------
+// Exact distance of one row by one warp: the generic-dims code path of scan_ldg_kernel, same order, same bits.
+template <int METRIC>
+__device__ __forceinline__ float exact_row_distance(const float *q, const float *v, uint32_t dims, float a2,
+                                                    float sqrt_a2, int lane) {
+    float a0 = 0.f, a1 = 0.f, a2_ = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+    auto acc = [&](float qx, float vx, float &a, float &b) {
+        if (METRIC == kL2) { const float dd = __fsub_rn(qx, vx); a = __fmaf_rn(dd, dd, a); }
+        else { a = __fmaf_rn(qx, vx, a); if (METRIC == kCosine) b = __fmaf_rn(vx, vx, b); }
+    };
+    if ((dims % 4u) == 0u) {
+        const float4 *v4 = reinterpret_cast<const float4 *>(v);
+        const float4 *q4 = reinterpret_cast<const float4 *>(q);
+        for (uint32_t c = lane; c < dims / 4u; c += 32u) {
+            const float4 x = __ldg(v4 + c), y = __ldg(q4 + c);
+            acc(y.x, x.x, a0, b0); acc(y.y, x.y, a1, b1); acc(y.z, x.z, a2_, b2); acc(y.w, x.w, a3, b3);
+        }
+    } else {
+        for (uint32_t base = 4u * lane; base < dims; base += 128u) {
+            acc(__ldg(q + base), __ldg(v + base), a0, b0);
+            if (base + 1 < dims) acc(__ldg(q + base + 1), __ldg(v + base + 1), a1, b1);
+            if (base + 2 < dims) acc(__ldg(q + base + 2), __ldg(v + base + 2), a2_, b2);
+            if (base + 3 < dims) acc(__ldg(q + base + 3), __ldg(v + base + 3), a3, b3);
+        }
+    }
+    const float s0 = warp_butterfly_sum(__fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2_, a3)));
+    if (METRIC == kCosine) {
+        const float s1 = warp_butterfly_sum(__fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3)));
+        return finish_cos(s0, a2, sqrt_a2, s1);
+    }
+    return METRIC == kDot ? finish_dot(s0) : finish_l2(s0);
+}
+
+__device__ __forceinline__ void block_bitonic_sort(uint64_t *sk, uint32_t pow2) {
+    for (uint32_t size = 2; size <= pow2; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = threadIdx.x; i < pow2 / 2; i += blockDim.x) {
+                const uint32_t lo = (i / stride) * (2 * stride) + (i % stride), hi = lo + stride;
+                const bool asc = ((lo & size) == 0);
+                const uint64_t a = sk[lo], b = sk[hi];
+                if ((a > b) == asc) { sk[lo] = b; sk[hi] = a; }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct FinishParams {
+    const float *corpus, *queries;
+    uint32_t n_rows, dims, n_queries, groups, slices, kprime, k;
+    int metric;
+    const uint64_t *heaps;
+    const uint32_t *max_norm_bits;
+    wax_vs_candidate *out;      // [n_queries][k]
+    uint32_t *ok;               // [n_queries] 1 = proven exact, 0 = re-run on the exact path
+    const uint64_t *frame_ids;
+    uint64_t id_base, row_offset;
+    uint32_t pow2_all;          // next pow2 >= slices*kprime
+};
+
+// One CTA per query.
+template <int METRIC>
+__global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p) {
+    extern __shared__ uint64_t fsm[];
+    uint64_t *sk = fsm;                 // [pow2_all] nominee keys of every slice
+    uint64_t *ek = fsm + p.pow2_all;    // [256] exact keys
+    __shared__ float s_a2, s_sqrt_a2;
+    __shared__ uint32_t s_valid;
+    const uint32_t q = blockIdx.x, g = q / kBatchM, t = q % kBatchM;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float *qv = p.queries + static_cast<size_t>(q) * p.dims;
+
+    if (threadIdx.x == 0) s_valid = 0;
+    const uint32_t total = p.slices * p.kprime;
+    for (uint32_t i = threadIdx.x; i < p.pow2_all; i += blockDim.x) {
+        uint64_t key = WAXVS_KEY_NONE;
+        if (i < total) {
+            const uint32_t s = i / p.kprime, e = i % p.kprime;
+            key = p.heaps[(static_cast<size_t>(s * p.groups + g) * kBatchM + t) * p.kprime + e];
+        }
+        sk[i] = key;
+    }
+    if (warp == 0) {  // |q|^2 in the kernels' order
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (uint32_t base = 4u * lane; base < p.dims; base += 128u) {
+            const float x = __ldg(qv + base); s0 = __fmaf_rn(x, x, s0);
+            if (base + 1 < p.dims) { const float y = __ldg(qv + base + 1); s1 = __fmaf_rn(y, y, s1); }
+            if (base + 2 < p.dims) { const float z = __ldg(qv + base + 2); s2 = __fmaf_rn(z, z, s2); }
+            if (base + 3 < p.dims) { const float w = __ldg(qv + base + 3); s3 = __fmaf_rn(w, w, s3); }
+        }
+        const float a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
+        if (lane == 0) { s_a2 = a2; s_sqrt_a2 = __fsqrt_rn(a2); }
+    }
+    __syncthreads();
+    block_bitonic_sort(sk, p.pow2_all);   // best nominees first
+
+    // how many real nominees exist (any slice heap that is full holds kprime of them)
+    uint32_t cnt = 0;
+    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) cnt += (sk[i] != WAXVS_KEY_NONE) ? 1u : 0u;
+    if (cnt) atomicAdd(&s_valid, cnt);
+    __syncthreads();
+    const uint32_t n_valid = s_valid;
+    const uint32_t kpp = min(p.kprime, n_valid);
+    const bool excluded_any = n_valid >= p.kprime;   // otherwise no heap ever overflowed: nothing was dropped
+    const float tau = excluded_any ? nominee_score(sk[p.kprime - 1]) : -INFINITY;
+
+    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) ek[i] = WAXVS_KEY_NONE;
+    __syncthreads();
+    for (uint32_t i = warp; i < kpp; i += (blockDim.x >> 5)) {
+        const uint32_t row = static_cast<uint32_t>(sk[i]);
+        const float d = exact_row_distance<METRIC>(qv, p.corpus + static_cast<size_t>(row) * p.dims, p.dims, s_a2,
+                                                   s_sqrt_a2, lane);
+        if (lane == 0) ek[i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
+    }
+    __syncthreads();
+    block_bitonic_sort(ek, 256);
+
+    if (threadIdx.x == 0) {
+        uint32_t n_exact = 0;
+        while (n_exact < kpp && ek[n_exact] != WAXVS_KEY_NONE) ++n_exact;
+        uint32_t ok = 1;
+        if (excluded_any) {
+            if (n_exact < p.k) ok = 0;
+            else {
+                const float dk = from_orderable_u32(static_cast<uint32_t>(ek[p.k - 1] >> 32));
+                const float qn = s_sqrt_a2;
+                float sk_exact, eps;
+                if (METRIC == kCosine) { sk_exact = (1.0f - dk) * qn; eps = kTf32Eps * qn; }
+                else { sk_exact = 1.0f - dk; eps = kTf32Eps * qn * __uint_as_float(*p.max_norm_bits); }
+                eps = eps * 1.01f + 1e-30f;
+                if (!(sk_exact > tau + eps) || !finite_f32(eps)) ok = 0;
+            }
+        }
+        p.ok[q] = ok;
+    }
+    ScanParams sp{};
+    sp.out = p.out + static_cast<size_t>(q) * p.k;
+    sp.frame_ids = p.frame_ids; sp.id_base = p.id_base; sp.row_offset = p.row_offset;
+    for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x) write_candidate(sp, static_cast<int>(i), i < 256 ? ek[i] : WAXVS_KEY_NONE);
+}
+
+}  // namespace waxvs

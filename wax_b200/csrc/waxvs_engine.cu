@@ -28,6 +28,9 @@
 #include "waxvs_scan.cuh"
 #include "waxvs_select.cuh"
 #include "waxvs_synth.cuh"
+#include "waxvs_batch.cuh"
+
+#include <cudaTypedefs.h>
 
 using namespace waxvs;
 
@@ -108,6 +111,9 @@ struct Tuning {
     int grid = 0;         // 0 = one CTA per SM
     int l2_hint = 0;
     int ldg_ctas_per_sm = 4;
+    int chunk_steps = 16;   // dynamic scheduling granularity of the TMA kernel (0 = static round-robin)
+    int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
+    int batch_min = 4;      // smallest batch routed to the tensor path
 };
 
 // Per-search scratch: the analogue of TransientBuffers (MetalVectorEngine.swift:36-41, :84-117).
@@ -124,6 +130,9 @@ struct SearchCtx {
     SelectState *d_select = nullptr;
     uint64_t *d_sel_keys = nullptr;                               // 16384 u64
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    uint64_t *d_heaps = nullptr; size_t heaps_cap = 0;            // batched path: nominee heaps
+    uint32_t *d_ok = nullptr; size_t ok_cap = 0;                  // batched path: per-query proof flags
+    uint32_t *h_ok = nullptr; size_t h_ok_cap = 0;                // pinned
 };
 
 struct wax_vs_engine {
@@ -151,6 +160,13 @@ struct wax_vs_engine {
     std::unordered_map<void *, SearchCtx *> stream_ctx;  // wax_vs_search_device: one ctx per caller stream
     uint64_t pool_allocs = 0, pool_reuses = 0;
     Tuning tune;
+
+    // cached per corpus version for the batched path: 1/|v| per row and max |v|
+    float *d_inv_norm = nullptr; size_t inv_norm_cap = 0;
+    uint32_t *d_max_norm = nullptr;
+    bool norms_valid = false;
+    std::mutex norms_mu;
+    uint64_t batch_tensor_queries = 0, batch_fallback_queries = 0;   // instrumentation
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -166,6 +182,9 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_dist_keys) cudaFree(c->d_dist_keys);
     if (c->d_select) cudaFree(c->d_select);
     if (c->d_sel_keys) cudaFree(c->d_sel_keys);
+    if (c->d_heaps) cudaFree(c->d_heaps);
+    if (c->d_ok) cudaFree(c->d_ok);
+    if (c->h_ok) cudaFreeHost(c->h_ok);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
     if (c->own_stream && c->stream) cudaStreamDestroy(c->stream);
@@ -183,8 +202,8 @@ static int32_t ctx_new(wax_vs_engine *e, SearchCtx **out, bool with_stream) {
     }
     c->block_keys_cap = static_cast<size_t>(std::max(e->sm_count * 8, 2048)) * 32;
     if (cudaMalloc(&c->d_block_keys, c->block_keys_cap * sizeof(uint64_t)) != cudaSuccess ||
-        cudaMalloc(&c->d_ticket, sizeof(uint32_t)) != cudaSuccess ||
-        cudaMemset(c->d_ticket, 0, sizeof(uint32_t)) != cudaSuccess ||
+        cudaMalloc(&c->d_ticket, 4 * sizeof(uint32_t)) != cudaSuccess ||      // [0] ticket, [1] work counter
+        cudaMemset(c->d_ticket, 0, 4 * sizeof(uint32_t)) != cudaSuccess ||
         cudaEventCreate(&c->ev0) != cudaSuccess || cudaEventCreate(&c->ev1) != cudaSuccess)
         return bail(fail(WAX_VS_ERR_CUDA, "failed to allocate search scratch: %s",
                          cudaGetErrorString(cudaGetLastError())));
@@ -247,12 +266,10 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     warps = std::max(1, std::min(16, warps));
     const size_t budget = e->smem_optin ? e->smem_optin : 232448;
     const size_t stage_bytes = static_cast<size_t>(R) * d * 4;
-    auto smem_for = [&](int st) { return static_cast<size_t>(warps) * st * (stage_bytes + 8) + static_cast<size_t>(warps) * 256; };
-    int stages = e->tune.stages;
-    if (stages <= 0) {
-        stages = 8;
-        while (stages > 2 && smem_for(stages) > budget) --stages;
-    }
+    auto smem_for = [&](int st) { return static_cast<size_t>(warps) * st * (stage_bytes + 8 + 4) + static_cast<size_t>(warps) * 256; };
+    // Default ring depth 2: measured best on B200 (profiles/sweep_r01_call2.json: ~48 KB in flight per SM beats
+    // deeper rings by 5-10 %).
+    int stages = e->tune.stages > 0 ? e->tune.stages : 2;
     if (stages < 1 || smem_for(stages) > budget) return false;
     cfg->C = C; cfg->R = R; cfg->warps = warps; cfg->stages = stages; cfg->smem = smem_for(stages);
     return true;
@@ -313,6 +330,8 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     p.block_keys = c->d_block_keys; p.ticket = c->d_ticket; p.out = d_out;
     p.frame_ids = d_ids; p.id_base = e->id_base; p.row_offset = row_offset;
     p.use_l2_hint = e->tune.l2_hint ? 1u : 0u;
+    p.chunk_steps = e->tune.chunk_steps > 0 ? static_cast<uint32_t>(e->tune.chunk_steps) : 0u;
+    p.work_counter = c->d_ticket + 1;
 
     const bool emit = k_eff > 32;
     if (emit) {
@@ -363,6 +382,123 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         select_sort_kernel<<<1, 1024, pow2 * sizeof(uint64_t), stream>>>(c->d_select, c->d_sel_keys, pow2, p);
         CUDA_TRY(cudaGetLastError());
         *launches += 3 + 2 * kSelectPasses;
+    }
+    return WAX_VS_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// batched path: tcgen05 TF32 nomination + exact re-score (waxvs_batch.cuh)
+static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+    });
+    return fn;
+}
+
+// Row-major [rows][dims] fp32 matrix, box = box_rows x 32 floats (128 B), 128-byte swizzle, OOB -> zeros.
+static int32_t make_tensor_map(CUtensorMap *map, const float *base, uint64_t rows, uint32_t dims, uint32_t box_rows) {
+    auto enc = tensor_map_encoder();
+    if (!enc) return fail(WAX_VS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const cuuint64_t gdim[2] = {dims, rows};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dims) * sizeof(float)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBatchKBlock), box_rows};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
+                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(WAX_VS_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
+    return WAX_VS_OK;
+}
+
+static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, uint32_t k_eff) {
+    return e->tune.batch_tensor && n_queries >= static_cast<uint32_t>(std::max(e->tune.batch_min, 1)) &&
+           (e->similarity == WAX_VS_COSINE || e->similarity == WAX_VS_DOT) && e->dims % kBatchKBlock == 0 &&
+           k_eff >= 1 && k_eff <= 128 && e->n_rows >= 1;
+}
+
+static uint32_t batch_kprime(uint32_t k_eff) {
+    const uint32_t want = std::max(2 * k_eff, k_eff + 54);
+    uint32_t kp = 64;
+    while (kp < want) kp <<= 1;
+    return std::min<uint32_t>(kp, 256);
+}
+
+// 1/|v| per row + max |v|, cached until the corpus changes.
+static int32_t ensure_norms(wax_vs_engine *e, cudaStream_t stream) {
+    std::lock_guard<std::mutex> g(e->norms_mu);
+    if (e->norms_valid) return WAX_VS_OK;
+    int32_t rc = ensure_dev(&e->d_inv_norm, &e->inv_norm_cap, static_cast<size_t>(std::max<uint64_t>(e->n_rows, 1)), "row norms");
+    if (rc) return rc;
+    if (!e->d_max_norm) CUDA_TRY(cudaMalloc(&e->d_max_norm, sizeof(uint32_t)));
+    CUDA_TRY(cudaMemsetAsync(e->d_max_norm, 0, sizeof(uint32_t), stream));
+    row_norms_kernel<<<e->sm_count * 8, 256, 0, stream>>>(e->d_corpus, static_cast<uint32_t>(e->n_rows), e->dims,
+                                                           e->d_inv_norm, e->d_max_norm);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    e->norms_valid = true;
+    return WAX_VS_OK;
+}
+
+// Enqueue the tensor-core nomination + exact finish for n_queries device-resident queries.  d_ok[i] = 1 when
+// query i's result is proven exact; the caller re-runs the others through enqueue_search.
+static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
+                                    uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, uint32_t *d_ok,
+                                    const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
+    int32_t rc = ensure_norms(e, stream);
+    if (rc) return rc;
+    const uint32_t kprime = batch_kprime(k_eff);
+    const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + kBatchN - 1) / kBatchN);
+    const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(batch_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmemBytes));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kDot>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
+    });
+    if (attr_err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+
+    CUtensorMap map_c;
+    if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, kBatchN))) return rc;
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += max_groups * kBatchM) {
+        const uint32_t nq = std::min<uint32_t>(n_queries - q0, max_groups * kBatchM);
+        const uint32_t groups = (nq + kBatchM - 1) / kBatchM;
+        uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(e->sm_count) / groups, tiles_total));
+        slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));
+        const uint32_t grid = groups * slices;
+        if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
+        CUtensorMap map_q;
+        const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
+        if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
+
+        BatchParams bp{};
+        bp.n_rows = static_cast<uint32_t>(e->n_rows); bp.dims = e->dims; bp.n_queries = nq; bp.groups = groups;
+        bp.slices = slices; bp.tiles_total = tiles_total; bp.kprime = kprime; bp.metric = e->similarity;
+        bp.row_scale = e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr;
+        bp.heaps = c->d_heaps;
+        batch_tf32_kernel<<<grid, kBatchThreads, kBatchSmemBytes, stream>>>(map_q, map_c, bp);
+        CUDA_TRY(cudaGetLastError());
+
+        FinishParams fp{};
+        fp.corpus = e->d_corpus; fp.queries = qbase; fp.n_rows = bp.n_rows; fp.dims = e->dims; fp.n_queries = nq;
+        fp.groups = groups; fp.slices = slices; fp.kprime = kprime; fp.k = k_eff; fp.metric = e->similarity;
+        fp.heaps = c->d_heaps; fp.max_norm_bits = e->d_max_norm;
+        fp.out = d_out + static_cast<size_t>(q0) * k_eff; fp.ok = d_ok + q0;
+        fp.frame_ids = d_ids; fp.id_base = e->id_base; fp.row_offset = row_offset;
+        uint32_t pow2 = 256;
+        while (pow2 < slices * kprime) pow2 <<= 1;
+        fp.pow2_all = pow2;
+        const size_t fsmem = static_cast<size_t>(pow2 + 256) * sizeof(uint64_t);
+        if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 256, fsmem, stream>>>(fp);
+        else batch_finish_kernel<kDot><<<nq, 256, fsmem, stream>>>(fp);
+        CUDA_TRY(cudaGetLastError());
+        *launches += 2;
     }
     return WAX_VS_OK;
 }
@@ -501,6 +637,8 @@ void wax_vs_destroy(wax_vs_engine *e) {
         for (auto &kv : e->stream_ctx) ctx_free(kv.second);
         if (e->d_corpus) cudaFree(e->d_corpus);
         if (e->d_ids) cudaFree(e->d_ids);
+        if (e->d_inv_norm) cudaFree(e->d_inv_norm);
+        if (e->d_max_norm) cudaFree(e->d_max_norm);
     }
     delete e;
 }
@@ -562,6 +700,7 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
         if (row != n0 + i) pure_append = false;
     }
     e->d_ids_dirty = true;
+    e->norms_valid = false;
     const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
     if (pure_append) {
         CUDA_TRY(cudaMemcpy(e->d_corpus + n0 * e->dims, rows, n * row_bytes, cudaMemcpyHostToDevice));
@@ -632,6 +771,7 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
     --e->n_rows;
     e->map_valid = false;
     e->d_ids_dirty = true;
+    e->norms_valid = false;
     return WAX_VS_OK;
 }
 
@@ -672,10 +812,34 @@ static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_qu
     memcpy(c->h_queries, queries, qfloats * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     uint64_t launches = 0;
-    for (uint32_t qi = 0; qi < n_queries; ++qi) {
-        rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
-                            c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
+    if (batch_tensor_eligible(e, n_queries, k_eff)) {
+        // Batched: one tensor-core pass over the corpus nominates, the finish kernel re-scores exactly and
+        // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
+        if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
+        if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
+        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        uint64_t failed = 0;
+        for (uint32_t qi = 0; qi < n_queries; ++qi) {
+            if (c->h_ok[qi]) continue;
+            ++failed;
+            rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
+                                c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        }
+        {
+            std::lock_guard<std::mutex> pg(e->pool_mu);
+            e->batch_tensor_queries += n_queries - failed;
+            e->batch_fallback_queries += failed;
+        }
+    } else {
+        for (uint32_t qi = 0; qi < n_queries; ++qi) {
+            rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
+                                c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        }
     }
     CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, ncand * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -819,6 +983,7 @@ int32_t wax_vs_deserialize(wax_vs_engine *e, const uint8_t *src, uint64_t len) {
     e->ids_identity = false;
     e->map_valid = false;
     e->d_ids_dirty = true;
+    e->norms_valid = false;
     return WAX_VS_OK;
 }
 
@@ -851,6 +1016,7 @@ int32_t wax_vs_debug_fill_synthetic(wax_vs_engine *e, uint64_t seed, uint64_t fi
     e->ids_identity = true; e->id_base = id_base;
     e->map = IdMap(); e->map_valid = true;
     e->d_ids_dirty = true;
+    e->norms_valid = false;
     return WAX_VS_OK;
 }
 
@@ -911,7 +1077,7 @@ int32_t wax_vs_debug_stream_read(wax_vs_engine *e, uint32_t iters, float *out_be
     for (uint32_t it = 0; it < iters + 2; ++it) {
         CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
         stream_read_kernel<<<e->sm_count * 4, 512, 0, c->stream>>>(reinterpret_cast<const uint4 *>(e->d_corpus),
-                                                                     bytes / 16, c->d_ticket + 0);
+                                                                     bytes / 16, c->d_ticket + 2);
         CUDA_TRY(cudaGetLastError());
         CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -919,9 +1085,58 @@ int32_t wax_vs_debug_stream_read(wax_vs_engine *e, uint32_t iters, float *out_be
         CUDA_TRY(cudaEventElapsedTime(&ms, c->ev0, c->ev1));
         if (it >= 2 && ms < best) best = ms;
     }
-    CUDA_TRY(cudaMemsetAsync(c->d_ticket, 0, sizeof(uint32_t), c->stream));
+    CUDA_TRY(cudaMemsetAsync(c->d_ticket, 0, 4 * sizeof(uint32_t), c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     *out_best_ms = best;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_debug_batch_stats(wax_vs_engine *e, uint64_t *tensor_queries, uint64_t *fallback_queries) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    std::lock_guard<std::mutex> g(e->pool_mu);
+    if (tensor_queries) *tensor_queries = e->batch_tensor_queries;
+    if (fallback_queries) *fallback_queries = e->batch_fallback_queries;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_debug_time_search_batch(wax_vs_engine *e, uint32_t n_queries, int64_t top_k, uint64_t seed,
+                                       uint32_t warmup, uint32_t iters, float *out_ms_total,
+                                       uint64_t *out_launches, uint32_t *out_unproven) {
+    if (!e || !out_ms_total) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (n_queries == 0) n_queries = 1;
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    DeviceGuard g(e->device);
+    const uint32_t k_eff = static_cast<uint32_t>(std::min<uint64_t>(clamp_topk(top_k), std::max<uint64_t>(e->n_rows, 1)));
+    if (!batch_tensor_eligible(e, n_queries, k_eff))
+        return fail(WAX_VS_ERR_UNSUPPORTED, "batch of %u queries, k=%u, dims=%u is not eligible for the tensor path", n_queries, k_eff, e->dims);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_acquire(e, &c);
+    if (rc) return rc;
+    struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); } } rel{e, c};
+    const size_t qfloats = static_cast<size_t>(n_queries) * e->dims;
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, qfloats, "query buffer"))) return rc;
+    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, static_cast<size_t>(n_queries) * k_eff, "result buffer"))) return rc;
+    if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
+    if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
+    synth_fill_kernel<<<(n_queries + 255) / 256, 256, 0, c->stream>>>(c->d_queries, n_queries, e->dims, seed, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    if ((rc = ensure_norms(e, c->stream))) return rc;   // cached per corpus version: outside the timed region
+    uint64_t launches = 0;
+    for (uint32_t it = 0; it < warmup + iters; ++it) {
+        if (it == warmup) { launches = 0; CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); }
+        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(out_ms_total, c->ev0, c->ev1));
+    if (out_launches) *out_launches = launches;
+    if (out_unproven) {
+        uint32_t bad = 0;
+        for (uint32_t i = 0; i < n_queries; ++i) bad += c->h_ok[i] ? 0u : 1u;
+        *out_unproven = bad;
+    }
     return WAX_VS_OK;
 }
 
@@ -935,6 +1150,9 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "warps")) e->tune.warps = v;
     else if (!strcmp(key, "grid")) e->tune.grid = v;
     else if (!strcmp(key, "l2_hint")) e->tune.l2_hint = v;
+    else if (!strcmp(key, "chunk_steps")) e->tune.chunk_steps = v;
+    else if (!strcmp(key, "batch_tensor")) e->tune.batch_tensor = v;
+    else if (!strcmp(key, "batch_min")) e->tune.batch_min = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);
     return WAX_VS_OK;

@@ -43,6 +43,8 @@ struct ScanParams {
     uint64_t id_base;
     uint64_t row_offset;        // added to the reported row (shard offset)
     uint32_t use_l2_hint;       // 1: evict-first policy on the corpus stream
+    uint32_t chunk_steps;       // > 0: dynamic scheduling, warps claim chunks of this many steps from work_counter
+    uint32_t *work_counter;     // zero on entry, zero again on exit (reset by the last CTA)
 };
 
 __device__ __forceinline__ void write_candidate(const ScanParams &p, int slot, uint64_t key) {
@@ -86,7 +88,7 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK &tk, u
     if (warp == 0) {
         for (int w = 1; w < warps; ++w) tk.merge_sorted(lists[w * 32 + lane], lane, k);
         if (lane < k) write_candidate(p, lane, tk.key);
-        if (lane == 0) *p.ticket = 0u;
+        if (lane == 0) { *p.ticket = 0u; if (p.work_counter) *p.work_counter = 0u; }
     }
 }
 
@@ -109,6 +111,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
                      warp * stages;
     uint64_t *lists = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(warps) * stages * STAGE_BYTES) +
                       warps * stages;
+    uint32_t *stage_step = reinterpret_cast<uint32_t *>(lists + warps * 32) + warp * stages;  // step held by each stage
 
     // ---- query chunks in registers + fused |q|^2 (the in-kernel L2 normalisation of the query) ----
     float4 q[C];
@@ -133,14 +136,38 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
     uint64_t policy = 0;
     if (p.use_l2_hint) policy = l2_policy_evict_first();
 
-    auto issue = [&](uint32_t step, uint32_t s) {
+    auto issue = [&](uint32_t step, uint32_t s) {   // lane 0 only
         const uint32_t row0 = step * R;
         const uint32_t rows = min(static_cast<uint32_t>(R), p.n_rows - row0);
         const uint32_t bytes = rows * ROW_BYTES;
+        stage_step[s] = step;                        // released to the warp by the mbarrier arrive below
         mbar_arrive_expect_tx(&bars[s], bytes);
         const float *src = p.corpus + static_cast<size_t>(row0) * (128u * C);
         if (p.use_l2_hint) bulk_copy_g2s_hint(ring + s * STAGE_BYTES, src, bytes, &bars[s], policy);
         else bulk_copy_g2s(ring + s * STAGE_BYTES, src, bytes, &bars[s]);
+    };
+
+    // Step sequence of this warp.  Static: gwarp, gwarp + total_warps, ...  Dynamic (chunk_steps > 0, fused
+    // top-k only): chunks of `chunk_steps` consecutive steps claimed from a global counter, the next claim
+    // always in flight, so SMs that stream faster simply take more chunks (no tail imbalance).
+    const bool dynamic = !EMIT && p.chunk_steps > 0 && p.work_counter != nullptr;
+    const uint32_t chunk = p.chunk_steps;
+    uint32_t cur = gwarp, cur_end = 0, claim_l0 = 0;
+    if (dynamic) {
+        if (lane == 0) { cur = atomicAdd(p.work_counter, chunk); claim_l0 = atomicAdd(p.work_counter, chunk); }
+        cur = __shfl_sync(WAXVS_FULL_MASK, cur, 0);
+        cur_end = min(cur + chunk, n_steps);
+    }
+    auto next_step = [&]() -> uint32_t {             // warp-uniform; >= n_steps when the warp is out of work
+        if (!dynamic) { const uint32_t st = cur; cur = (cur < n_steps) ? cur + total_warps : cur; return st; }
+        if (cur < cur_end) return cur++;
+        if (cur >= n_steps) return n_steps;
+        const uint32_t start = __shfl_sync(WAXVS_FULL_MASK, claim_l0, 0);
+        if (lane == 0 && start < n_steps) claim_l0 = atomicAdd(p.work_counter, chunk);
+        cur = start;
+        cur_end = min(start + chunk, n_steps);
+        if (cur >= n_steps) return n_steps;
+        return cur++;
     };
 
     if (lane == 0) {
@@ -148,11 +175,12 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
         mbar_fence_init();
     }
     __syncwarp();
-    if (lane == 0) {
-        for (uint32_t s = 0; s < stages; ++s) {
-            const uint32_t step = gwarp + s * total_warps;
-            if (step < n_steps) issue(step, s);
-        }
+    uint32_t issued = 0, consumed = 0;
+    for (uint32_t s = 0; s < stages; ++s) {
+        const uint32_t step = next_step();
+        if (step >= n_steps) break;
+        if (lane == 0) issue(step, s);
+        ++issued;
     }
 
     WarpTopK tk;
@@ -160,8 +188,9 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
     const int k = static_cast<int>(p.k);
 
     uint32_t s = 0, parity = 0;
-    for (uint32_t step = gwarp; step < n_steps; step += total_warps) {
+    while (consumed < issued) {
         mbar_wait_parity(&bars[s], parity);
+        const uint32_t step = stage_step[s];
         const float4 *tile = reinterpret_cast<const float4 *>(ring + s * STAGE_BYTES);
 
         float sum0[R], sum1[R];
@@ -188,11 +217,15 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
             sum0[r] = __fadd_rn(__fadd_rn(a0, a1), __fadd_rn(a2_, a3));
             sum1[r] = __fadd_rn(__fadd_rn(b0, b1), __fadd_rn(b2, b3));
         }
-        __syncwarp();  // every lane has consumed this stage: safe to refill it
-        if (lane == 0) {
-            const uint32_t next = step + stages * total_warps;
-            if (next < n_steps) issue(next, s);
+        __syncwarp();  // every lane has consumed this stage (and read stage_step): safe to refill it
+        {
+            const uint32_t next = next_step();
+            if (next < n_steps) {
+                if (lane == 0) issue(next, s);
+                ++issued;
+            }
         }
+        ++consumed;
         if (++s == stages) { s = 0; parity ^= 1u; }
 
         warp_reduce_scatter<R>(sum0, lane);

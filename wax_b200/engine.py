@@ -289,6 +289,19 @@ class CUDAVectorEngine:
                                                 C.byref(ms), C.byref(launches)))
         return ms.value, launches.value
 
+    def batch_stats(self) -> Tuple[int, int]:
+        """(queries answered by the tensor-core path with a completed proof, queries re-run exactly)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        _check(L.lib().wax_vs_debug_batch_stats(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def time_search_batch(self, n_queries: int, top_k: int, iters: int, warmup: int = 2, seed: int = 7):
+        """Device-only timing of the batched path. Returns (ms_total, launches, unproven_in_last_step)."""
+        ms, launches, bad = C.c_float(0), C.c_uint64(0), C.c_uint32(0)
+        _check(L.lib().wax_vs_debug_time_search_batch(self._h, n_queries, int(top_k), seed, warmup, iters,
+                                                      C.byref(ms), C.byref(launches), C.byref(bad)))
+        return ms.value, launches.value, bad.value
+
     def stream_read_gbs(self, iters: int = 5) -> float:
         """Plain coalesced read of the corpus bytes: the box's streaming-read ceiling in GB/s."""
         ms, nbytes = C.c_float(0), C.c_uint64(0)
