@@ -276,22 +276,29 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     small = shard_bytes <= 4 * 126e6
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
 
-    def step_device(i):
-        if small:
-            flush.fill_(i & 0xFF)
-        return eng.search_async(qs_dev[i % n_distinct], TOP_K)
+    depth = max(1, args.pipeline)      # independent queries in flight (throughput metric): host merge of
+                                       # query i overlaps the scan + all-gather of query i+1
 
-    # ---- value: inputs resident in HBM; per step = local fused kernel + all-gather + D2H of the candidates
-    for i in range(warm):
-        eng.finish(step_device(i))
+    def run_steps(n, query_of):
+        from collections import deque
+        pending, last = deque(), None
+        for i in range(n):
+            if small:
+                flush.fill_(i & 0xFF)
+            pending.append(eng.search_async(query_of(i), TOP_K, slot=i % depth))
+            if len(pending) == depth:
+                last = eng.finish(pending.popleft())
+        while pending:
+            last = eng.finish(pending.popleft())
+        return last
+
+    # ---- value: inputs resident in HBM; per step = local fused kernel + all-gather + D2H + host merge
+    run_steps(warm, lambda i: qs_dev[i % n_distinct])
     dist.barrier(); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         ev0.record()
-        for i in range(args.steps):
-            h = step_device(i)
-            # buffers are per-k singletons: merge each step before reusing them
-            last = eng.finish(h)
+        last = run_steps(args.steps, lambda i: qs_dev[i % n_distinct])
         ev1.record()
         torch.cuda.synchronize(); dist.barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
@@ -299,17 +306,16 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         ms_total = float(ms.item())
 
         # ---- e2e: host query -> H2D -> scan -> all-gather -> D2H -> host merge, every step
-        d_q = torch.empty(DIMS, dtype=torch.float32, device="cuda")
-        for i in range(warm):
+        d_qs = [torch.empty(DIMS, dtype=torch.float32, device="cuda") for _ in range(depth)]
+
+        def host_query(i):
+            d_q = d_qs[i % depth]
             d_q.copy_(qs_pinned[i % n_distinct], non_blocking=True)
-            eng.finish(eng.search_async(d_q, TOP_K))
+            return d_q
+        run_steps(warm, host_query)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        for i in range(args.steps):
-            if small:
-                flush.fill_(i & 0xFF)
-            d_q.copy_(qs_pinned[i % n_distinct], non_blocking=True)
-            last = eng.finish(eng.search_async(d_q, TOP_K))
+        last = run_steps(args.steps, host_query)
         torch.cuda.synchronize(); dist.barrier()
         e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
         dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
@@ -331,7 +337,7 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": DIMS * 4,
                     "d2h_bytes_per_step": world * TOP_K * 24, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "ShardedVectorEngine.search_async/finish (host query -> host ids/scores on every rank)"},
-            "gpu_launches": args.steps, "collective": f"1 all_gather_into_tensor of {TOP_K * 24} B per rank per step (nccl)",
+            "gpu_launches": args.steps, "queries_in_flight": depth, "collective": f"1 all_gather_into_tensor of {TOP_K * 24} B per rank per step (nccl)",
             "clocks": clocks,
             "check": {"top1_frame_id": last[0][0], "top1_score": last[0][1]},
         }
@@ -348,6 +354,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS, help="override the corpus size (experiments only)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning option key=value (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--pipeline", type=int, default=2, help="N>1: independent queries in flight per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -111,7 +111,7 @@ struct Tuning {
     int grid = 0;         // 0 = one CTA per SM
     int l2_hint = 0;
     int ldg_ctas_per_sm = 4;
-    int chunk_steps = 16;   // dynamic scheduling granularity of the TMA kernel (0 = static round-robin)
+    int chunk_steps = 8;    // dynamic scheduling granularity of the TMA kernel (0 = static round-robin)
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
 };

@@ -87,9 +87,9 @@ class ShardedVectorEngine:
                                    normalize=normalize)
 
     # -- search
-    def _buffers(self, k: int):
+    def _buffers(self, k: int, slot: int = 0):
         torch = self._torch
-        key = k
+        key = (k, slot)
         if key not in self._bufs:
             local = torch.zeros(k * 24, dtype=torch.uint8, device=self.device)
             gathered = torch.zeros(self.world_size * k * 24, dtype=torch.uint8, device=self.device)
@@ -98,11 +98,13 @@ class ShardedVectorEngine:
             self._bufs[key] = (local, gathered, host)
         return self._bufs[key]
 
-    def search_async(self, d_query, top_k: int):
-        """Enqueue local scan + all-gather + D2H on the current stream; returns a handle for finish()."""
+    def search_async(self, d_query, top_k: int, slot: int = 0):
+        """Enqueue local scan + all-gather + D2H on the current stream; returns a handle for finish().
+        Queries are independent, so several may be in flight: give each a distinct `slot` (its result buffers)
+        and finish() them in order -- the host merge of query i then overlaps the scan of query i+1."""
         torch, dist = self._torch, self._dist
         k = clamp_topk(top_k)
-        local, gathered, host = self._buffers(k)
+        local, gathered, host = self._buffers(k, slot)
         if self._local_search is not None:
             cands = np.ascontiguousarray(self._local_search(np.asarray(d_query, np.float32), k), dtype=CAND_DTYPE)
             local.copy_(torch.from_numpy(cands.view(np.uint8).reshape(-1).copy()))
