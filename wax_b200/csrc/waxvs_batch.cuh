@@ -37,7 +37,9 @@ constexpr int kBatchStages = 4;
 constexpr uint32_t kBatchABytes = kBatchM * 128u;   // 16 KB
 constexpr uint32_t kBatchBBytes = kBatchN * 128u;   // 32 KB
 constexpr uint32_t kBatchStageBytes = kBatchABytes + kBatchBBytes;
-constexpr uint32_t kBatchSmemBytes = kBatchStages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ + 1024 /*align*/;
+constexpr int kBatchStageSlots = 8;      // staged nominees per epilogue thread before a forced flush
+constexpr uint32_t kBatchSmemBytes = kBatchStages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ +
+                                     kBatchStageSlots * kBatchM * 8 /*nominee staging*/ + 1024 /*align*/;
 constexpr int kBatchThreads = 192;
 constexpr float kTf32Eps = 1.25f * 0x1p-9f;
 
@@ -50,6 +52,8 @@ struct BatchParams {
     int metric;             // kCosine or kDot
     const float *row_scale; // [n_rows] 1/|v| (cosine) or nullptr
     uint64_t *heaps;        // [slices*groups][128][kprime]
+    uint32_t *tau_global;   // [n_queries] orderable(score') of the best k'-th nominee any slice has reached (0 = none)
+    uint32_t no_insert;     // instrumentation: skip nominations (timing floor of the GEMM pipeline)
 };
 
 // ---- PTX wrappers (tcgen05 / TMA tensor) ---------------------------------------------------------------------
@@ -122,7 +126,7 @@ __device__ __forceinline__ uint64_t nominee_key(float score, uint32_t row) {
 }
 __device__ __forceinline__ float nominee_score(uint64_t key) { return -from_orderable_u32(static_cast<uint32_t>(key >> 32)); }
 
-__device__ __forceinline__ float heap_replace_root(uint64_t *heap, uint32_t n, uint64_t x) {
+__device__ __noinline__ uint64_t heap_replace_root(uint64_t *heap, uint32_t n, uint64_t x) {
     uint32_t i = 0;
     for (;;) {
         const uint32_t l = 2 * i + 1;
@@ -137,8 +141,7 @@ __device__ __forceinline__ float heap_replace_root(uint64_t *heap, uint32_t n, u
         i = c;
     }
     heap[i] = x;
-    const uint64_t root = heap[0];
-    return root == WAXVS_KEY_NONE ? -INFINITY : nominee_score(root);
+    return i == 0 ? x : heap[0];
 }
 
 // ---- row norms (cached per corpus version) --------------------------------------------------------------------
@@ -189,6 +192,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t *tmem_full = empty + kBatchStages;                                              // [2]
     uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + kBatchStages * kBatchStageBytes + 2048 + 256);  // [slots][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t group = blockIdx.x % p.groups, slice = blockIdx.x / p.groups;
@@ -258,12 +262,28 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
     } else {
         // ===== epilogue: thread t <-> query group*128 + t <-> TMEM lane t =====
+        // A nominee costs one compare against tau in the hot loop; winners are STAGED in shared memory and the
+        // whole warp flushes together (every lane sifts its own heap concurrently) so a lane's insert never idles
+        // the other 31.  tau is also shared across the slices of a query through tau_global: any slice's k'-th
+        // best is a valid filter for all of them (the union then holds >= k' nominees at or above it).
         const uint32_t tid = threadIdx.x;                              // 0..127
         const uint32_t q = group * kBatchM + tid;
-        const bool q_valid = q < p.n_queries;
+        const bool q_valid = q < p.n_queries && !p.no_insert;
         uint64_t *heap = p.heaps + (static_cast<size_t>(blockIdx.x) * kBatchM + tid) * p.kprime;
         for (uint32_t i = 0; i < p.kprime; ++i) heap[i] = WAXVS_KEY_NONE;
+        uint64_t root = WAXVS_KEY_NONE;                               // heap[0]: this slice's k'-th best so far
         float tau = -INFINITY;
+        uint64_t *stage = stage_smem + tid;                           // slot i at stage[i * 128]
+        uint32_t cnt = 0;
+        bool improved = false;
+        auto flush = [&]() {
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint64_t x = stage[i * kBatchM];
+                if (x < root) { root = heap_replace_root(heap, p.kprime, x); improved = true; }
+            }
+            cnt = 0;
+            if (root != WAXVS_KEY_NONE) tau = fmaxf(tau, nominee_score(root));
+        };
         const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
         uint32_t t = 0;
         for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
@@ -276,6 +296,10 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const uint32_t r = row0 + tid + h * 128u;
                     sc[tid + h * 128u] = (r < p.n_rows) ? __ldg(p.row_scale + r) : 0.0f;
                 }
+            }
+            if (q_valid) {                                            // adopt the best threshold any slice has published
+                const uint32_t g = __ldcg(p.tau_global + q);
+                if (g) tau = fmaxf(tau, from_orderable_u32(g));
             }
             asm volatile("bar.sync 1, 128;" ::: "memory");            // scales visible; previous use of sc[] finished
             mbar_wait_parity(&tmem_full[acc], acc_phase);
@@ -291,13 +315,25 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const uint32_t col = chunk * 32u + j;
                     float s = __uint_as_float(v[j]);
                     if (p.row_scale) s *= sc[col];
-                    if (s > tau && col < rows_here && q_valid) tau = heap_replace_root(heap, p.kprime, nominee_key(s, row0 + col));
+                    if (s > tau && col < rows_here && q_valid) {
+                        if (cnt == kBatchStageSlots) flush();         // rare: this lane alone filled its slots
+                        stage[cnt * kBatchM] = nominee_key(s, row0 + col);
+                        ++cnt;
+                    }
                 }
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+            if (lane == 0) mbar_arrive(&tmem_empty[acc]);             // accumulator buffer is free again
+            if (__any_sync(WAXVS_FULL_MASK, cnt >= kBatchStageSlots / 2)) {
+                flush();
+                if (improved && q_valid && root != WAXVS_KEY_NONE) {  // heap full: publish this slice's k'-th best
+                    atomicMax(p.tau_global + q, orderable_u32(nominee_score(root)));
+                    improved = false;
+                }
+            }
         }
+        flush();
     }
     tcgen05_fence_before();
     __syncthreads();

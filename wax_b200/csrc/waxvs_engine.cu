@@ -114,6 +114,7 @@ struct Tuning {
     int chunk_steps = 8;    // dynamic scheduling granularity of the TMA kernel (0 = static round-robin)
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
+    int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
 };
 
 // Per-search scratch: the analogue of TransientBuffers (MetalVectorEngine.swift:36-41, :84-117).
@@ -133,6 +134,7 @@ struct SearchCtx {
     uint64_t *d_heaps = nullptr; size_t heaps_cap = 0;            // batched path: nominee heaps
     uint32_t *d_ok = nullptr; size_t ok_cap = 0;                  // batched path: per-query proof flags
     uint32_t *h_ok = nullptr; size_t h_ok_cap = 0;                // pinned
+    uint32_t *d_tau = nullptr; size_t tau_cap = 0;                // batched path: shared per-query thresholds
 };
 
 struct wax_vs_engine {
@@ -184,6 +186,7 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_sel_keys) cudaFree(c->d_sel_keys);
     if (c->d_heaps) cudaFree(c->d_heaps);
     if (c->d_ok) cudaFree(c->d_ok);
+    if (c->d_tau) cudaFree(c->d_tau);
     if (c->h_ok) cudaFreeHost(c->h_ok);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -473,6 +476,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));
         const uint32_t grid = groups * slices;
         if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
+        if ((rc = ensure_dev(&c->d_tau, &c->tau_cap, static_cast<size_t>(nq), "shared thresholds"))) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->d_tau, 0, nq * sizeof(uint32_t), stream));
         CUtensorMap map_q;
         const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
         if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
@@ -482,6 +487,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         bp.slices = slices; bp.tiles_total = tiles_total; bp.kprime = kprime; bp.metric = e->similarity;
         bp.row_scale = e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr;
         bp.heaps = c->d_heaps;
+        bp.tau_global = c->d_tau;
+        bp.no_insert = e->tune.batch_noinsert ? 1u : 0u;
         batch_tf32_kernel<<<grid, kBatchThreads, kBatchSmemBytes, stream>>>(map_q, map_c, bp);
         CUDA_TRY(cudaGetLastError());
 
@@ -1153,6 +1160,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "chunk_steps")) e->tune.chunk_steps = v;
     else if (!strcmp(key, "batch_tensor")) e->tune.batch_tensor = v;
     else if (!strcmp(key, "batch_min")) e->tune.batch_min = v;
+    else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);
     return WAX_VS_OK;
