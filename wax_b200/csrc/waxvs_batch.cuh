@@ -184,7 +184,9 @@ __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                   const BatchParams p) {
     extern __shared__ uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // 1024-byte alignment for the 128B-swizzled tiles, computed as an OFFSET into the shared array so the compiler
+    // keeps the shared address space (LDS/STS, not generic LD/ST).
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *stages = smem;                                            // [stage][A 16 KB | B 32 KB], 1024-aligned
     float *scale_smem = reinterpret_cast<float *>(smem + kBatchStages * kBatchStageBytes);   // [2][256]
     uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kBatchN);                 // [stages]
@@ -310,15 +312,39 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + lane_base + acc * kBatchN + chunk * 32u, v);
                 if (chunk * 32u >= rows_here) continue;               // warp-uniform
+                // Hot path, branch-free: scale the 32 scores and take their max (fmaxf drops NaNs); only a chunk
+                // whose max beats tau (rare once the heap has warmed up) is examined element by element.
+                float sv[32];
+                if (p.row_scale) {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(sc + chunk * 32u);
 #pragma unroll
-                for (uint32_t j = 0; j < 32; ++j) {
-                    const uint32_t col = chunk * 32u + j;
-                    float s = __uint_as_float(v[j]);
-                    if (p.row_scale) s *= sc[col];
-                    if (s > tau && col < rows_here && q_valid) {
-                        if (cnt == kBatchStageSlots) flush();         // rare: this lane alone filled its slots
-                        stage[cnt * kBatchM] = nominee_key(s, row0 + col);
-                        ++cnt;
+                    for (uint32_t j4 = 0; j4 < 8; ++j4) {
+                        const float4 w = sc4[j4];
+                        sv[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * w.x;
+                        sv[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * w.y;
+                        sv[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * w.z;
+                        sv[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * w.w;
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
+                }
+                float m[16];
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) m[j] = fmaxf(sv[j], sv[j + 16]);
+#pragma unroll
+                for (uint32_t w = 8; w >= 1; w >>= 1)
+#pragma unroll
+                    for (uint32_t j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
+                if (m[0] > tau && q_valid) {                          // rare slow path (per lane)
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) {
+                        const uint32_t col = chunk * 32u + j;
+                        if (sv[j] > tau && col < rows_here) {
+                            if (cnt == kBatchStageSlots) flush();     // rarer still: this lane alone filled its slots
+                            stage[cnt * kBatchM] = nominee_key(sv[j], row0 + col);
+                            ++cnt;
+                        }
                     }
                 }
             }
