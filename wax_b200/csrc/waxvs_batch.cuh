@@ -33,13 +33,16 @@ namespace waxvs {
 constexpr int kBatchM = 128;            // queries per CTA  (UMMA M)
 constexpr int kBatchN = 256;            // corpus rows per tile (UMMA N)
 constexpr int kBatchKBlock = 32;        // floats per k-block = one 128-byte swizzle atom
-constexpr int kBatchStages = 4;
+constexpr int kBatchStages = 3;
+constexpr int kBatchHeap = 64;           // nominees kept per (row slice, query): a max-heap in shared memory
+constexpr int kBatchRescore = 256;       // nominees of the union re-scored exactly per query
 constexpr uint32_t kBatchABytes = kBatchM * 128u;   // 16 KB
 constexpr uint32_t kBatchBBytes = kBatchN * 128u;   // 32 KB
 constexpr uint32_t kBatchStageBytes = kBatchABytes + kBatchBBytes;
 constexpr int kBatchStageSlots = 8;      // staged nominees per epilogue thread before a forced flush
 constexpr uint32_t kBatchSmemBytes = kBatchStages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ +
-                                     kBatchStageSlots * kBatchM * 8 /*nominee staging*/ + 1024 /*align*/;
+                                     kBatchStageSlots * kBatchM * 8 /*nominee staging*/ +
+                                     kBatchHeap * kBatchM * 8 /*heaps*/ + 1024 /*align*/;
 constexpr int kBatchThreads = 192;
 constexpr float kTf32Eps = 1.25f * 0x1p-9f;
 
@@ -48,10 +51,10 @@ struct BatchParams {
     uint32_t groups;        // ceil(n_queries / 128)
     uint32_t slices;        // row slices; CTA b -> (group b % groups, slice b / groups)
     uint32_t tiles_total;   // ceil(n_rows / 256)
-    uint32_t kprime;        // nominees kept per (slice, query)
+    uint32_t kprime;        // == kBatchHeap (kept for the finish kernel's bookkeeping)
     int metric;             // kCosine or kDot
     const float *row_scale; // [n_rows] 1/|v| (cosine) or nullptr
-    uint64_t *heaps;        // [slices*groups][128][kprime]
+    uint64_t *heaps;        // [slices*groups][kBatchHeap][128]: each CTA's heaps, dumped entry-major at the end
     uint32_t *tau_global;   // [n_queries] orderable(score') of the best k'-th nominee any slice has reached (0 = none)
     uint32_t no_insert;     // instrumentation: skip nominations (timing floor of the GEMM pipeline)
 };
@@ -126,21 +129,24 @@ __device__ __forceinline__ uint64_t nominee_key(float score, uint32_t row) {
 }
 __device__ __forceinline__ float nominee_score(uint64_t key) { return -from_orderable_u32(static_cast<uint32_t>(key >> 32)); }
 
-__device__ __noinline__ uint64_t heap_replace_root(uint64_t *heap, uint32_t n, uint64_t x) {
+// `heap` points at this thread's node 0 in shared memory; node i lives at heap[i * kBatchM] (entry-major, so the
+// 32 lanes of a warp touching the same level hit 32 different banks).  Returns the new root.
+__device__ __forceinline__ uint64_t heap_replace_root(uint64_t *heap, uint64_t x) {
     uint32_t i = 0;
+#pragma unroll 1
     for (;;) {
         const uint32_t l = 2 * i + 1;
-        if (l >= n) break;
+        if (l >= kBatchHeap) break;
         const uint32_t r = l + 1;
-        const uint64_t kl = heap[l];
-        const uint64_t kr = (r < n) ? heap[r] : 0ull;
+        const uint64_t kl = heap[l * kBatchM];
+        const uint64_t kr = (r < kBatchHeap) ? heap[r * kBatchM] : 0ull;
         const uint32_t c = (kr > kl) ? r : l;
         const uint64_t kc = (kr > kl) ? kr : kl;
         if (kc <= x) break;
-        heap[i] = kc;
+        heap[i * kBatchM] = kc;
         i = c;
     }
-    heap[i] = x;
+    heap[i * kBatchM] = x;
     return i == 0 ? x : heap[0];
 }
 
@@ -195,6 +201,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
     uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + kBatchStages * kBatchStageBytes + 2048 + 256);  // [slots][128]
+    uint64_t *heap_smem = stage_smem + kBatchStageSlots * kBatchM;                                            // [64][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t group = blockIdx.x % p.groups, slice = blockIdx.x / p.groups;
@@ -271,8 +278,8 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t tid = threadIdx.x;                              // 0..127
         const uint32_t q = group * kBatchM + tid;
         const bool q_valid = q < p.n_queries && !p.no_insert;
-        uint64_t *heap = p.heaps + (static_cast<size_t>(blockIdx.x) * kBatchM + tid) * p.kprime;
-        for (uint32_t i = 0; i < p.kprime; ++i) heap[i] = WAXVS_KEY_NONE;
+        uint64_t *heap = heap_smem + tid;
+        for (uint32_t i = 0; i < kBatchHeap; ++i) heap[i * kBatchM] = WAXVS_KEY_NONE;
         uint64_t root = WAXVS_KEY_NONE;                               // heap[0]: this slice's k'-th best so far
         float tau = -INFINITY;
         uint64_t *stage = stage_smem + tid;                           // slot i at stage[i * 128]
@@ -281,7 +288,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         auto flush = [&]() {
             for (uint32_t i = 0; i < cnt; ++i) {
                 const uint64_t x = stage[i * kBatchM];
-                if (x < root) { root = heap_replace_root(heap, p.kprime, x); improved = true; }
+                if (x < root) { root = heap_replace_root(heap, x); improved = true; }
             }
             cnt = 0;
             if (root != WAXVS_KEY_NONE) tau = fmaxf(tau, nominee_score(root));
@@ -360,6 +367,9 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
         }
         flush();
+        // dump this CTA's heaps (entry-major, coalesced) for batch_finish_kernel
+        uint64_t *dst = p.heaps + static_cast<size_t>(blockIdx.x) * kBatchHeap * kBatchM + tid;
+        for (uint32_t i = 0; i < kBatchHeap; ++i) dst[i * kBatchM] = heap[i * kBatchM];
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -429,28 +439,39 @@ struct FinishParams {
     uint32_t pow2_all;          // next pow2 >= slices*kprime
 };
 
-// One CTA per query.
+// One CTA per query.  Union of the slices' nominee heaps -> best kBatchRescore by score' -> exact re-score ->
+// proof.  Rows that were never nominated have score' <= tau_excl = max over slices of that slice's final heap
+// root (a slice only ever filtered by its own root or by a root another slice had published); nominated rows
+// beyond the first kBatchRescore have score' <= the (kBatchRescore+1)-th nominee.
 template <int METRIC>
 __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p) {
     extern __shared__ uint64_t fsm[];
     uint64_t *sk = fsm;                 // [pow2_all] nominee keys of every slice
-    uint64_t *ek = fsm + p.pow2_all;    // [256] exact keys
+    uint64_t *ek = fsm + p.pow2_all;    // [kBatchRescore] exact keys
     __shared__ float s_a2, s_sqrt_a2;
-    __shared__ uint32_t s_valid;
+    __shared__ uint32_t s_valid, s_excl;
     const uint32_t q = blockIdx.x, g = q / kBatchM, t = q % kBatchM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *qv = p.queries + static_cast<size_t>(q) * p.dims;
 
-    if (threadIdx.x == 0) s_valid = 0;
-    const uint32_t total = p.slices * p.kprime;
+    if (threadIdx.x == 0) { s_valid = 0; s_excl = 0; }
+    __syncthreads();
+    const uint32_t total = p.slices * kBatchHeap;
+    uint32_t cnt = 0;
     for (uint32_t i = threadIdx.x; i < p.pow2_all; i += blockDim.x) {
         uint64_t key = WAXVS_KEY_NONE;
         if (i < total) {
-            const uint32_t s = i / p.kprime, e = i % p.kprime;
-            key = p.heaps[(static_cast<size_t>(s * p.groups + g) * kBatchM + t) * p.kprime + e];
+            const uint32_t s = i / kBatchHeap, e = i % kBatchHeap;
+            key = p.heaps[(static_cast<size_t>(s * p.groups + g) * kBatchHeap + e) * kBatchM + t];
+            if (key != WAXVS_KEY_NONE) {
+                ++cnt;
+                // node 0 is the slice's root: real only when its heap filled up, i.e. when it could exclude rows
+                if (e == 0) atomicMax(&s_excl, orderable_u32(nominee_score(key)));
+            }
         }
         sk[i] = key;
     }
+    if (cnt) atomicAdd(&s_valid, cnt);
     if (warp == 0) {  // |q|^2 in the kernels' order
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
         for (uint32_t base = 4u * lane; base < p.dims; base += 128u) {
@@ -465,17 +486,13 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
     __syncthreads();
     block_bitonic_sort(sk, p.pow2_all);   // best nominees first
 
-    // how many real nominees exist (any slice heap that is full holds kprime of them)
-    uint32_t cnt = 0;
-    for (uint32_t i = threadIdx.x; i < total; i += blockDim.x) cnt += (sk[i] != WAXVS_KEY_NONE) ? 1u : 0u;
-    if (cnt) atomicAdd(&s_valid, cnt);
-    __syncthreads();
     const uint32_t n_valid = s_valid;
-    const uint32_t kpp = min(p.kprime, n_valid);
-    const bool excluded_any = n_valid >= p.kprime;   // otherwise no heap ever overflowed: nothing was dropped
-    const float tau = excluded_any ? nominee_score(sk[p.kprime - 1]) : -INFINITY;
+    const uint32_t kpp = min(static_cast<uint32_t>(kBatchRescore), n_valid);
+    float tau = s_excl ? from_orderable_u32(s_excl) : -INFINITY;                     // never-nominated rows
+    if (n_valid > kBatchRescore) tau = fmaxf(tau, nominee_score(sk[kBatchRescore]));  // nominated, not re-scored
+    const bool excluded_any = (s_excl != 0u) || (n_valid > kBatchRescore);
 
-    for (uint32_t i = threadIdx.x; i < 256; i += blockDim.x) ek[i] = WAXVS_KEY_NONE;
+    for (uint32_t i = threadIdx.x; i < kBatchRescore; i += blockDim.x) ek[i] = WAXVS_KEY_NONE;
     __syncthreads();
     for (uint32_t i = warp; i < kpp; i += (blockDim.x >> 5)) {
         const uint32_t row = static_cast<uint32_t>(sk[i]);
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
         if (lane == 0) ek[i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
     }
     __syncthreads();
-    block_bitonic_sort(ek, 256);
+    block_bitonic_sort(ek, kBatchRescore);
 
     if (threadIdx.x == 0) {
         uint32_t n_exact = 0;
@@ -507,7 +524,8 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
     ScanParams sp{};
     sp.out = p.out + static_cast<size_t>(q) * p.k;
     sp.frame_ids = p.frame_ids; sp.id_base = p.id_base; sp.row_offset = p.row_offset;
-    for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x) write_candidate(sp, static_cast<int>(i), i < 256 ? ek[i] : WAXVS_KEY_NONE);
+    for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x)
+        write_candidate(sp, static_cast<int>(i), i < kBatchRescore ? ek[i] : WAXVS_KEY_NONE);
 }
 
 }  // namespace waxvs

@@ -425,13 +425,6 @@ static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, ui
            k_eff >= 1 && k_eff <= 128 && e->n_rows >= 1;
 }
 
-static uint32_t batch_kprime(uint32_t k_eff) {
-    const uint32_t want = std::max(2 * k_eff, k_eff + 54);
-    uint32_t kp = 64;
-    while (kp < want) kp <<= 1;
-    return std::min<uint32_t>(kp, 256);
-}
-
 // 1/|v| per row + max |v|, cached until the corpus changes.
 static int32_t ensure_norms(wax_vs_engine *e, cudaStream_t stream) {
     std::lock_guard<std::mutex> g(e->norms_mu);
@@ -455,7 +448,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
-    const uint32_t kprime = batch_kprime(k_eff);
+    const uint32_t kprime = kBatchHeap;
     const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + kBatchN - 1) / kBatchN);
     const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
     static std::once_flag attr_once;
@@ -473,7 +466,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         const uint32_t nq = std::min<uint32_t>(n_queries - q0, max_groups * kBatchM);
         const uint32_t groups = (nq + kBatchM - 1) / kBatchM;
         uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(e->sm_count) / groups, tiles_total));
-        slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));
+        slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));   // union fits the finish sort
         const uint32_t grid = groups * slices;
         if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
         if ((rc = ensure_dev(&c->d_tau, &c->tau_cap, static_cast<size_t>(nq), "shared thresholds"))) return rc;
@@ -498,10 +491,10 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         fp.heaps = c->d_heaps; fp.max_norm_bits = e->d_max_norm;
         fp.out = d_out + static_cast<size_t>(q0) * k_eff; fp.ok = d_ok + q0;
         fp.frame_ids = d_ids; fp.id_base = e->id_base; fp.row_offset = row_offset;
-        uint32_t pow2 = 256;
+        uint32_t pow2 = 512;
         while (pow2 < slices * kprime) pow2 <<= 1;
         fp.pow2_all = pow2;
-        const size_t fsmem = static_cast<size_t>(pow2 + 256) * sizeof(uint64_t);
+        const size_t fsmem = static_cast<size_t>(pow2 + kBatchRescore) * sizeof(uint64_t);
         if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 256, fsmem, stream>>>(fp);
         else batch_finish_kernel<kDot><<<nq, 256, fsmem, stream>>>(fp);
         CUDA_TRY(cudaGetLastError());
