@@ -336,21 +336,47 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
 #pragma unroll
                     for (uint32_t j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
                 }
-                float m[16];
+                // max tree with the intermediate levels kept (strided pairing: node j of a level covers columns
+                // j, j+W, j+2W, ... of the level below)
+                float m16[16], m8[8], m4[4], m2[2];
 #pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) m[j] = fmaxf(sv[j], sv[j + 16]);
+                for (uint32_t j = 0; j < 16; ++j) m16[j] = fmaxf(sv[j], sv[j + 16]);
 #pragma unroll
-                for (uint32_t w = 8; w >= 1; w >>= 1)
+                for (uint32_t j = 0; j < 8; ++j) m8[j] = fmaxf(m16[j], m16[j + 8]);
 #pragma unroll
-                    for (uint32_t j = 0; j < w; ++j) m[j] = fmaxf(m[j], m[j + w]);
-                if (m[0] > tau && q_valid) {                          // rare slow path (per lane)
+                for (uint32_t j = 0; j < 4; ++j) m4[j] = fmaxf(m8[j], m8[j + 4]);
 #pragma unroll
-                    for (uint32_t j = 0; j < 32; ++j) {
+                for (uint32_t j = 0; j < 2; ++j) m2[j] = fmaxf(m4[j], m4[j + 2]);
+                if (fmaxf(m2[0], m2[1]) > tau && q_valid) {
+                    // Rare slow path (per lane): walk down only the branches whose max beats tau -- about ten
+                    // compares for the usual single winner instead of testing all 32 columns.
+                    auto leaf = [&](uint32_t j, float sj) {
                         const uint32_t col = chunk * 32u + j;
-                        if (sv[j] > tau && col < rows_here) {
+                        if (sj > tau && col < rows_here) {
                             if (cnt == kBatchStageSlots) flush();     // rarer still: this lane alone filled its slots
-                            stage[cnt * kBatchM] = nominee_key(sv[j], row0 + col);
+                            stage[cnt * kBatchM] = nominee_key(sj, row0 + col);
                             ++cnt;
+                        }
+                    };
+#pragma unroll
+                    for (uint32_t a = 0; a < 2; ++a) {
+                        if (!(m2[a] > tau)) continue;
+#pragma unroll
+                        for (uint32_t b = 0; b < 2; ++b) {
+                            const uint32_t i4 = a + 2 * b;
+                            if (!(m4[i4] > tau)) continue;
+#pragma unroll
+                            for (uint32_t c = 0; c < 2; ++c) {
+                                const uint32_t i8 = i4 + 4 * c;
+                                if (!(m8[i8] > tau)) continue;
+#pragma unroll
+                                for (uint32_t d = 0; d < 2; ++d) {
+                                    const uint32_t i16 = i8 + 8 * d;
+                                    if (!(m16[i16] > tau)) continue;
+                                    leaf(i16, sv[i16]);
+                                    leaf(i16 + 16, sv[i16 + 16]);
+                                }
+                            }
                         }
                     }
                 }
