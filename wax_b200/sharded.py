@@ -73,10 +73,12 @@ class ShardedVectorEngine:
         self._local_search = local_search
         self.engine = None
         self._bufs = {}
+        self._comm_stream = None
         if local_search is None:
             from .engine import CUDAVectorEngine
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             self.engine = CUDAVectorEngine(metric, dimensions, device=self.device.index)
+            self._comm_stream = torch.cuda.Stream(device=self.device)   # all-gather + D2H overlap the next scan
         else:
             self.device = torch.device("cpu")
 
@@ -116,16 +118,26 @@ class ShardedVectorEngine:
                                               C.c_void_p(stream.cuda_stream))
             if rc != 0:
                 raise RuntimeError(f"wax_vs_search_device rc={rc}: {L.last_error()}")
+        if self._comm_stream is not None:
+            # exchange + D2H on the communication stream: the compute stream is free to start the next query
+            scanned = torch.cuda.Event()
+            scanned.record()
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(scanned)
+                if self.world_size > 1:
+                    dist.all_gather_into_tensor(gathered, local, group=self.group)
+                else:
+                    gathered.copy_(local)
+                host.copy_(gathered, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+            return (host, ev, k)
         if self.world_size > 1:
             dist.all_gather_into_tensor(gathered, local, group=self.group)
         else:
             gathered.copy_(local)
-        host.copy_(gathered, non_blocking=True)
-        ev = None
-        if self.device.type == "cuda":
-            ev = torch.cuda.Event()
-            ev.record()
-        return (host, ev, k)
+        host.copy_(gathered)
+        return (host, None, k)
 
     def finish(self, handle) -> List[Tuple[int, float]]:
         host, ev, k = handle
