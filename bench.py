@@ -354,7 +354,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS, help="override the corpus size (experiments only)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning option key=value (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=2, help="N>1: independent queries in flight per rank")
+    ap.add_argument("--pipeline", type=int, default=4, help="N>1: independent queries in flight per rank")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
