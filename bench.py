@@ -279,26 +279,37 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
     depth = max(1, args.pipeline)      # independent queries in flight (throughput metric): host merge of
                                        # query i overlaps the scan + all-gather of query i+1
 
-    def run_steps(n, query_of):
+    micro = max(1, args.micro)         # queries per exchange: one all-gather carries `micro` queries' candidates
+
+    def run_steps(n, queries_of):
+        """n single-query steps, issued in micro-batches; queries_of(i0, g) -> [g, DIMS] device tensor."""
         from collections import deque
-        pending, last = deque(), None
-        for i in range(n):
+        pending, last, i, b = deque(), None, 0, 0
+        while i < n:
+            g = min(micro, n - i)
             if small:
                 flush.fill_(i & 0xFF)
-            pending.append(eng.search_async(query_of(i), TOP_K, slot=i % depth))
+            pending.append(eng.search_many_async(queries_of(i, g), TOP_K, slot=b % depth))
+            i += g; b += 1
             if len(pending) == depth:
-                last = eng.finish(pending.popleft())
+                last = eng.finish_many(pending.popleft())[-1]
         while pending:
-            last = eng.finish(pending.popleft())
+            last = eng.finish_many(pending.popleft())[-1]
         return last
 
+    def resident(i0, g):
+        j0 = i0 % n_distinct
+        if j0 + g <= n_distinct:
+            return qs_dev[j0:j0 + g]                       # a view: no kernel, queries already resident in HBM
+        return torch.cat([qs_dev[j0:], qs_dev[: g - (n_distinct - j0)]])
+
     # ---- value: inputs resident in HBM; per step = local fused kernel + all-gather + D2H + host merge
-    run_steps(warm, lambda i: qs_dev[i % n_distinct])
+    run_steps(warm, resident)
     dist.barrier(); torch.cuda.synchronize()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
         ev0.record()
-        last = run_steps(args.steps, lambda i: qs_dev[i % n_distinct])
+        last = run_steps(args.steps, resident)
         ev1.record()
         torch.cuda.synchronize(); dist.barrier()
         ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
@@ -306,12 +317,17 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         ms_total = float(ms.item())
 
         # ---- e2e: host query -> H2D -> scan -> all-gather -> D2H -> host merge, every step
-        d_qs = [torch.empty(DIMS, dtype=torch.float32, device="cuda") for _ in range(depth)]
+        d_qs = [torch.empty((micro, DIMS), dtype=torch.float32, device="cuda") for _ in range(depth)]
+        pin_stage = [torch.empty((micro, DIMS), dtype=torch.float32).pin_memory() for _ in range(depth)]
+        counter = [0]
 
-        def host_query(i):
-            d_q = d_qs[i % depth]
-            d_q.copy_(qs_pinned[i % n_distinct], non_blocking=True)
-            return d_q
+        def host_query(i0, g):
+            slot = counter[0] % depth
+            counter[0] += 1
+            for j in range(g):                                    # host queries arrive one by one
+                pin_stage[slot][j].copy_(qs_pinned[(i0 + j) % n_distinct])
+            d_qs[slot][:g].copy_(pin_stage[slot][:g], non_blocking=True)
+            return d_qs[slot][:g]
         run_steps(warm, host_query)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
@@ -337,7 +353,8 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": DIMS * 4,
                     "d2h_bytes_per_step": world * TOP_K * 24, "ms_per_step": e2e_s / args.steps * 1e3,
                     "api": "ShardedVectorEngine.search_async/finish (host query -> host ids/scores on every rank)"},
-            "gpu_launches": args.steps, "queries_in_flight": depth, "collective": f"1 all_gather_into_tensor of {TOP_K * 24} B per rank per step (nccl)",
+            "gpu_launches": args.steps, "queries_in_flight": depth * micro,
+            "collective": f"1 all_gather_into_tensor of {micro} x {TOP_K * 24} B per rank per {micro} steps (nccl)",
             "clocks": clocks,
             "check": {"top1_frame_id": last[0][0], "top1_score": last[0][1]},
         }
@@ -354,7 +371,8 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS, help="override the corpus size (experiments only)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning option key=value (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--pipeline", type=int, default=4, help="N>1: independent queries in flight per rank")
+    ap.add_argument("--pipeline", type=int, default=2, help="N>1: micro-batches in flight per rank")
+    ap.add_argument("--micro", type=int, default=4, help="N>1: queries per exchange (one all-gather carries them all)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -28,6 +28,12 @@ for qi, k in ((0, 10), (1, 32), (2, 72), (3, 1)):
     ok = ok and same
     if rank == 0:
         print(f"k={k}: {'OK' if same else 'MISMATCH'} top1={got[0]}", flush=True)
+qs = o.synth_rows(778, 0, 4, dims, normalize=True)
+many = eng.finish_many(eng.search_many_async(torch.from_numpy(qs).cuda(), 10, slot=0))
+same = many == [eng.search(q, 10) for q in qs]
+ok = ok and same
+if rank == 0:
+    print(f"micro-batched exchange (4 queries, one all-gather): {'OK' if same else 'MISMATCH'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

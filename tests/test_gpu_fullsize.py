@@ -103,3 +103,17 @@ def test_single_rank_sharded_engine(oracle):
     got = eng.search(q, 10)
     rows, _, s = oracle.search_synth(oracle.COSINE, 11, 0, 100_000, DIMS, True, q, 10, mode=oracle.ACC_F32_TREE, threads=8)
     assert [g[0] for g in got] == rows.tolist() and np.array_equal(np.float32([g[1] for g in got]), s)
+
+
+def test_single_rank_micro_batched_exchange(oracle):
+    """search_many_async: several queries, one exchange -- same answers as one query at a time."""
+    import torch
+    eng = sharded.ShardedVectorEngine(VectorMetric.cosine, DIMS, total_rows=60_000)
+    eng.fill_synthetic(12)
+    qs = oracle.synth_rows(1006, 0, 5, DIMS)
+    d_qs = torch.from_numpy(qs).cuda()
+    many = eng.finish_many(eng.search_many_async(d_qs, 10, slot=0))
+    assert many == [eng.search(q, 10) for q in qs]
+    h1 = eng.search_many_async(d_qs[:2], 10, slot=0)
+    h2 = eng.search_many_async(d_qs[2:], 10, slot=1)             # two micro-batches in flight
+    assert eng.finish_many(h1) + eng.finish_many(h2) == many

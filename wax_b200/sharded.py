@@ -79,6 +79,8 @@ class ShardedVectorEngine:
             self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
             self.engine = CUDAVectorEngine(metric, dimensions, device=self.device.index)
             self._comm_stream = torch.cuda.Stream(device=self.device)   # all-gather + D2H overlap the next scan
+            # two scan streams: consecutive queries alternate, so one scan's tail overlaps the next one's prologue
+            self._scan_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
         else:
             self.device = torch.device("cpu")
 
@@ -138,6 +140,62 @@ class ShardedVectorEngine:
             gathered.copy_(local)
         host.copy_(gathered)
         return (host, None, k)
+
+    def search_many_async(self, d_queries, top_k: int, slot: int = 0):
+        """G independent queries (`d_queries`: [G, dims] device tensor) with ONE exchange: G fused scans alternating
+        over two streams, one all-gather of G*k candidates per rank, one D2H.  Returns a handle for finish_many()."""
+        torch, dist = self._torch, self._dist
+        from . import _lib as L
+        g = int(d_queries.shape[0])
+        k = clamp_topk(top_k)
+        key = (k, g, slot)
+        if key not in self._bufs:
+            local = torch.zeros(g * k * 24, dtype=torch.uint8, device=self.device)
+            gathered = torch.zeros(self.world_size * g * k * 24, dtype=torch.uint8, device=self.device)
+            host = torch.zeros(self.world_size * g * k * 24, dtype=torch.uint8, pin_memory=True)
+            self._bufs[key] = (local, gathered, host)
+        local, gathered, host = self._bufs[key]
+        ready = torch.cuda.Event()
+        ready.record()                                   # queries were produced on the current stream
+        scanned = []
+        for si, st in enumerate(self._scan_streams[: min(2, g)]):
+            st.wait_event(ready)
+        q_base, q_stride = d_queries.data_ptr(), d_queries.stride(0) * 4
+        for i in range(g):
+            st = self._scan_streams[i % 2]
+            rc = L.lib().wax_vs_search_device(self.engine.handle, C.c_void_p(q_base + i * q_stride), 1, k,
+                                              self.row_lo, C.c_void_p(local.data_ptr() + i * k * 24),
+                                              C.c_void_p(st.cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"wax_vs_search_device rc={rc}: {L.last_error()}")
+        for st in self._scan_streams[: min(2, g)]:
+            ev = torch.cuda.Event()
+            ev.record(st)
+            scanned.append(ev)
+        with torch.cuda.stream(self._comm_stream):
+            for ev in scanned:
+                self._comm_stream.wait_event(ev)
+            if self.world_size > 1:
+                dist.all_gather_into_tensor(gathered, local, group=self.group)
+            else:
+                gathered.copy_(local)
+            host.copy_(gathered, non_blocking=True)
+            done = torch.cuda.Event()
+            done.record()
+        return (host, done, k, g)
+
+    def finish_many(self, handle) -> List[List[Tuple[int, float]]]:
+        host, done, k, g = handle
+        done.synchronize()
+        cands = host.numpy().view(CAND_DTYPE).reshape(self.world_size, g, k)
+        k_eff = min(k, self.total_rows) if self.total_rows else k
+        sim = self.metric.to_vec_similarity()
+        out = []
+        for i in range(g):
+            best = merge_candidates(cands[:, i, :], k_eff)
+            scores = score_from_distance(sim, best["distance"])
+            out.append([(int(best["frame_id"][j]), float(scores[j])) for j in range(best.size)])
+        return out
 
     def finish(self, handle) -> List[Tuple[int, float]]:
         host, ev, k = handle
