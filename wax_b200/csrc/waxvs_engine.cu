@@ -280,9 +280,17 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
 
 template <int C, int R, int M, bool E>
 static cudaError_t launch_tma_inst(const ScanParams &p, int grid, const TmaConfig &cfg, cudaStream_t s) {
-    cudaError_t err = cudaFuncSetAttribute(scan_tma_kernel<C, R, M, E>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
-    if (err != cudaSuccess) return err;
+    // The opt-in shared-memory limit is per function and per device: set it once (and again only if a larger
+    // ring is requested) instead of on every launch -- it costs more host time than a 10 K-row scan takes.
+    static int granted[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64 || granted[dev] < static_cast<int>(cfg.smem)) {
+        cudaError_t err = cudaFuncSetAttribute(scan_tma_kernel<C, R, M, E>,
+                                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
+        if (err != cudaSuccess) return err;
+        if (dev >= 0 && dev < 64) granted[dev] = static_cast<int>(cfg.smem);
+    }
     scan_tma_kernel<C, R, M, E><<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
     return cudaGetLastError();
 }
