@@ -177,3 +177,22 @@ def test_kernel_variants_agree(oracle):
             eng.set_option(key, opts.get(key, 0))
         assert eng.search(q, 32) == ref, opts
         assert eng.search(q, 100)[:32] == ref, opts
+
+
+@pytest.mark.parametrize("metric", list(VectorMetric))
+def test_fused_k128_lists_agree_with_the_select_path(oracle, metric):
+    """33 <= k <= 128 stays in the fused launch (4 list slots per lane); forcing the emit + radix-select path must
+    give the same bits.  k = 72 is the production candidateLimit (UnifiedSearch.swift:1195-1200)."""
+    corpus = oracle.synth_rows(1200, 0, 30_011, 384, normalize=(metric is not VectorMetric.dot))
+    corpus[100:164] = corpus[99]                       # 65 exact duplicates straddling list slots
+    eng = _engine_from(metric, corpus)
+    q = corpus[99] + oracle.synth_row(1201, 0, 384, True) * np.float32(0.05)
+    for k in (33, 64, 65, 72, 96, 97, 128):
+        eng.set_option("fused_k_max", 128)
+        fused = _check(oracle, eng, metric, corpus, q, k, rel_scale=1.0 if metric is VectorMetric.cosine else 384.0)
+        eng.set_option("fused_k_max", 32)
+        assert eng.search(q, k) == fused
+    eng.set_option("fused_k_max", 128)
+    eng.set_option("variant", 2)                       # generic (direct-load) kernel, same lists
+    assert eng.search(q, 72) == fused[:72] or eng.search(q, 128) == fused
+    assert eng.search(q, 128) == fused

@@ -91,26 +91,56 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[R], int lane) {
     for (; off >= 1; off >>= 1) v[0] = __fadd_rn(v[0], __shfl_xor_sync(WAXVS_FULL_MASK, v[0], off));
 }
 
-// ---- per-warp sorted top-k list (k <= 32): lane i holds the i-th best key ---------------------------------
+// ---- per-warp sorted top-k list in registers: k <= 32*E, entry i lives in key[i / 32] of lane i % 32 ------------
+template <int E>
 struct WarpTopK {
-    uint64_t key;     // this lane's entry (WAXVS_KEY_NONE beyond k)
-    uint64_t thresh;  // key of entry k-1 (warp-uniform): only strictly smaller keys enter
-    __device__ __forceinline__ void init() { key = WAXVS_KEY_NONE; thresh = WAXVS_KEY_NONE; }
-    // x is warp-uniform and x < thresh.
-    __device__ __forceinline__ void insert(uint64_t x, int lane, int k) {
-        const int pos = __popc(__ballot_sync(WAXVS_FULL_MASK, key < x));
-        const uint64_t up = shfl_up_u64(key, 1);
-        if (lane == pos) key = x;
-        else if (lane > pos) key = up;
-        if (lane >= k) key = WAXVS_KEY_NONE;
-        thresh = shfl_u64(key, k - 1);
+    uint64_t key[E];   // sorted ascending over the entry index; WAXVS_KEY_NONE beyond k
+    uint64_t thresh;   // key of entry k-1 (warp-uniform): only strictly smaller keys enter
+    __device__ __forceinline__ void init() {
+#pragma unroll
+        for (int j = 0; j < E; ++j) key[j] = WAXVS_KEY_NONE;
+        thresh = WAXVS_KEY_NONE;
     }
-    // Merge a sorted list held one-entry-per-lane by `other` (entries beyond its length are KEY_NONE).
-    __device__ __forceinline__ void merge_sorted(uint64_t other, int lane, int k) {
-        for (int i = 0; i < k; ++i) {
-            const uint64_t x = shfl_u64(other, i);
-            if (x >= thresh) break;  // sorted: the rest are worse (KEY_NONE never passes)
-            insert(x, lane, k);
+    // x is warp-uniform and x < thresh.  One ballot + one shuffle pair per slot.
+    __device__ __forceinline__ void insert(uint64_t x, int lane, int k) {
+        bool carried = false;          // warp-uniform
+        uint64_t carry = 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const uint64_t up = shfl_up_u64(key[j], 1);
+            const uint64_t last = shfl_u64(key[j], 31);
+            if (!carried) {
+                const int pos = __popc(__ballot_sync(WAXVS_FULL_MASK, key[j] < x));
+                if (pos < 32) {        // x belongs in this slot at lane `pos`
+                    if (lane == pos) key[j] = x;
+                    else if (lane > pos) key[j] = up;
+                    carry = last;
+                    carried = true;
+                }
+            } else {                   // everything after the insertion point moves up by one entry
+                key[j] = (lane == 0) ? carry : up;
+                carry = last;
+            }
+            if (j * 32 + lane >= k) key[j] = WAXVS_KEY_NONE;
+        }
+        uint64_t t = WAXVS_KEY_NONE;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const uint64_t cand = shfl_u64(key[j], (k - 1) & 31);
+            if (((k - 1) >> 5) == j) t = cand;
+        }
+        thresh = t;
+    }
+    // Merge a sorted list held in the same distributed layout by `other` (entries beyond its length KEY_NONE).
+    __device__ __forceinline__ void merge_sorted(const uint64_t (&other)[E], int lane, int k) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            for (int l = 0; l < 32; ++l) {
+                if (j * 32 + l >= k) return;
+                const uint64_t x = shfl_u64(other[j], l);
+                if (x >= thresh) return;  // sorted: the rest are worse (KEY_NONE never passes)
+                insert(x, lane, k);
+            }
         }
     }
 };

@@ -112,6 +112,7 @@ struct Tuning {
     int l2_hint = 0;
     int ldg_ctas_per_sm = 4;
     int chunk_steps = 8;    // dynamic scheduling granularity of the TMA kernel (0 = static round-robin)
+    int fused_k_max = 128;  // k <= this stays in the single fused launch (register lists); larger k: emit + radix select
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
@@ -203,7 +204,7 @@ static int32_t ctx_new(wax_vs_engine *e, SearchCtx **out, bool with_stream) {
             return bail(fail(WAX_VS_ERR_CUDA, "cudaStreamCreate failed"));
         c->own_stream = true;
     }
-    c->block_keys_cap = static_cast<size_t>(std::max(e->sm_count * 8, 2048)) * 32;
+    c->block_keys_cap = static_cast<size_t>(std::max(e->sm_count * 8, 2048)) * 128;
     if (cudaMalloc(&c->d_block_keys, c->block_keys_cap * sizeof(uint64_t)) != cudaSuccess ||
         cudaMalloc(&c->d_ticket, 4 * sizeof(uint32_t)) != cudaSuccess ||      // [0] ticket, [1] work counter
         cudaMemset(c->d_ticket, 0, 4 * sizeof(uint32_t)) != cudaSuccess ||
@@ -269,7 +270,7 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     warps = std::max(1, std::min(16, warps));
     const size_t budget = e->smem_optin ? e->smem_optin : 232448;
     const size_t stage_bytes = static_cast<size_t>(R) * d * 4;
-    auto smem_for = [&](int st) { return static_cast<size_t>(warps) * st * (stage_bytes + 8 + 4) + static_cast<size_t>(warps) * 256; };
+    auto smem_for = [&](int st) { return static_cast<size_t>(warps) * st * (stage_bytes + 8 + 4) + static_cast<size_t>(warps) * 1024; };
     // Default ring depth 2: measured best on B200 (profiles/sweep_r01_call2.json: ~48 KB in flight per SM beats
     // deeper rings by 5-10 %).
     int stages = e->tune.stages > 0 ? e->tune.stages : 2;
@@ -278,7 +279,7 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     return true;
 }
 
-template <int C, int R, int M, bool E>
+template <int C, int R, int M, int E, bool EMIT>
 static cudaError_t launch_tma_inst(const ScanParams &p, int grid, const TmaConfig &cfg, cudaStream_t s) {
     // The opt-in shared-memory limit is per function and per device: set it once (and again only if a larger
     // ring is requested) instead of on every launch -- it costs more host time than a 10 K-row scan takes.
@@ -286,43 +287,50 @@ static cudaError_t launch_tma_inst(const ScanParams &p, int grid, const TmaConfi
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev < 0 || dev >= 64 || granted[dev] < static_cast<int>(cfg.smem)) {
-        cudaError_t err = cudaFuncSetAttribute(scan_tma_kernel<C, R, M, E>,
+        cudaError_t err = cudaFuncSetAttribute(scan_tma_kernel<C, R, M, E, EMIT>,
                                                cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
         if (err != cudaSuccess) return err;
         if (dev >= 0 && dev < 64) granted[dev] = static_cast<int>(cfg.smem);
     }
-    scan_tma_kernel<C, R, M, E><<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
+    scan_tma_kernel<C, R, M, E, EMIT><<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
     return cudaGetLastError();
 }
+// mode: 0 = fused list k <= 32, 1 = fused list k <= 128, 2 = emit distance keys
 template <int C, int R>
-static cudaError_t launch_tma_cr(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, bool emit,
+static cudaError_t launch_tma_cr(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, int mode,
                                  cudaStream_t s) {
-    switch (metric * 2 + (emit ? 1 : 0)) {
-        case 0: return launch_tma_inst<C, R, kCosine, false>(p, grid, cfg, s);
-        case 1: return launch_tma_inst<C, R, kCosine, true>(p, grid, cfg, s);
-        case 2: return launch_tma_inst<C, R, kDot, false>(p, grid, cfg, s);
-        case 3: return launch_tma_inst<C, R, kDot, true>(p, grid, cfg, s);
-        case 4: return launch_tma_inst<C, R, kL2, false>(p, grid, cfg, s);
-        default: return launch_tma_inst<C, R, kL2, true>(p, grid, cfg, s);
+    switch (metric * 3 + mode) {
+        case 0: return launch_tma_inst<C, R, kCosine, 1, false>(p, grid, cfg, s);
+        case 1: return launch_tma_inst<C, R, kCosine, 4, false>(p, grid, cfg, s);
+        case 2: return launch_tma_inst<C, R, kCosine, 1, true>(p, grid, cfg, s);
+        case 3: return launch_tma_inst<C, R, kDot, 1, false>(p, grid, cfg, s);
+        case 4: return launch_tma_inst<C, R, kDot, 4, false>(p, grid, cfg, s);
+        case 5: return launch_tma_inst<C, R, kDot, 1, true>(p, grid, cfg, s);
+        case 6: return launch_tma_inst<C, R, kL2, 1, false>(p, grid, cfg, s);
+        case 7: return launch_tma_inst<C, R, kL2, 4, false>(p, grid, cfg, s);
+        default: return launch_tma_inst<C, R, kL2, 1, true>(p, grid, cfg, s);
     }
 }
-static cudaError_t launch_tma(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, bool emit,
+static cudaError_t launch_tma(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, int mode,
                               cudaStream_t s) {
-#define WAXVS_CASE(Cv, Rv) if (cfg.C == Cv && cfg.R == Rv) return launch_tma_cr<Cv, Rv>(p, grid, cfg, metric, emit, s)
+#define WAXVS_CASE(Cv, Rv) if (cfg.C == Cv && cfg.R == Rv) return launch_tma_cr<Cv, Rv>(p, grid, cfg, metric, mode, s)
     WAXVS_CASE(1, 4); WAXVS_CASE(1, 8); WAXVS_CASE(2, 4); WAXVS_CASE(2, 8);
     WAXVS_CASE(3, 4); WAXVS_CASE(3, 8); WAXVS_CASE(4, 4); WAXVS_CASE(4, 8);
     WAXVS_CASE(6, 2); WAXVS_CASE(6, 4); WAXVS_CASE(8, 2); WAXVS_CASE(8, 4);
 #undef WAXVS_CASE
     return cudaErrorInvalidValue;
 }
-static cudaError_t launch_ldg(const ScanParams &p, int grid, int metric, bool emit, cudaStream_t s) {
-    switch (metric * 2 + (emit ? 1 : 0)) {
-        case 0: scan_ldg_kernel<kCosine, false><<<grid, 256, 0, s>>>(p); break;
-        case 1: scan_ldg_kernel<kCosine, true><<<grid, 256, 0, s>>>(p); break;
-        case 2: scan_ldg_kernel<kDot, false><<<grid, 256, 0, s>>>(p); break;
-        case 3: scan_ldg_kernel<kDot, true><<<grid, 256, 0, s>>>(p); break;
-        case 4: scan_ldg_kernel<kL2, false><<<grid, 256, 0, s>>>(p); break;
-        default: scan_ldg_kernel<kL2, true><<<grid, 256, 0, s>>>(p); break;
+static cudaError_t launch_ldg(const ScanParams &p, int grid, int metric, int mode, cudaStream_t s) {
+    switch (metric * 3 + mode) {
+        case 0: scan_ldg_kernel<kCosine, 1, false><<<grid, 256, 0, s>>>(p); break;
+        case 1: scan_ldg_kernel<kCosine, 4, false><<<grid, 256, 0, s>>>(p); break;
+        case 2: scan_ldg_kernel<kCosine, 1, true><<<grid, 256, 0, s>>>(p); break;
+        case 3: scan_ldg_kernel<kDot, 1, false><<<grid, 256, 0, s>>>(p); break;
+        case 4: scan_ldg_kernel<kDot, 4, false><<<grid, 256, 0, s>>>(p); break;
+        case 5: scan_ldg_kernel<kDot, 1, true><<<grid, 256, 0, s>>>(p); break;
+        case 6: scan_ldg_kernel<kL2, 1, false><<<grid, 256, 0, s>>>(p); break;
+        case 7: scan_ldg_kernel<kL2, 4, false><<<grid, 256, 0, s>>>(p); break;
+        default: scan_ldg_kernel<kL2, 1, true><<<grid, 256, 0, s>>>(p); break;
     }
     return cudaGetLastError();
 }
@@ -344,7 +352,8 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     p.chunk_steps = e->tune.chunk_steps > 0 ? static_cast<uint32_t>(e->tune.chunk_steps) : 0u;
     p.work_counter = c->d_ticket + 1;
 
-    const bool emit = k_eff > 32;
+    const bool emit = k_eff > static_cast<uint32_t>(e->tune.fused_k_max);
+    const int mode = emit ? 2 : (k_eff <= 32 ? 0 : 1);
     if (emit) {
         int32_t rc = ensure_dev(&c->d_dist_keys, &c->dist_keys_cap, static_cast<size_t>(e->n_rows), "distance keys");
         if (rc) return rc;
@@ -358,19 +367,19 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     if (e->tune.variant == 1 && !use_tma)
         return fail(WAX_VS_ERR_UNSUPPORTED, "TMA-staged kernel does not support dims=%u", e->dims);
     int grid;
-    const int grid_cap = static_cast<int>(c->block_keys_cap / 32);
+    const int grid_cap = static_cast<int>(c->block_keys_cap / 128);
     if (use_tma) {
         p.stages = static_cast<uint32_t>(cfg.stages);
         const uint64_t steps = (e->n_rows + cfg.R - 1) / cfg.R;
         const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count;
         grid = static_cast<int>(std::min<uint64_t>(max_grid, (steps + cfg.warps - 1) / cfg.warps));
         grid = std::max(std::min(grid, grid_cap), 1);
-        CUDA_TRY(launch_tma(p, grid, cfg, e->similarity, emit, stream));
+        CUDA_TRY(launch_tma(p, grid, cfg, e->similarity, mode, stream));
     } else {
         const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count * e->tune.ldg_ctas_per_sm;
         grid = static_cast<int>(std::min<uint64_t>(max_grid, (e->n_rows + 7) / 8));
         grid = std::max(std::min(grid, grid_cap), 1);
-        CUDA_TRY(launch_ldg(p, grid, e->similarity, emit, stream));
+        CUDA_TRY(launch_ldg(p, grid, e->similarity, mode, stream));
     }
     ++*launches;
 
@@ -1159,6 +1168,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "grid")) e->tune.grid = v;
     else if (!strcmp(key, "l2_hint")) e->tune.l2_hint = v;
     else if (!strcmp(key, "chunk_steps")) e->tune.chunk_steps = v;
+    else if (!strcmp(key, "fused_k_max")) e->tune.fused_k_max = std::max(0, std::min(128, v));
     else if (!strcmp(key, "batch_tensor")) e->tune.batch_tensor = v;
     else if (!strcmp(key, "batch_min")) e->tune.batch_min = v;
     else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;

@@ -33,9 +33,9 @@ struct ScanParams {
     const float *query;         // [dims]
     uint32_t n_rows;
     uint32_t dims;
-    uint32_t k;                 // entries to produce (<= 32 for the fused list kernels)
+    uint32_t k;                 // entries to produce (<= 128 for the fused list kernels)
     uint32_t stages;            // ring depth per warp (TMA kernels)
-    uint64_t *block_keys;       // [grid][32] scratch
+    uint64_t *block_keys;       // [grid][32*E] scratch
     uint32_t *ticket;           // zero on entry, zero again on exit
     wax_vs_candidate *out;      // [k] results, best first
     uint32_t *dist_keys;        // emit mode: [n_rows] orderable distance keys (WAXVS_UKEY_NONE = dropped)
@@ -62,16 +62,28 @@ __device__ __forceinline__ void write_candidate(const ScanParams &p, int slot, u
 }
 
 // CTA merge + grid merge + output.  Called by every thread of the CTA after the scan loop.
-// lists: shared [warps][32] u64.
-__device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK &tk, uint64_t *lists, int warp,
+// lists: shared [warps][E*32] u64;  block_keys: global [grid][E*32].
+template <int E>
+__device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk, uint64_t *lists, int warp,
                                             int lane, int warps) {
     const int k = static_cast<int>(p.k);
+    constexpr int W = E * 32;
     __shared__ uint32_t s_last;
-    lists[warp * 32 + lane] = tk.key;
+    auto load_list = [&](const uint64_t *src, uint64_t (&dst)[E]) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) dst[j] = src[j * 32 + lane];
+    };
+#pragma unroll
+    for (int j = 0; j < E; ++j) lists[warp * W + j * 32 + lane] = tk.key[j];
     __syncthreads();
     if (warp == 0) {
-        for (int w = 1; w < warps; ++w) tk.merge_sorted(lists[w * 32 + lane], lane, k);
-        p.block_keys[static_cast<size_t>(blockIdx.x) * 32 + lane] = tk.key;
+        for (int w = 1; w < warps; ++w) {
+            uint64_t other[E];
+            load_list(lists + w * W, other);
+            tk.merge_sorted(other, lane, k);
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j) p.block_keys[static_cast<size_t>(blockIdx.x) * W + j * 32 + lane] = tk.key[j];
         __threadfence();
         __syncwarp();
         if (lane == 0) s_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
@@ -80,14 +92,25 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK &tk, u
     if (!s_last) return;
     __threadfence();
     tk.init();
-    for (uint32_t b = warp; b < gridDim.x; b += warps)
-        tk.merge_sorted(ld_cg_u64(p.block_keys + static_cast<size_t>(b) * 32 + lane), lane, k);
+    for (uint32_t b = warp; b < gridDim.x; b += warps) {
+        uint64_t other[E];
+#pragma unroll
+        for (int j = 0; j < E; ++j) other[j] = ld_cg_u64(p.block_keys + static_cast<size_t>(b) * W + j * 32 + lane);
+        tk.merge_sorted(other, lane, k);
+    }
     __syncthreads();  // everyone is done reading lists from the CTA merge
-    lists[warp * 32 + lane] = tk.key;
+#pragma unroll
+    for (int j = 0; j < E; ++j) lists[warp * W + j * 32 + lane] = tk.key[j];
     __syncthreads();
     if (warp == 0) {
-        for (int w = 1; w < warps; ++w) tk.merge_sorted(lists[w * 32 + lane], lane, k);
-        if (lane < k) write_candidate(p, lane, tk.key);
+        for (int w = 1; w < warps; ++w) {
+            uint64_t other[E];
+            load_list(lists + w * W, other);
+            tk.merge_sorted(other, lane, k);
+        }
+#pragma unroll
+        for (int j = 0; j < E; ++j)
+            if (j * 32 + lane < k) write_candidate(p, j * 32 + lane, tk.key[j]);
         if (lane == 0) { *p.ticket = 0u; if (p.work_counter) *p.work_counter = 0u; }
     }
 }
@@ -95,8 +118,10 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK &tk, u
 // ------------------------------------------------------------------------------------------------------------
 // TMA-staged kernel for dims == 128*C.
 //   R      rows per step (power of two)
-//   EMIT   false: fused top-k (k <= 32);  true: write orderable distance keys for the large-k select path
-template <int C, int R, int METRIC, bool EMIT>
+//   E      register-list slots per lane: fused top-k for k <= 32*E (E = 1: k <= 32, E = 4: k <= 128 -- the production
+//          candidateLimit of 72, UnifiedSearch.swift:1195-1200, stays in the single launch)
+//   EMIT   false: fused top-k;  true: write orderable distance keys for the large-k select path
+template <int C, int R, int METRIC, int E, bool EMIT>
 __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
     constexpr int D4 = 32 * C;  // float4 per row
     constexpr uint32_t ROW_BYTES = 512u * C;
@@ -111,7 +136,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
                      warp * stages;
     uint64_t *lists = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(warps) * stages * STAGE_BYTES) +
                       warps * stages;
-    uint32_t *stage_step = reinterpret_cast<uint32_t *>(lists + warps * 32) + warp * stages;  // step held by each stage
+    uint32_t *stage_step = reinterpret_cast<uint32_t *>(lists + warps * 32 * E) + warp * stages;  // step held by each stage
 
     // ---- query chunks in registers + fused |q|^2 (the in-kernel L2 normalisation of the query) ----
     float4 q[C];
@@ -183,7 +208,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
         ++issued;
     }
 
-    WarpTopK tk;
+    WarpTopK<E> tk;
     tk.init();
     const int k = static_cast<int>(p.k);
 
@@ -253,15 +278,15 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
         }
     }
 
-    if (!EMIT) finish_topk(p, tk, lists, warp, lane, warps);
+    if (!EMIT) finish_topk<E>(p, tk, lists, warp, lane, warps);
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // Generic kernel: any dims (including dims % 4 != 0 and rows too large for a shared-memory tile).
 // One warp per row, coalesced direct global loads (LDG.128 when dims % 4 == 0), same accumulation order.
-template <int METRIC, bool EMIT>
+template <int METRIC, int E, bool EMIT>
 __global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
-    __shared__ uint64_t lists[8 * 32];
+    __shared__ uint64_t lists[8 * 32 * E];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const uint32_t dims = p.dims;
     const bool vec4 = (dims % 4u) == 0u;
@@ -284,7 +309,7 @@ __global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
         sqrt_a2 = __fsqrt_rn(a2);
     }
 
-    WarpTopK tk;
+    WarpTopK<E> tk;
     tk.init();
     const int k = static_cast<int>(p.k);
     const uint32_t total_warps = gridDim.x * warps;
@@ -331,7 +356,7 @@ __global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
             if (key < tk.thresh) tk.insert(key, lane, k);
         }
     }
-    if (!EMIT) finish_topk(p, tk, lists, warp, lane, warps);
+    if (!EMIT) finish_topk<E>(p, tk, lists, warp, lane, warps);
 }
 
 }  // namespace waxvs
