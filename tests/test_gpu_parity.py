@@ -171,10 +171,11 @@ def test_kernel_variants_agree(oracle):
     q = oracle.synth_row(801, 0, 384, True)
     eng = _engine_from(VectorMetric.cosine, corpus)
     ref = eng.search(q, 32)
-    for opts in ({"variant": 2}, {"variant": 1, "rows_per_step": 8, "stages": 2}, {"variant": 1, "rows_per_step": 4, "stages": 3, "warps": 12},
-                 {"variant": 1, "rows_per_step": 4, "stages": 2, "warps": 16}, {"variant": 1, "warps": 4, "grid": 7}, {"variant": 1, "l2_hint": 1}):
+    for opts in ({"variant": 2}, {"variant": 1, "rows_per_step": 8, "stages": 2}, {"variant": 1, "rows_per_step": 4, "stages": 3, "warps": 10},
+                 {"variant": 1, "rows_per_step": 4, "stages": 2, "warps": 16}, {"variant": 1, "chunk_steps": 0}, {"variant": 1, "chunk_steps": 3}, {"variant": 1, "warps": 4, "grid": 7}, {"variant": 1, "l2_hint": 1}):
         for key in ("variant", "rows_per_step", "stages", "warps", "grid", "l2_hint"):
             eng.set_option(key, opts.get(key, 0))
+        eng.set_option("chunk_steps", opts.get("chunk_steps", 8))
         assert eng.search(q, 32) == ref, opts
         assert eng.search(q, 100)[:32] == ref, opts
 
