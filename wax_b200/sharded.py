@@ -81,6 +81,10 @@ class ShardedVectorEngine:
             self._comm_stream = torch.cuda.Stream(device=self.device)   # all-gather + D2H overlap the next scan
             # two scan streams: consecutive queries alternate, so one scan's tail overlaps the next one's prologue
             self._scan_streams = [torch.cuda.Stream(device=self.device) for _ in range(2)]
+            # Overlapping two scans pays when a shard is small (kernel tails/prologues overlap: +8 % at 7.7 GB,
+            # +15 % at 1.9 GB) and costs ~3 % when it is large (19 GB: twice the bytes in flight per SM), measured
+            # in profiles/bench_r01_n*_m*.json -- so alternate streams only below 12 GB per shard.
+            self._overlap_scans = (self.row_hi - self.row_lo) * self.dimensions * 4 < 12e9
         else:
             self.device = torch.device("cpu")
 
@@ -168,7 +172,7 @@ class ShardedVectorEngine:
                                               C.c_void_p(st.cuda_stream))
             if rc != 0:
                 raise RuntimeError(f"wax_vs_search_device rc={rc}: {L.last_error()}")
-        for st in self._scan_streams[: min(2, g)]:
+        for st in self._scan_streams[:n_streams]:
             ev = torch.cuda.Event()
             ev.record(st)
             scanned.append(ev)
