@@ -33,16 +33,20 @@ namespace waxvs {
 constexpr int kBatchM = 128;            // queries per CTA  (UMMA M)
 constexpr int kBatchN = 256;            // corpus rows per tile (UMMA N)
 constexpr int kBatchKBlock = 32;        // floats per k-block = one 128-byte swizzle atom
-constexpr int kBatchStages = 3;
-constexpr int kBatchHeap = 64;           // nominees kept per (row slice, query): a max-heap in shared memory
+// Two shapes of the same kernel share the 227 KB of shared memory differently (template <STAGES, HEAP>):
+//   <4, 16>: four TMA stages (192 KB) + 16-entry nominee heaps (16 KB)  -- the pipeline is latency-bound on TMA
+//            (profiles/ncu_batch_tf32_r01b_summary.csv: 3 stages keep the tensor pipe 54 % busy), so the 4th stage
+//            matters; used whenever 16 nominees per slice are plenty (16 * slices >= 8 * k);
+//   <3, 64>: three stages + 64-entry heaps, for few slices or large k.
 constexpr int kBatchRescore = 256;       // nominees of the union re-scored exactly per query
 constexpr uint32_t kBatchABytes = kBatchM * 128u;   // 16 KB
 constexpr uint32_t kBatchBBytes = kBatchN * 128u;   // 32 KB
 constexpr uint32_t kBatchStageBytes = kBatchABytes + kBatchBBytes;
 constexpr int kBatchStageSlots = 8;      // staged nominees per epilogue thread before a forced flush
-constexpr uint32_t kBatchSmemBytes = kBatchStages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ +
-                                     kBatchStageSlots * kBatchM * 8 /*nominee staging*/ +
-                                     kBatchHeap * kBatchM * 8 /*heaps*/ + 1024 /*align*/;
+constexpr uint32_t batch_smem_bytes(int stages, int heap) {
+    return stages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ + kBatchStageSlots * kBatchM * 8 /*staging*/ +
+           heap * kBatchM * 8 /*heaps*/ + 1024 /*align*/;
+}
 constexpr int kBatchThreads = 192;
 constexpr float kTf32Eps = 1.25f * 0x1p-9f;
 
@@ -51,10 +55,10 @@ struct BatchParams {
     uint32_t groups;        // ceil(n_queries / 128)
     uint32_t slices;        // row slices; CTA b -> (group b % groups, slice b / groups)
     uint32_t tiles_total;   // ceil(n_rows / 256)
-    uint32_t kprime;        // == kBatchHeap (kept for the finish kernel's bookkeeping)
+    uint32_t kprime;        // == HEAP of the kernel shape in use
     int metric;             // kCosine or kDot
     const float *row_scale; // [n_rows] 1/|v| (cosine) or nullptr
-    uint64_t *heaps;        // [slices*groups][kBatchHeap][128]: each CTA's heaps, dumped entry-major at the end
+    uint64_t *heaps;        // [slices*groups][HEAP][128]: each CTA's heaps, dumped entry-major at the end
     uint32_t *tau_global;   // [n_queries] orderable(score') of the best k'-th nominee any slice has reached (0 = none)
     uint32_t no_insert;     // instrumentation: skip nominations (timing floor of the GEMM pipeline)
 };
@@ -131,15 +135,16 @@ __device__ __forceinline__ float nominee_score(uint64_t key) { return -from_orde
 
 // `heap` points at this thread's node 0 in shared memory; node i lives at heap[i * kBatchM] (entry-major, so the
 // 32 lanes of a warp touching the same level hit 32 different banks).  Returns the new root.
+template <int HEAP>
 __device__ __forceinline__ uint64_t heap_replace_root(uint64_t *heap, uint64_t x) {
     uint32_t i = 0;
 #pragma unroll 1
     for (;;) {
         const uint32_t l = 2 * i + 1;
-        if (l >= kBatchHeap) break;
+        if (l >= HEAP) break;
         const uint32_t r = l + 1;
         const uint64_t kl = heap[l * kBatchM];
-        const uint64_t kr = (r < kBatchHeap) ? heap[r * kBatchM] : 0ull;
+        const uint64_t kr = (r < HEAP) ? heap[r * kBatchM] : 0ull;
         const uint32_t c = (kr > kl) ? r : l;
         const uint64_t kc = (kr > kl) ? kr : kl;
         if (kc <= x) break;
@@ -186,6 +191,7 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float *corpus, uin
 }
 
 // ---- the tensor-core kernel ---------------------------------------------------------------------------------------
+template <int STAGES, int HEAP>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                   const BatchParams p) {
@@ -194,13 +200,13 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // keeps the shared address space (LDS/STS, not generic LD/ST).
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t *stages = smem;                                            // [stage][A 16 KB | B 32 KB], 1024-aligned
-    float *scale_smem = reinterpret_cast<float *>(smem + kBatchStages * kBatchStageBytes);   // [2][256]
+    float *scale_smem = reinterpret_cast<float *>(smem + STAGES * kBatchStageBytes);   // [2][256]
     uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kBatchN);                 // [stages]
-    uint64_t *empty = full + kBatchStages;                                                   // [stages]
-    uint64_t *tmem_full = empty + kBatchStages;                                              // [2]
+    uint64_t *empty = full + STAGES;                                                   // [stages]
+    uint64_t *tmem_full = empty + STAGES;                                              // [2]
     uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + kBatchStages * kBatchStageBytes + 2048 + 256);  // [slots][128]
+    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + STAGES * kBatchStageBytes + 2048 + 256);  // [slots][128]
     uint64_t *heap_smem = stage_smem + kBatchStageSlots * kBatchM;                                            // [64][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -213,7 +219,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_c);
-        for (int s = 0; s < kBatchStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
         mbar_fence_init();
     }
@@ -241,7 +247,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                                 static_cast<int32_t>(group * kBatchM));
                     tma_load_2d(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
                                 static_cast<int32_t>(tile * kBatchN));
-                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
@@ -264,7 +270,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     for (uint32_t j = 0; j < kBatchKBlock / 8; ++j)   // UMMA K = 8 tf32 = 32 bytes = +2 in the address field
                         umma_tf32_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
                     tcgen05_commit(&empty[stage]);                    // frees the smem stage when the MMAs retire
-                    if (++stage == kBatchStages) { stage = 0; phase ^= 1u; }
+                    if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
                 tcgen05_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
             }
@@ -279,7 +285,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         const uint32_t q = group * kBatchM + tid;
         const bool q_valid = q < p.n_queries && !p.no_insert;
         uint64_t *heap = heap_smem + tid;
-        for (uint32_t i = 0; i < kBatchHeap; ++i) heap[i * kBatchM] = WAXVS_KEY_NONE;
+        for (uint32_t i = 0; i < HEAP; ++i) heap[i * kBatchM] = WAXVS_KEY_NONE;
         uint64_t root = WAXVS_KEY_NONE;                               // heap[0]: this slice's k'-th best so far
         float tau = -INFINITY;
         uint64_t *stage = stage_smem + tid;                           // slot i at stage[i * 128]
@@ -288,7 +294,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         auto flush = [&]() {
             for (uint32_t i = 0; i < cnt; ++i) {
                 const uint64_t x = stage[i * kBatchM];
-                if (x < root) { root = heap_replace_root(heap, x); improved = true; }
+                if (x < root) { root = heap_replace_root<HEAP>(heap, x); improved = true; }
             }
             cnt = 0;
             if (root != WAXVS_KEY_NONE) tau = fmaxf(tau, nominee_score(root));
@@ -394,8 +400,8 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         flush();
         // dump this CTA's heaps (entry-major, coalesced) for batch_finish_kernel
-        uint64_t *dst = p.heaps + static_cast<size_t>(blockIdx.x) * kBatchHeap * kBatchM + tid;
-        for (uint32_t i = 0; i < kBatchHeap; ++i) dst[i * kBatchM] = heap[i * kBatchM];
+        uint64_t *dst = p.heaps + static_cast<size_t>(blockIdx.x) * HEAP * kBatchM + tid;
+        for (uint32_t i = 0; i < HEAP; ++i) dst[i * kBatchM] = heap[i * kBatchM];
     }
     tcgen05_fence_before();
     __syncthreads();
@@ -482,13 +488,13 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
 
     if (threadIdx.x == 0) { s_valid = 0; s_excl = 0; }
     __syncthreads();
-    const uint32_t total = p.slices * kBatchHeap;
+    const uint32_t total = p.slices * p.kprime;
     uint32_t cnt = 0;
     for (uint32_t i = threadIdx.x; i < p.pow2_all; i += blockDim.x) {
         uint64_t key = WAXVS_KEY_NONE;
         if (i < total) {
-            const uint32_t s = i / kBatchHeap, e = i % kBatchHeap;
-            key = p.heaps[(static_cast<size_t>(s * p.groups + g) * kBatchHeap + e) * kBatchM + t];
+            const uint32_t s = i / p.kprime, e = i % p.kprime;
+            key = p.heaps[(static_cast<size_t>(s * p.groups + g) * p.kprime + e) * kBatchM + t];
             if (key != WAXVS_KEY_NONE) {
                 ++cnt;
                 // node 0 is the slice's root: real only when its heap filled up, i.e. when it could exclude rows

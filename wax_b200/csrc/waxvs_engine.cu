@@ -115,6 +115,8 @@ struct Tuning {
     int fused_k_max = 128;  // k <= this stays in the single fused launch (register lists); larger k: emit + radix select
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
+    int time_overlap = 0;   // wax_vs_debug_time_search: alternate consecutive queries over two streams
+    int batch_heap = 0;     // 0 auto, 16 or 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
 };
 
@@ -465,13 +467,13 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
-    const uint32_t kprime = kBatchHeap;
     const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + kBatchN - 1) / kBatchN);
     const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(batch_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kBatchSmemBytes));
+        attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 16)));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(3, 64)));
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kDot>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
     });
@@ -483,6 +485,9 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         const uint32_t nq = std::min<uint32_t>(n_queries - q0, max_groups * kBatchM);
         const uint32_t groups = (nq + kBatchM - 1) / kBatchM;
         uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(e->sm_count) / groups, tiles_total));
+        // kernel shape: 16-entry heaps + 4 stages when 16 nominees per slice comfortably cover k, else 64 + 3
+        const bool small_heap = e->tune.batch_heap == 16 || (e->tune.batch_heap == 0 && 16u * slices >= 8u * k_eff);
+        const uint32_t kprime = small_heap ? 16u : 64u;
         slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));   // union fits the finish sort
         const uint32_t grid = groups * slices;
         if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
@@ -499,7 +504,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         bp.heaps = c->d_heaps;
         bp.tau_global = c->d_tau;
         bp.no_insert = e->tune.batch_noinsert ? 1u : 0u;
-        batch_tf32_kernel<<<grid, kBatchThreads, kBatchSmemBytes, stream>>>(map_q, map_c, bp);
+        if (small_heap) batch_tf32_kernel<4, 16><<<grid, kBatchThreads, batch_smem_bytes(4, 16), stream>>>(map_q, map_c, bp);
+        else batch_tf32_kernel<3, 64><<<grid, kBatchThreads, batch_smem_bytes(3, 64), stream>>>(map_q, map_c, bp);
         CUDA_TRY(cudaGetLastError());
 
         FinishParams fp{};
@@ -1064,13 +1070,29 @@ int32_t wax_vs_debug_time_search(wax_vs_engine *e, uint32_t n_queries, int64_t t
     synth_fill_kernel<<<(n_queries + 255) / 256, 256, 0, c->stream>>>(c->d_queries, n_queries, e->dims, seed, 0, 1);
     CUDA_TRY(cudaGetLastError());
     uint64_t launches = 0;
-    for (uint32_t it = 0; it < warmup + iters; ++it) {
-        if (it == warmup) { launches = 0; CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); }
-        const uint32_t qi = it % n_queries;
-        rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
-                            c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
-        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    // time_overlap: consecutive (independent) queries alternate over two streams so that one scan's tail overlaps
+    // the next one's prologue -- what the sharded engine does with search_many_async.
+    SearchCtx *c2 = nullptr;
+    if (e->tune.time_overlap) {
+        if ((rc = ctx_acquire(e, &c2))) return rc;
+        if ((rc = ensure_dev(&c2->d_out, &c2->d_out_cap, static_cast<size_t>(n_queries) * k_eff, "result buffer"))) { ctx_release(e, c2); return rc; }
     }
+    struct Rel2 { wax_vs_engine *e; SearchCtx *c; ~Rel2() { if (c) ctx_release(e, c); } } rel2{e, c2};
+    for (uint32_t it = 0; it < warmup + iters; ++it) {
+        if (it == warmup) {
+            launches = 0;
+            if (c2) { CUDA_TRY(cudaEventRecord(c2->ev0, c2->stream)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c2->ev0, 0)); }
+            CUDA_TRY(cudaEventRecord(c->ev0, c->stream));
+            if (c2) CUDA_TRY(cudaStreamWaitEvent(c2->stream, c->ev0, 0));
+        }
+        const uint32_t qi = it % n_queries;
+        SearchCtx *cc = (c2 && (it & 1u)) ? c2 : c;
+        if (c2 && it == 0) { CUDA_TRY(cudaEventRecord(c->ev1, c->stream)); CUDA_TRY(cudaStreamWaitEvent(c2->stream, c->ev1, 0)); }  // queries ready
+        rc = enqueue_search(e, cc, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
+                            cc->d_out + static_cast<size_t>(qi) * k_eff, nullptr, cc->stream, &launches);
+        if (rc) { cudaStreamSynchronize(c->stream); if (c2) cudaStreamSynchronize(c2->stream); return rc; }
+    }
+    if (c2) { CUDA_TRY(cudaEventRecord(c2->ev1, c2->stream)); CUDA_TRY(cudaStreamWaitEvent(c->stream, c2->ev1, 0)); }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
     CUDA_TRY(cudaEventElapsedTime(out_ms_total, c->ev0, c->ev1));
@@ -1172,6 +1194,8 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_tensor")) e->tune.batch_tensor = v;
     else if (!strcmp(key, "batch_min")) e->tune.batch_min = v;
     else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;
+    else if (!strcmp(key, "batch_heap")) e->tune.batch_heap = v;
+    else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);
     return WAX_VS_OK;
