@@ -206,3 +206,17 @@ def test_growth_from_initial_reserve(oracle):
     r, _, s = oracle.search(oracle.L2, rows, rows[500], 5, mode=oracle.ACC_F32_TREE)
     got = eng.search(rows[500], 5)
     assert [g[0] for g in got] == r.tolist() and got[0][0] == 500 and got[0][1] == 0.0
+
+
+def test_cpp_mirror_runs_the_reference_tests_on_the_gpu(tmp_path):
+    """The header-only C++ mirror over the C-ABI (the compiled-language host side): build and run its GPU test."""
+    import subprocess
+    from pathlib import Path
+    from wax_b200 import build
+    root = Path(__file__).resolve().parents[1]
+    lib = build.build()
+    exe = tmp_path / "cpp_engine_gpu"
+    subprocess.run(["g++", "-std=c++17", "-O1", "-Wall", str(root / "tests" / "cpp_engine_gpu.cpp"), f"-L{lib.parent}",
+                    "-lwaxvs_cuda", f"-Wl,-rpath,{lib.parent}", "-o", str(exe)], check=True, capture_output=True)
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0 and "cpp mirror ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
