@@ -126,6 +126,16 @@ int32_t wax_vs_search_batch(wax_vs_engine *engine, const float *queries, uint32_
                             uint32_t query_len, int64_t top_k, uint64_t *out_ids, float *out_scores,
                             uint32_t out_stride, uint32_t *out_n);
 
+/* Filtered search -- SURVEY.md section 8(f) rank 4, an API EXTENSION over the reference: Wax filters frames
+   after the engine call and over-fetches 3 x topK to compensate (UnifiedSearch.swift:58, :371-442, :1195-1200,
+   :1241-1258).  Here the filter is applied below the top-k, so exactly min(clamp(top_k), #allowed) best
+   allowed rows come back.  mode 0: only rows whose frameId is in frame_ids[] may be returned (allow-list);
+   mode 1: rows whose frameId is in frame_ids[] are excluded (deny-list, e.g. deleted / superseded frames).
+   Unknown ids are ignored.  Same ordering, scoring and error behaviour as wax_vs_search. */
+int32_t wax_vs_search_filtered(wax_vs_engine *engine, const float *query, uint32_t query_len, int64_t top_k,
+                               const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
+                               float *out_scores, uint32_t out_cap, uint32_t *out_n);
+
 /* Device-resident form used by the row-sharded engine: `d_queries` (n_queries x dims) and
    `d_candidates` (n_queries x k_eff entries, k_eff = min(clamp(top_k), 10000) -- NOT clipped to N, padding
    has valid = 0) are DEVICE pointers on the engine's device; the work is enqueued on `cuda_stream`

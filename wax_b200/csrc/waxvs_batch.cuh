@@ -458,6 +458,41 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t *sk, uint32_t pow2) 
     }
 }
 
+// ---- small allow-lists: score only the listed rows (O(n_allow), not O(N)) --------------------------------------------
+// One warp per listed row, exact distance in the kernels' order; then one CTA sorts the keys.
+template <int METRIC>
+__global__ void __launch_bounds__(256) gather_score_kernel(const float *corpus, const float *query, uint32_t dims,
+                                                           const uint32_t *rows, uint32_t n, uint64_t *keys) {
+    const int lane = threadIdx.x & 31;
+    float a2 = 0.0f, sqrt_a2 = 0.0f;
+    if (METRIC == kCosine) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (uint32_t base = 4u * lane; base < dims; base += 128u) {
+            const float x = __ldg(query + base); s0 = __fmaf_rn(x, x, s0);
+            if (base + 1 < dims) { const float y = __ldg(query + base + 1); s1 = __fmaf_rn(y, y, s1); }
+            if (base + 2 < dims) { const float z = __ldg(query + base + 2); s2 = __fmaf_rn(z, z, s2); }
+            if (base + 3 < dims) { const float w = __ldg(query + base + 3); s3 = __fmaf_rn(w, w, s3); }
+        }
+        a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
+        sqrt_a2 = __fsqrt_rn(a2);
+    }
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const uint32_t row = rows[i];
+        const float d = exact_row_distance<METRIC>(query, corpus + static_cast<size_t>(row) * dims, dims, a2, sqrt_a2, lane);
+        if (lane == 0) keys[i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
+    }
+}
+
+__global__ void __launch_bounds__(1024) gather_sort_kernel(const uint64_t *keys, uint32_t n, uint32_t pow2, ScanParams p) {
+    extern __shared__ uint64_t gsk[];
+    for (uint32_t i = threadIdx.x; i < pow2; i += blockDim.x) gsk[i] = (i < n) ? keys[i] : WAXVS_KEY_NONE;
+    __syncthreads();
+    block_bitonic_sort(gsk, pow2);
+    for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x)
+        write_candidate(p, static_cast<int>(i), i < pow2 ? gsk[i] : WAXVS_KEY_NONE);
+}
+
 struct FinishParams {
     const float *corpus, *queries;
     uint32_t n_rows, dims, n_queries, groups, slices, kprime, k;

@@ -138,6 +138,8 @@ struct SearchCtx {
     uint32_t *d_ok = nullptr; size_t ok_cap = 0;                  // batched path: per-query proof flags
     uint32_t *h_ok = nullptr; size_t h_ok_cap = 0;                // pinned
     uint32_t *d_tau = nullptr; size_t tau_cap = 0;                // batched path: shared per-query thresholds
+    uint32_t *d_mask = nullptr; size_t mask_cap = 0;              // filtered search: row bitset / listed rows
+    uint64_t *d_gather_keys = nullptr; size_t gather_cap = 0;     // filtered search: keys of the listed rows
 };
 
 struct wax_vs_engine {
@@ -190,6 +192,8 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_heaps) cudaFree(c->d_heaps);
     if (c->d_ok) cudaFree(c->d_ok);
     if (c->d_tau) cudaFree(c->d_tau);
+    if (c->d_mask) cudaFree(c->d_mask);
+    if (c->d_gather_keys) cudaFree(c->d_gather_keys);
     if (c->h_ok) cudaFreeHost(c->h_ok);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -340,7 +344,7 @@ static cudaError_t launch_ldg(const ScanParams &p, int grid, int metric, int mod
 // Enqueue one query's scan + top-k on `stream`.  k_eff <= 10000.  Adds the number of kernels launched.
 static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_query, uint32_t k_eff,
                               uint64_t row_offset, wax_vs_candidate *d_out, const uint64_t *d_ids,
-                              cudaStream_t stream, uint64_t *launches) {
+                              cudaStream_t stream, uint64_t *launches, const uint32_t *d_mask = nullptr) {
     if (e->n_rows == 0) {
         CUDA_TRY(cudaMemsetAsync(d_out, 0, static_cast<size_t>(k_eff) * sizeof(wax_vs_candidate), stream));
         return WAX_VS_OK;
@@ -353,6 +357,7 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     p.use_l2_hint = e->tune.l2_hint ? 1u : 0u;
     p.chunk_steps = e->tune.chunk_steps > 0 ? static_cast<uint32_t>(e->tune.chunk_steps) : 0u;
     p.work_counter = c->d_ticket + 1;
+    p.mask = d_mask;
 
     const bool emit = k_eff > static_cast<uint32_t>(e->tune.fused_k_max);
     const int mode = emit ? 2 : (k_eff <= 32 ? 0 : 1);
@@ -925,6 +930,111 @@ int32_t wax_vs_search_device(wax_vs_engine *e, const float *d_queries, uint32_t 
                             static_cast<cudaStream_t>(cuda_stream), &launches);
         if (rc) return rc;
     }
+    return WAX_VS_OK;
+}
+
+// ---- filtered search -------------------------------------------------------------------
+// The reference filters AFTER the engine call and over-fetches 3 x topK to compensate (UnifiedSearch.swift:58,
+// 371-442, 1195-1200, 1241-1258).  Here the filter is pushed below the top-k: a row bitset consulted only for rows
+// that would enter the list, or -- for small allow-lists -- a gather that scores only the listed rows.
+int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k,
+                               const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
+                               float *out_scores, uint32_t out_cap, uint32_t *out_n) {
+    if (!e || !out_n) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (mode != 0 && mode != 1) return fail(WAX_VS_ERR_ARGUMENT, "filter mode must be 0 (allow-list) or 1 (deny-list)");
+    if (n_ids && !frame_ids) return fail(WAX_VS_ERR_NULL, "frame_ids is NULL");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    *out_n = 0;
+    if (e->n_rows == 0) return WAX_VS_OK;
+    if (!query) return fail(WAX_VS_ERR_NULL, "query is NULL");
+    if (query_len != e->dims)
+        return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, query_len);
+
+    // ids -> rows (unknown ids are ignored), as a bitset and as a list
+    const uint64_t n_rows = e->n_rows;
+    std::vector<uint32_t> bits((n_rows + 31) / 32, mode == 0 ? 0u : 0xFFFFFFFFu);
+    if (mode == 1 && (n_rows & 31u)) bits.back() = (1u << (n_rows & 31u)) - 1u;
+    std::vector<uint32_t> listed;
+    {
+        std::lock_guard<std::mutex> g(e->ids_mu);   // the lazily built id map is shared by concurrent readers
+        if (!e->ids_identity) ensure_map(e);
+        for (uint64_t i = 0; i < n_ids; ++i) {
+            uint64_t row;
+            if (e->ids_identity) {
+                if (frame_ids[i] < e->id_base || frame_ids[i] - e->id_base >= n_rows) continue;
+                row = frame_ids[i] - e->id_base;
+            } else {
+                const uint32_t f = e->map.find(frame_ids[i]);
+                if (f == 0xFFFFFFFFu) continue;
+                row = f;
+            }
+            const uint32_t w = static_cast<uint32_t>(row >> 5), b = 1u << (row & 31u);
+            if (mode == 0) { if (!(bits[w] & b)) { bits[w] |= b; listed.push_back(static_cast<uint32_t>(row)); } }
+            else if (bits[w] & b) { bits[w] &= ~b; listed.push_back(static_cast<uint32_t>(row)); }
+        }
+    }
+    const uint64_t allowed = mode == 0 ? listed.size() : n_rows - listed.size();
+    const uint32_t k_eff = static_cast<uint32_t>(std::min<uint64_t>(clamp_topk(top_k), allowed));
+    if (k_eff == 0) return WAX_VS_OK;
+    if (!out_ids || !out_scores) return fail(WAX_VS_ERR_NULL, "output buffer is NULL");
+    if (out_cap < k_eff) return fail(WAX_VS_ERR_BUFFER, "output buffers hold %u entries, need %u", out_cap, k_eff);
+
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_acquire(e, &c);
+    if (rc) return rc;
+    struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); } } rel{e, c};
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(e->dims), "query buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, static_cast<size_t>(e->dims), "query staging"))) return rc;
+    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, static_cast<size_t>(k_eff), "result buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_out, &c->h_out_cap, static_cast<size_t>(k_eff), "result staging"))) return rc;
+    memcpy(c->h_queries, query, e->dims * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, e->dims * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+
+    uint64_t launches = 0;
+    if (mode == 0 && listed.size() <= 16384) {
+        // small allow-list: gather + exact score of the listed rows only, then one-CTA sort
+        std::sort(listed.begin(), listed.end());
+        const uint32_t n = static_cast<uint32_t>(listed.size());
+        if ((rc = ensure_dev(&c->d_mask, &c->mask_cap, static_cast<size_t>(std::max<uint32_t>(n, 1)), "listed rows"))) return rc;
+        if ((rc = ensure_dev(&c->d_gather_keys, &c->gather_cap, static_cast<size_t>(std::max<uint32_t>(n, 1)), "gather keys"))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->d_mask, listed.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        const int ggrid = static_cast<int>(std::min<uint32_t>((n + 7) / 8, static_cast<uint32_t>(e->sm_count) * 8));
+        switch (e->similarity) {
+            case WAX_VS_COSINE: gather_score_kernel<kCosine><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, c->d_queries, e->dims, c->d_mask, n, c->d_gather_keys); break;
+            case WAX_VS_DOT: gather_score_kernel<kDot><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, c->d_queries, e->dims, c->d_mask, n, c->d_gather_keys); break;
+            default: gather_score_kernel<kL2><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, c->d_queries, e->dims, c->d_mask, n, c->d_gather_keys); break;
+        }
+        CUDA_TRY(cudaGetLastError());
+        uint32_t pow2 = 64;
+        while (pow2 < n) pow2 <<= 1;
+        static std::once_flag once;
+        static cudaError_t attr = cudaSuccess;
+        std::call_once(once, [] { attr = cudaFuncSetAttribute(gather_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8); });
+        if (attr != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
+        ScanParams sp{};
+        sp.k = k_eff; sp.out = c->d_out; sp.id_base = e->id_base;
+        gather_sort_kernel<<<1, 1024, pow2 * sizeof(uint64_t), c->stream>>>(c->d_gather_keys, n, pow2, sp);
+        CUDA_TRY(cudaGetLastError());
+        launches += 2;
+    } else {
+        if ((rc = ensure_dev(&c->d_mask, &c->mask_cap, bits.size(), "row filter"))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->d_mask, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+        rc = enqueue_search(e, c, c->d_queries, k_eff, 0, c->d_out, nullptr, c->stream, &launches, c->d_mask);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    }
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, k_eff * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // also keeps `bits` / `listed` alive until the copies are done
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < k_eff; ++i) {
+        const wax_vs_candidate &cd = c->h_out[i];
+        if (!cd.valid) continue;
+        out_ids[m] = e->ids_identity ? e->id_base + cd.row : e->ids[cd.row];
+        out_scores[m] = score_from_distance(e->similarity, cd.distance);
+        ++m;
+    }
+    *out_n = m;
     return WAX_VS_OK;
 }
 

@@ -45,7 +45,12 @@ struct ScanParams {
     uint32_t use_l2_hint;       // 1: evict-first policy on the corpus stream
     uint32_t chunk_steps;       // > 0: dynamic scheduling, warps claim chunks of this many steps from work_counter
     uint32_t *work_counter;     // zero on entry, zero again on exit (reset by the last CTA)
+    const uint32_t *mask;       // optional row filter: bit r of mask[r / 32] set = row r may be returned (nullptr = all)
 };
+
+__device__ __forceinline__ bool row_allowed(const ScanParams &p, uint32_t row) {
+    return p.mask == nullptr || ((__ldg(p.mask + (row >> 5)) >> (row & 31u)) & 1u) != 0u;
+}
 
 __device__ __forceinline__ void write_candidate(const ScanParams &p, int slot, uint64_t key) {
     wax_vs_candidate c;
@@ -274,10 +279,13 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
         const bool ok = (my_row < p.n_rows) && finite_f32(d);
 
         if (EMIT) {
-            if (leader && my_row < p.n_rows) p.dist_keys[my_row] = ok ? orderable_u32(d) : WAXVS_UKEY_NONE;
+            if (leader && my_row < p.n_rows)
+                p.dist_keys[my_row] = (ok && row_allowed(p, my_row)) ? orderable_u32(d) : WAXVS_UKEY_NONE;
         } else {
             const uint64_t key = ok ? make_key(d, my_row) : WAXVS_KEY_NONE;
-            uint32_t m = __ballot_sync(WAXVS_FULL_MASK, leader && key < tk.thresh);
+            // the filter is consulted only for rows that would enter the list (rare once the list is warm)
+            const bool cand = leader && key < tk.thresh && row_allowed(p, my_row);
+            uint32_t m = __ballot_sync(WAXVS_FULL_MASK, cand);
             while (m) {
                 const int src = __ffs(m) - 1;
                 m &= m - 1;
@@ -359,10 +367,10 @@ __global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
         else d = finish_l2(s0);
         const bool ok = finite_f32(d);
         if (EMIT) {
-            if (lane == 0) p.dist_keys[row] = ok ? orderable_u32(d) : WAXVS_UKEY_NONE;
+            if (lane == 0) p.dist_keys[row] = (ok && row_allowed(p, row)) ? orderable_u32(d) : WAXVS_UKEY_NONE;
         } else if (ok) {
             const uint64_t key = make_key(d, row);
-            if (key < tk.thresh) tk.insert(key, lane, k);
+            if (key < tk.thresh && row_allowed(p, row)) tk.insert(key, lane, k);
         }
     }
     if (!EMIT) finish_topk<E>(p, tk, lists, warp, lane, warps);

@@ -189,6 +189,26 @@ class CUDAVectorEngine:
                                      scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return [(int(ids[i]), float(scores[i])) for i in range(n.value)]
 
+    def search_filtered(self, vector: Sequence[float], top_k: int, allow: Optional[Sequence[int]] = None,
+                        deny: Optional[Sequence[int]] = None) -> List[Tuple[int, float]]:
+        """Filter pushed below the top-k (API extension): the best `top_k` rows among the frames in
+        `allow` (allow-list) or among all frames except those in `deny` (deny-list).  Replaces the reference's
+        post-hoc frame filter + 3 x topK over-fetch (UnifiedSearch.swift:58,1241-1258)."""
+        if (allow is None) == (deny is None):
+            raise ValueError("pass exactly one of allow= / deny=")
+        ids = np.ascontiguousarray(allow if allow is not None else deny, dtype=np.uint64).reshape(-1)
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(self.count, 1)))
+        out_ids = np.zeros(cap, np.uint64)
+        scores = np.zeros(cap, np.float32)
+        n = C.c_uint32(0)
+        idp = ids.ctypes.data_as(C.POINTER(C.c_uint64)) if ids.size else None
+        _check(L.lib().wax_vs_search_filtered(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k), idp,
+                                              ids.size, 0 if allow is not None else 1,
+                                              out_ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                              scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
+        return [(int(out_ids[i]), float(scores[i])) for i in range(n.value)]
+
     def search_batch(self, vectors, top_k: int) -> List[List[Tuple[int, float]]]:
         qs = _as_rows(vectors, self.dimensions) if len(vectors) else np.zeros((0, self.dimensions), np.float32)
         b = qs.shape[0]
