@@ -162,11 +162,12 @@ class ShardedVectorEngine:
         ready = torch.cuda.Event()
         ready.record()                                   # queries were produced on the current stream
         scanned = []
-        for si, st in enumerate(self._scan_streams[: min(2, g)]):
+        n_streams = min(2 if self._overlap_scans else 1, g)
+        for st in self._scan_streams[:n_streams]:
             st.wait_event(ready)
         q_base, q_stride = d_queries.data_ptr(), d_queries.stride(0) * 4
         for i in range(g):
-            st = self._scan_streams[i % 2]
+            st = self._scan_streams[i % n_streams]
             rc = L.lib().wax_vs_search_device(self.engine.handle, C.c_void_p(q_base + i * q_stride), 1, k,
                                               self.row_lo, C.c_void_p(local.data_ptr() + i * k * 24),
                                               C.c_void_p(st.cuda_stream))
