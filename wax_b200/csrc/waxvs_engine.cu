@@ -266,22 +266,32 @@ struct TmaConfig { int C, R, warps, stages; size_t smem; };
 
 static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     const uint32_t d = e->dims;
-    if (d % 128u != 0) return false;
-    const int C = static_cast<int>(d / 128u);
-    if (!(C == 1 || C == 2 || C == 3 || C == 4 || C == 6 || C == 8)) return false;
-    const bool wide = (C >= 6);
-    int R = e->tune.rows_per_step ? e->tune.rows_per_step : (wide ? 2 : 4);
-    if (wide) { if (R != 2 && R != 4) R = 2; } else { if (R != 4 && R != 8) R = 4; }
-    int warps = e->tune.warps ? e->tune.warps : 8;
-    warps = std::max(1, std::min(16, warps));
+    if (d % 4u != 0) return false;                      // rows must be 16-byte multiples for the bulk copy
     const size_t budget = e->smem_optin ? e->smem_optin : 232448;
-    const size_t stage_bytes = static_cast<size_t>(R) * d * 4;
-    auto smem_for = [&](int st) { return static_cast<size_t>(warps) * st * (stage_bytes + 8 + 4) + static_cast<size_t>(warps) * 1024; };
+    int C = 0;
+    if (d % 128u == 0) {
+        const int c = static_cast<int>(d / 128u);
+        if (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8) C = c;   // unrolled shapes
+    }
+    int R;
+    if (C == 0) {                                        // generic shape: run-time chunk count, query in shared memory
+        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d >= 1536 ? 1 : 2);
+    } else if (C >= 6) {
+        R = e->tune.rows_per_step == 2 || e->tune.rows_per_step == 4 ? e->tune.rows_per_step : 2;
+    } else {
+        R = e->tune.rows_per_step == 4 || e->tune.rows_per_step == 8 ? e->tune.rows_per_step : 4;
+    }
     // Default ring depth 2: measured best on B200 (profiles/sweep_r01_call2.json: ~48 KB in flight per SM beats
     // deeper rings by 5-10 %).
-    int stages = e->tune.stages > 0 ? e->tune.stages : 2;
-    if (stages < 1 || smem_for(stages) > budget) return false;
-    cfg->C = C; cfg->R = R; cfg->warps = warps; cfg->stages = stages; cfg->smem = smem_for(stages);
+    const int stages = e->tune.stages > 0 ? e->tune.stages : 2;
+    const size_t stage_bytes = static_cast<size_t>(R) * d * 4;
+    const size_t query_bytes = C == 0 ? (static_cast<size_t>(d) * 4 + 512 + 32) : 0;
+    auto smem_for = [&](int w) { return static_cast<size_t>(w) * stages * (stage_bytes + 8 + 4) + static_cast<size_t>(w) * 1024 + 16 + query_bytes; };
+    int warps = e->tune.warps ? e->tune.warps : 8;
+    warps = std::max(1, std::min(16, warps));
+    if (!e->tune.warps) while (warps > 2 && smem_for(warps) > budget) --warps;   // long rows: fewer warps per CTA
+    if (smem_for(warps) > budget) return false;
+    cfg->C = C; cfg->R = R; cfg->warps = warps; cfg->stages = stages; cfg->smem = smem_for(warps);
     return true;
 }
 
@@ -323,6 +333,7 @@ static cudaError_t launch_tma(const ScanParams &p, int grid, const TmaConfig &cf
     WAXVS_CASE(1, 4); WAXVS_CASE(1, 8); WAXVS_CASE(2, 4); WAXVS_CASE(2, 8);
     WAXVS_CASE(3, 4); WAXVS_CASE(3, 8); WAXVS_CASE(4, 4); WAXVS_CASE(4, 8);
     WAXVS_CASE(6, 2); WAXVS_CASE(6, 4); WAXVS_CASE(8, 2); WAXVS_CASE(8, 4);
+    WAXVS_CASE(0, 1); WAXVS_CASE(0, 2);
 #undef WAXVS_CASE
     return cudaErrorInvalidValue;
 }

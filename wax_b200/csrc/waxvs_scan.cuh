@@ -130,16 +130,19 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// TMA-staged kernel for dims == 128*C.
+// TMA-staged kernel.  C > 0: dims == 128*C, query chunks in registers, loops fully unrolled (the hot shapes
+// 128..1024).  C == 0: any dims % 4 == 0 whose rows fit a stage (1536, 3072, 1000, ...): same algorithm with the
+// chunk count at run time and the query chunks read from a shared-memory copy.
 //   R      rows per step (power of two)
 //   E      register-list slots per lane: fused top-k for k <= 32*E (E = 1: k <= 32, E = 4: k <= 128 -- the production
 //          candidateLimit of 72, UnifiedSearch.swift:1195-1200, stays in the single launch)
 //   EMIT   false: fused top-k;  true: write orderable distance keys for the large-k select path
 template <int C, int R, int METRIC, int E, bool EMIT>
 __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
-    constexpr int D4 = 32 * C;  // float4 per row
-    constexpr uint32_t ROW_BYTES = 512u * C;
-    constexpr uint32_t STAGE_BYTES = ROW_BYTES * R;
+    const int D4 = C > 0 ? 32 * C : static_cast<int>(p.dims / 4u);          // float4 per row
+    const int CN = C > 0 ? C : (D4 + 31) / 32;                               // chunks per lane
+    const uint32_t ROW_BYTES = C > 0 ? 512u * C : p.dims * 4u;
+    const uint32_t STAGE_BYTES = ROW_BYTES * R;
     constexpr int LANES_PER_ROW = 32 / R;
 
     extern __shared__ __align__(128) unsigned char smem[];
@@ -151,19 +154,28 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
     uint64_t *lists = reinterpret_cast<uint64_t *>(smem + static_cast<size_t>(warps) * stages * STAGE_BYTES) +
                       warps * stages;
     uint32_t *stage_step = reinterpret_cast<uint32_t *>(lists + warps * 32 * E) + warp * stages;  // step held by each stage
+    float4 *qs = reinterpret_cast<float4 *>(reinterpret_cast<uint32_t *>(lists + warps * 32 * E) + warps * stages + 4);  // C == 0
 
-    // ---- query chunks in registers + fused |q|^2 (the in-kernel L2 normalisation of the query) ----
-    float4 q[C];
+    // ---- query chunks in registers (C > 0) or shared memory (C == 0) + fused |q|^2 ----
+    float4 q[C > 0 ? C : 1];
     const float4 *q4 = reinterpret_cast<const float4 *>(p.query);
+    if (C > 0) {
 #pragma unroll
-    for (int c = 0; c < C; ++c) q[c] = __ldg(q4 + lane + 32 * c);
+        for (int c = 0; c < (C > 0 ? C : 1); ++c) q[c] = __ldg(q4 + lane + 32 * c);
+    } else {
+        qs = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(qs) + 15) & ~uintptr_t(15));
+        for (int i = threadIdx.x; i < CN * 32; i += blockDim.x) qs[i] = (i < D4) ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        __syncthreads();
+    }
+    auto qchunk = [&](int c) -> float4 { return C > 0 ? q[C > 0 ? c : 0] : qs[lane + 32 * c]; };
     float a2 = 0.0f, sqrt_a2 = 0.0f;
     if (METRIC == kCosine) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) {
-            s0 = __fmaf_rn(q[c].x, q[c].x, s0); s1 = __fmaf_rn(q[c].y, q[c].y, s1);
-            s2 = __fmaf_rn(q[c].z, q[c].z, s2); s3 = __fmaf_rn(q[c].w, q[c].w, s3);
+        for (int c = 0; c < CN; ++c) {
+            const float4 qc = qchunk(c);
+            s0 = __fmaf_rn(qc.x, qc.x, s0); s1 = __fmaf_rn(qc.y, qc.y, s1);
+            s2 = __fmaf_rn(qc.z, qc.z, s2); s3 = __fmaf_rn(qc.w, qc.w, s3);
         }
         a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
         sqrt_a2 = __fsqrt_rn(a2);
@@ -181,7 +193,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
         const uint32_t bytes = rows * ROW_BYTES;
         stage_step[s] = step;                        // released to the warp by the mbarrier arrive below
         mbar_arrive_expect_tx(&bars[s], bytes);
-        const float *src = p.corpus + static_cast<size_t>(row0) * (128u * C);
+        const float *src = p.corpus + static_cast<size_t>(row0) * p.dims;
         if (p.use_l2_hint) bulk_copy_g2s_hint(ring + s * STAGE_BYTES, src, bytes, &bars[s], policy);
         else bulk_copy_g2s(ring + s * STAGE_BYTES, src, bytes, &bars[s]);
     };
@@ -237,16 +249,18 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
         for (int r = 0; r < R; ++r) {
             float a0 = 0.f, a1 = 0.f, a2_ = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
 #pragma unroll
-            for (int c = 0; c < C; ++c) {
+            for (int c = 0; c < CN; ++c) {
+                if (C == 0 && lane + 32 * c >= D4) break;   // ragged last chunk (dims % 128 != 0): this lane has no element
                 const float4 v = tile[r * D4 + lane + 32 * c];
+                const float4 qc = qchunk(c);
                 if (METRIC == kL2) {
-                    const float dx = __fsub_rn(q[c].x, v.x), dy = __fsub_rn(q[c].y, v.y);
-                    const float dz = __fsub_rn(q[c].z, v.z), dw = __fsub_rn(q[c].w, v.w);
+                    const float dx = __fsub_rn(qc.x, v.x), dy = __fsub_rn(qc.y, v.y);
+                    const float dz = __fsub_rn(qc.z, v.z), dw = __fsub_rn(qc.w, v.w);
                     a0 = __fmaf_rn(dx, dx, a0); a1 = __fmaf_rn(dy, dy, a1);
                     a2_ = __fmaf_rn(dz, dz, a2_); a3 = __fmaf_rn(dw, dw, a3);
                 } else {
-                    a0 = __fmaf_rn(q[c].x, v.x, a0); a1 = __fmaf_rn(q[c].y, v.y, a1);
-                    a2_ = __fmaf_rn(q[c].z, v.z, a2_); a3 = __fmaf_rn(q[c].w, v.w, a3);
+                    a0 = __fmaf_rn(qc.x, v.x, a0); a1 = __fmaf_rn(qc.y, v.y, a1);
+                    a2_ = __fmaf_rn(qc.z, v.z, a2_); a3 = __fmaf_rn(qc.w, v.w, a3);
                     if (METRIC == kCosine) {
                         b0 = __fmaf_rn(v.x, v.x, b0); b1 = __fmaf_rn(v.y, v.y, b1);
                         b2 = __fmaf_rn(v.z, v.z, b2); b3 = __fmaf_rn(v.w, v.w, b3);
