@@ -273,13 +273,18 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
         const int c = static_cast<int>(d / 128u);
         if (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8) C = c;   // unrolled shapes
     }
-    int R;
+    if (C == 0 && d < 128) return false;                 // short rows: the direct-load kernel is faster (dims sweep)
+    // rows per step / warps per CTA by row length (profiles/dims_sweep_r01_call17.json): keep a step at >= 4-12 KB
+    // and give short rows more warps (their bound is per-row instruction latency, not bytes in flight)
+    int R, warps_default = 8;
     if (C == 0) {                                        // generic shape: run-time chunk count, query in shared memory
-        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d >= 1536 ? 1 : 2);
+        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d > 2048 ? 1 : 2);
     } else if (C >= 6) {
         R = e->tune.rows_per_step == 2 || e->tune.rows_per_step == 4 ? e->tune.rows_per_step : 2;
     } else {
-        R = e->tune.rows_per_step == 4 || e->tune.rows_per_step == 8 ? e->tune.rows_per_step : 4;
+        R = e->tune.rows_per_step == 4 || e->tune.rows_per_step == 8 ? e->tune.rows_per_step : (C <= 2 ? 8 : 4);
+        if (C == 1) warps_default = 16;
+        else if (C == 2) warps_default = 12;
     }
     // Default ring depth 2: measured best on B200 (profiles/sweep_r01_call2.json: ~48 KB in flight per SM beats
     // deeper rings by 5-10 %).
@@ -287,7 +292,7 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     const size_t stage_bytes = static_cast<size_t>(R) * d * 4;
     const size_t query_bytes = C == 0 ? (static_cast<size_t>(d) * 4 + 512 + 32) : 0;
     auto smem_for = [&](int w) { return static_cast<size_t>(w) * stages * (stage_bytes + 8 + 4) + static_cast<size_t>(w) * 1024 + 16 + query_bytes; };
-    int warps = e->tune.warps ? e->tune.warps : 8;
+    int warps = e->tune.warps ? e->tune.warps : warps_default;
     warps = std::max(1, std::min(16, warps));
     if (!e->tune.warps) while (warps > 2 && smem_for(warps) > budget) --warps;   // long rows: fewer warps per CTA
     if (smem_for(warps) > budget) return false;
