@@ -92,3 +92,21 @@ def test_ineligible_batches_use_the_loop(oracle):
     qs2 = oracle.synth_rows(83, 0, 9, 100)
     assert eng2.search_batch(qs2, 10) == [eng2.search(q, 10) for q in qs2]
     assert eng.batch_stats() == (t0, f0) and eng2.batch_stats() == (0, 0)
+
+
+@pytest.mark.parametrize("dims,n,b,k", [(384, 100_003, 256, 10), (384, 100_003, 300, 10), (768, 30_001, 200, 100),
+                                        (384, 50_000, 1024, 72), (128, 257, 129, 10)])
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+def test_cta_pair_mode_equals_single_query_path(oracle, metric, dims, n, b, k):
+    """cta_group::2 shape (two CTAs of a cluster issue one 256-row MMA; each stages half of the corpus tile):
+    same nominees -> same proof -> identical results."""
+    eng = _engine(oracle, metric, n, dims, seed=950 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_pair", 1)
+    qs = oracle.synth_rows(951 + b, 0, b, dims, normalize=True)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, k)
+    t1, f1 = eng.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == b
+    assert got == _single(eng, qs, k)
+    if n >= 1000:
+        assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"

@@ -38,13 +38,17 @@ constexpr int kBatchKBlock = 32;        // floats per k-block = one 128-byte swi
 //            (profiles/ncu_batch_tf32_r01b_summary.csv: 3 stages keep the tensor pipe 54 % busy), so the 4th stage
 //            matters; used whenever 16 nominees per slice are plenty (16 * slices >= 8 * k);
 //   <3, 64>: three stages + 64-entry heaps, for few slices or large k.
+// PAIR = true is the cta_group::2 form: two CTAs of a cluster (two query groups, the same row slice) issue ONE
+// 256 x 256 x 8 MMA; each CTA stages only its own 128 query rows and HALF of the corpus tile (16 + 16 KB per
+// k-block instead of 16 + 32), so six stages fit where four did and the L2->SM traffic per SM drops by a third.
 constexpr int kBatchRescore = 256;       // nominees of the union re-scored exactly per query
 constexpr uint32_t kBatchABytes = kBatchM * 128u;   // 16 KB
 constexpr uint32_t kBatchBBytes = kBatchN * 128u;   // 32 KB
 constexpr uint32_t kBatchStageBytes = kBatchABytes + kBatchBBytes;
 constexpr int kBatchStageSlots = 8;      // staged nominees per epilogue thread before a forced flush
-constexpr uint32_t batch_smem_bytes(int stages, int heap) {
-    return stages * kBatchStageBytes + 2048 /*scales*/ + 256 /*barriers*/ + kBatchStageSlots * kBatchM * 8 /*staging*/ +
+__host__ __device__ constexpr uint32_t batch_stage_bytes(bool pair) { return kBatchABytes + (pair ? kBatchBBytes / 2 : kBatchBBytes); }
+__host__ __device__ constexpr uint32_t batch_smem_bytes(int stages, int heap, bool pair = false) {
+    return stages * batch_stage_bytes(pair) + 2048 /*scales*/ + 256 /*barriers*/ + kBatchStageSlots * kBatchM * 8 /*staging*/ +
            heap * kBatchM * 8 /*heaps*/ + 1024 /*align*/;
 }
 constexpr int kBatchThreads = 192;
@@ -110,6 +114,54 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
+// ---- 2-CTA (cta_group::2) variants: the CTA pair of a cluster works as one 256-row MMA --------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by either CTA of the pair into its OWN shared memory; the transaction bytes are credited to the
+// LEADER CTA's mbarrier (peer bit of the shared::cluster address cleared, as cute::SM100_TMA_2SM_LOAD_2D does).
+__device__ __forceinline__ void tma_load_2d_pair(void *smem_dst, const CUtensorMap *map, uint64_t *bar, int32_t c0,
+                                                 int32_t c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar) & 0xFEFFFFFFu), "r"(c0), "r"(c1)
+        : "memory");
+}
+// mbarrier.arrive on the barrier at the same offset in CTA `rank` of the cluster.
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t *bar, uint32_t rank) {
+    asm volatile(
+        "{\n\t.reg .b32 remote;\n\t"
+        "mapa.shared::cluster.u32 remote, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [remote];\n\t}" ::"r"(smem_u32(bar)),
+        "r"(rank)
+        : "memory");
+}
+__device__ __forceinline__ void tcgen05_commit_pair(uint64_t *bar) {   // arrives on `bar` in BOTH CTAs of the pair
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle (canonical layout ((8,n),2):((8,SBO),1) in 16-byte
 // units; rows 128 B apart, 8-row groups SBO = 1024 B apart).  Field layout: cute::UMMA::SmemDescriptor.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(const void *smem_tile) {
@@ -124,6 +176,10 @@ __device__ __forceinline__ uint64_t umma_desc_k_sw128(const void *smem_tile) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major, M = 128, N = 256.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_m128_n256() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+}
+// cta_group::2: M = 256 (128 rows per CTA of the pair), N = 256.
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m256_n256() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 }
 
 // ---- per-thread nominee heap (max-heap on the ordering key: root = worst nominee) ----------------------------
@@ -191,7 +247,7 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float *corpus, uin
 }
 
 // ---- the tensor-core kernel ---------------------------------------------------------------------------------------
-template <int STAGES, int HEAP>
+template <int STAGES, int HEAP, bool PAIR>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                   const BatchParams p) {
@@ -199,19 +255,26 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     // 1024-byte alignment for the 128B-swizzled tiles, computed as an OFFSET into the shared array so the compiler
     // keeps the shared address space (LDS/STS, not generic LD/ST).
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    constexpr uint32_t STAGE_BYTES = batch_stage_bytes(PAIR);
+    constexpr uint32_t B_ROWS = PAIR ? kBatchN / 2 : kBatchN;       // corpus rows this CTA stages per tile
     uint8_t *stages = smem;                                            // [stage][A 16 KB | B 32 KB], 1024-aligned
-    float *scale_smem = reinterpret_cast<float *>(smem + STAGES * kBatchStageBytes);   // [2][256]
+    float *scale_smem = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);   // [2][256]
     uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kBatchN);                 // [stages]
     uint64_t *empty = full + STAGES;                                                   // [stages]
     uint64_t *tmem_full = empty + STAGES;                                              // [2]
     uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + STAGES * kBatchStageBytes + 2048 + 256);  // [slots][128]
+    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2048 + 256);  // [slots][128]
     uint64_t *heap_smem = stage_smem + kBatchStageSlots * kBatchM;                                            // [64][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t group = blockIdx.x % p.groups, slice = blockIdx.x / p.groups;
-    if (slice >= p.slices) return;                    // surplus CTAs (grid is a multiple of groups anyway)
+    // PAIR: cluster c = (pair of groups c % (groups/2), slice c / (groups/2)); the CTA's rank picks the group.
+    const uint32_t rank = PAIR ? cluster_ctarank() : 0u;
+    const uint32_t unit = PAIR ? blockIdx.x / 2u : blockIdx.x;
+    const uint32_t units_per_slice = PAIR ? p.groups / 2u : p.groups;
+    const uint32_t group = PAIR ? (unit % units_per_slice) * 2u + rank : unit % units_per_slice;
+    const uint32_t slice = unit / units_per_slice;
+    const bool leader = rank == 0u;
     const uint32_t tile_lo = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * slice / p.slices);
     const uint32_t tile_hi = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * (slice + 1) / p.slices);
     const uint32_t num_kb = p.dims / kBatchKBlock;
@@ -219,18 +282,27 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
         tma_prefetch_desc(&tmap_c);
-        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 4); }
+        // PAIR: the leader's full[] collects both producers (its own expect_tx arrive + the peer's remote arrive) and
+        // its tmem_empty[] collects the 4 epilogue warps of both CTAs.
+        for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PAIR ? 2 : 1); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], PAIR ? 8 : 4); }
         mbar_fence_init();
     }
     if (warp == 5) {  // whole warp: allocate all 512 TMEM columns (2 accumulator buffers of 256)
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"(512)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (PAIR) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"(512)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();
     tcgen05_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -241,20 +313,29 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             for (uint32_t tile = tile_lo; tile < tile_hi; ++tile) {
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_parity(&empty[stage], phase ^ 1u);
-                    mbar_arrive_expect_tx(&full[stage], kBatchStageBytes);
-                    uint8_t *a = stages + stage * kBatchStageBytes;
-                    tma_load_2d(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
-                                static_cast<int32_t>(group * kBatchM));
-                    tma_load_2d(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
-                                static_cast<int32_t>(tile * kBatchN));
+                    uint8_t *a = stages + stage * STAGE_BYTES;
+                    if (PAIR) {
+                        if (leader) mbar_arrive_expect_tx(&full[stage], 2u * STAGE_BYTES);   // both CTAs' bytes
+                        else mbar_arrive_remote(&full[stage], 0u);
+                        tma_load_2d_pair(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                                         static_cast<int32_t>(group * kBatchM));
+                        tma_load_2d_pair(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                                         static_cast<int32_t>(tile * kBatchN + rank * B_ROWS));
+                    } else {
+                        mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
+                        tma_load_2d(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                                    static_cast<int32_t>(group * kBatchM));
+                        tma_load_2d(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                                    static_cast<int32_t>(tile * kBatchN));
+                    }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
             }
         }
     } else if (warp == 5) {
         // ===== MMA issuer (one thread) =====
-        if (lane == 0) {
-            constexpr uint32_t idesc = umma_idesc_tf32_m128_n256();
+        if (lane == 0 && leader) {      // PAIR: the leader CTA issues for both
+            constexpr uint32_t idesc = PAIR ? umma_idesc_tf32_m256_n256() : umma_idesc_tf32_m128_n256();
             uint32_t stage = 0, phase = 0, t = 0;
             for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
                 const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
@@ -264,15 +345,18 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     mbar_wait_parity(&full[stage], phase);            // TMA bytes have landed
                     tcgen05_fence_after();
-                    const uint8_t *a = stages + stage * kBatchStageBytes;
+                    const uint8_t *a = stages + stage * STAGE_BYTES;
                     const uint64_t da = umma_desc_k_sw128(a), db = umma_desc_k_sw128(a + kBatchABytes);
 #pragma unroll
                     for (uint32_t j = 0; j < kBatchKBlock / 8; ++j)   // UMMA K = 8 tf32 = 32 bytes = +2 in the address field
-                        umma_tf32_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
-                    tcgen05_commit(&empty[stage]);                    // frees the smem stage when the MMAs retire
+                        if (PAIR) umma_tf32_ss_pair(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
+                        else umma_tf32_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
+                    if (PAIR) tcgen05_commit_pair(&empty[stage]);     // frees the stage in both CTAs
+                    else tcgen05_commit(&empty[stage]);               // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
                 }
-                tcgen05_commit(&tmem_full[acc]);                      // accumulator complete -> epilogue
+                if (PAIR) tcgen05_commit_pair(&tmem_full[acc]);       // accumulators complete -> both epilogues
+                else tcgen05_commit(&tmem_full[acc]);                 // accumulator complete -> epilogue
             }
         }
     } else {
@@ -389,7 +473,10 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             }
             tcgen05_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);             // accumulator buffer is free again
+            if (lane == 0) {                                          // accumulator buffer is free again
+                if (PAIR) mbar_arrive_remote(&tmem_empty[acc], 0u);   // the leader's barrier gates the shared MMA
+                else mbar_arrive(&tmem_empty[acc]);
+            }
             if (__any_sync(WAXVS_FULL_MASK, cnt >= kBatchStageSlots / 2)) {
                 flush();
                 if (improved && q_valid && root != WAXVS_KEY_NONE) {  // heap full: publish this slice's k'-th best
@@ -400,14 +487,15 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         }
         flush();
         // dump this CTA's heaps (entry-major, coalesced) for batch_finish_kernel
-        uint64_t *dst = p.heaps + static_cast<size_t>(blockIdx.x) * HEAP * kBatchM + tid;
+        uint64_t *dst = p.heaps + static_cast<size_t>(slice * p.groups + group) * HEAP * kBatchM + tid;
         for (uint32_t i = 0; i < HEAP; ++i) dst[i * kBatchM] = heap[i * kBatchM];
     }
     tcgen05_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer may still arrive on / read this CTA's shared memory
     if (warp == 5) {
         tcgen05_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        if (PAIR) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+        else asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
     }
 }
 

@@ -116,6 +116,7 @@ struct Tuning {
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
     int time_overlap = 0;   // wax_vs_debug_time_search: alternate consecutive queries over two streams
+    int batch_pair = 0;     // 1: cta_group::2 CTA pairs (experimental until validated on hardware)
     int batch_heap = 0;     // 0 auto, 16 or 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
 };
@@ -493,30 +494,37 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 16)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<3, 64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(3, 64)));
+        attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 16)));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<3, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(3, 64)));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<6, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(6, 16, true)));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 64, true)));
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kDot>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
     });
     if (attr_err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
 
-    CUtensorMap map_c;
-    if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, kBatchN))) return rc;
     for (uint32_t q0 = 0; q0 < n_queries; q0 += max_groups * kBatchM) {
         const uint32_t nq = std::min<uint32_t>(n_queries - q0, max_groups * kBatchM);
-        const uint32_t groups = (nq + kBatchM - 1) / kBatchM;
-        uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(e->sm_count) / groups, tiles_total));
-        // kernel shape: 16-entry heaps + 4 stages when 16 nominees per slice comfortably cover k, else 64 + 3
+        uint32_t groups = (nq + kBatchM - 1) / kBatchM;
+        // cta_group::2: CTA pairs (two query groups, one row slice) issue one 256-row MMA and each stages only half of
+        // the corpus tile.  Needs at least two groups; an odd group count is padded with an all-out-of-range group.
+        const bool pair = e->tune.batch_pair != 0 && groups >= 2;
+        if (pair) groups = (groups + 1u) & ~1u;
+        const uint32_t units = pair ? groups / 2u : groups;                       // clusters (or CTAs) per slice
+        const uint32_t unit_slots = static_cast<uint32_t>(e->sm_count) / (pair ? 2u : 1u);
+        uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(unit_slots / units, tiles_total));
+        // kernel shape: 16-entry heaps + more stages when 16 nominees per slice comfortably cover k, else 64-entry heaps
         const bool small_heap = e->tune.batch_heap == 16 || (e->tune.batch_heap == 0 && 16u * slices >= 8u * k_eff);
         const uint32_t kprime = small_heap ? 16u : 64u;
         slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));   // union fits the finish sort
         const uint32_t grid = groups * slices;
         if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
-        if ((rc = ensure_dev(&c->d_tau, &c->tau_cap, static_cast<size_t>(nq), "shared thresholds"))) return rc;
-        CUDA_TRY(cudaMemsetAsync(c->d_tau, 0, nq * sizeof(uint32_t), stream));
-        CUtensorMap map_q;
+        if ((rc = ensure_dev(&c->d_tau, &c->tau_cap, static_cast<size_t>(groups) * kBatchM, "shared thresholds"))) return rc;
+        CUDA_TRY(cudaMemsetAsync(c->d_tau, 0, static_cast<size_t>(groups) * kBatchM * sizeof(uint32_t), stream));
+        CUtensorMap map_q, map_c;
         const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
         if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
+        if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, pair ? kBatchN / 2 : kBatchN))) return rc;
 
         BatchParams bp{};
         bp.n_rows = static_cast<uint32_t>(e->n_rows); bp.dims = e->dims; bp.n_queries = nq; bp.groups = groups;
@@ -525,8 +533,20 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         bp.heaps = c->d_heaps;
         bp.tau_global = c->d_tau;
         bp.no_insert = e->tune.batch_noinsert ? 1u : 0u;
-        if (small_heap) batch_tf32_kernel<4, 16><<<grid, kBatchThreads, batch_smem_bytes(4, 16), stream>>>(map_q, map_c, bp);
-        else batch_tf32_kernel<3, 64><<<grid, kBatchThreads, batch_smem_bytes(3, 64), stream>>>(map_q, map_c, bp);
+        if (pair) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBatchThreads); cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (small_heap) { cfg.dynamicSmemBytes = batch_smem_bytes(6, 16, true); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_kernel<6, 16, true>, map_q, map_c, bp)); }
+            else { cfg.dynamicSmemBytes = batch_smem_bytes(4, 64, true); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_kernel<4, 64, true>, map_q, map_c, bp)); }
+        } else if (small_heap) {
+            batch_tf32_kernel<4, 16, false><<<grid, kBatchThreads, batch_smem_bytes(4, 16), stream>>>(map_q, map_c, bp);
+        } else {
+            batch_tf32_kernel<3, 64, false><<<grid, kBatchThreads, batch_smem_bytes(3, 64), stream>>>(map_q, map_c, bp);
+        }
         CUDA_TRY(cudaGetLastError());
 
         FinishParams fp{};
@@ -1321,6 +1341,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_min")) e->tune.batch_min = v;
     else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;
     else if (!strcmp(key, "batch_heap")) e->tune.batch_heap = v;
+    else if (!strcmp(key, "batch_pair")) e->tune.batch_pair = v;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);
