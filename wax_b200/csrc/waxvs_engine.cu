@@ -279,7 +279,7 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     // and give short rows more warps (their bound is per-row instruction latency, not bytes in flight)
     int R, warps_default = 8;
     if (C == 0) {                                        // generic shape: run-time chunk count, query in shared memory
-        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d > 2048 ? 1 : 2);
+        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d >= 2048 ? 1 : 2);
     } else if (C >= 6) {
         R = e->tune.rows_per_step == 2 || e->tune.rows_per_step == 4 ? e->tune.rows_per_step : 2;
     } else {
