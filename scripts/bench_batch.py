@@ -31,12 +31,13 @@ for cfg in CONFIGS:
     rng = np.random.default_rng(1)
     qs = rng.uniform(-1, 1, size=(cfg["batch"], cfg["dims"])).astype(np.float32)
     qs /= np.linalg.norm(qs, axis=1, keepdims=True)
-    eng.search_batch(qs, cfg["k"])
+    eng.search_batch_arrays(qs, cfg["k"])
     t0, f0 = eng.batch_stats()
     t = time.perf_counter()
     for _ in range(steps):
-        res = eng.search_batch(qs, cfg["k"])
+        ids, scores, ns = eng.search_batch_arrays(qs, cfg["k"])
     e2e_s = (time.perf_counter() - t) / steps
+    res = [[(int(ids[0, 0]), float(scores[0, 0]))]]
     t1, f1 = eng.batch_stats()
     single_ms, _ = eng.time_search(cfg["k"], 5, warmup=2, n_queries=2)
     line = {
@@ -48,7 +49,7 @@ for cfg in CONFIGS:
                      "useful_flops_per_launch": flops, "hbm_floor_ms": cfg["rows"] * cfg["dims"] * 4 / 7.5e12 * 1e3},
         "e2e": {"value": cfg["batch"] / e2e_s, "unit": "queries/s", "ms_per_batch": e2e_s * 1e3,
                 "h2d_bytes_per_step": int(qs.nbytes), "d2h_bytes_per_step": cfg["batch"] * cfg["k"] * 24,
-                "api": "wax_vs_search_batch (host queries -> host ids/scores)"},
+                "api": "wax_vs_search_batch (host queries -> host ids/scores arrays)"},
         "gpu_launches_per_batch": launches / steps, "unproven_queries_last_step": bad,
         "tensor_path_queries": t1 - t0, "exact_fallback_queries": f1 - f0,
         "single_query_path_ms": single_ms / 5, "speedup_vs_single_query_loop": (single_ms / 5) * cfg["batch"] / per,

@@ -71,6 +71,45 @@ public actor CUDAVectorEngine {
         }
     }
 
+    /// Batched form (no counterpart in the reference protocol): one tensor-core pass over the corpus nominates,
+    /// an exact fp32 re-score decides; results are identical to calling `search` per query.
+    public func searchBatch(vectors: [[Float]], topK: Int) async throws -> [[(frameId: UInt64, score: Float)]] {
+        guard !vectors.isEmpty else { return [] }
+        let dims = dimensions
+        for v in vectors where v.count != dims {
+            throw WaxError.encodingError(reason: "vector dimension mismatch: expected \(dims), got \(v.count)")
+        }
+        let handle = self.handle
+        let cap = min(max(topK, 1), Self.maxResults)
+        return try await io.run {
+            var flat = [Float](); flat.reserveCapacity(vectors.count * dims)
+            for v in vectors { flat.append(contentsOf: v) }
+            var ids = [UInt64](repeating: 0, count: vectors.count * cap)
+            var scores = [Float](repeating: 0, count: vectors.count * cap)
+            var counts = [UInt32](repeating: 0, count: vectors.count)
+            let rc = wax_vs_search_batch(handle, flat, UInt32(vectors.count), UInt32(dims), Int64(topK),
+                                         &ids, &scores, UInt32(cap), &counts)
+            guard rc == WAX_VS_OK else { throw Self.error(rc) }
+            return (0..<vectors.count).map { q in (0..<Int(counts[q])).map { (ids[q * cap + $0], scores[q * cap + $0]) } }
+        }
+    }
+
+    /// Frame filter pushed below the top-k (replaces the post-hoc filter + 3 x topK over-fetch of
+    /// UnifiedSearch.swift:58,1241-1258): `allow == true` keeps only `frameIds`, `false` excludes them.
+    public func search(vector: [Float], topK: Int, frameIds: [UInt64], allow: Bool) async throws -> [(frameId: UInt64, score: Float)] {
+        let handle = self.handle
+        let cap = min(max(topK, 1), Self.maxResults)
+        return try await io.run {
+            var ids = [UInt64](repeating: 0, count: cap)
+            var scores = [Float](repeating: 0, count: cap)
+            var n: UInt32 = 0
+            let rc = wax_vs_search_filtered(handle, vector, UInt32(vector.count), Int64(topK), frameIds,
+                                            UInt64(frameIds.count), allow ? 0 : 1, &ids, &scores, UInt32(cap), &n)
+            guard rc == WAX_VS_OK else { throw Self.error(rc) }
+            return (0..<Int(n)).map { (ids[$0], scores[$0]) }
+        }
+    }
+
     public func add(frameId: UInt64, vector: [Float]) async throws {
         try await addBatch(frameIds: [frameId], vectors: [vector])
     }

@@ -210,10 +210,16 @@ class CUDAVectorEngine:
         return [(int(out_ids[i]), float(scores[i])) for i in range(n.value)]
 
     def search_batch(self, vectors, top_k: int) -> List[List[Tuple[int, float]]]:
+        ids, scores, ns = self.search_batch_arrays(vectors, top_k)
+        return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(ids.shape[0])]
+
+    def search_batch_arrays(self, vectors, top_k: int):
+        """Batched search returning arrays: (ids u64 [B, k_eff], scores f32 [B, k_eff], counts u32 [B]); row i holds
+        counts[i] results, best first.  The list-of-tuples form above costs more host time than the GPU pass."""
         qs = _as_rows(vectors, self.dimensions) if len(vectors) else np.zeros((0, self.dimensions), np.float32)
         b = qs.shape[0]
         if b == 0:
-            return []
+            return np.zeros((0, 0), np.uint64), np.zeros((0, 0), np.float32), np.zeros(0, np.uint32)
         n_rows = self.count
         cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(n_rows, 1)))
         ids = np.zeros((b, cap), np.uint64)
@@ -223,7 +229,7 @@ class CUDAVectorEngine:
                                            int(top_k), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
                                            scores.ctypes.data_as(C.POINTER(C.c_float)), cap,
                                            ns.ctypes.data_as(C.POINTER(C.c_uint32))))
-        return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(b)]
+        return ids, scores, ns
 
     def add(self, frame_id: int, vector: Sequence[float]) -> None:
         v = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
