@@ -110,3 +110,21 @@ def test_cta_pair_mode_equals_single_query_path(oracle, metric, dims, n, b, k):
     assert got == _single(eng, qs, k)
     if n >= 1000:
         assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"
+
+
+@pytest.mark.parametrize("dims,n,b,k", [(384, 100_003, 256, 10), (384, 100_003, 300, 10), (256, 30_001, 200, 100),
+                                        (384, 50_000, 1024, 72), (128, 65, 129, 10), (384, 20_000, 130, 1)])
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+def test_queries_in_tmem_shape_equals_single_query_path(oracle, metric, dims, n, b, k):
+    """TS + pair shape: the queries are written once into tensor memory (tcgen05.st) and every MMA reads its A
+    operand from there, so shared memory only carries the corpus.  Same nominees -> same proof -> identical results."""
+    eng = _engine(oracle, metric, n, dims, seed=970 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_ts", 1)
+    qs = oracle.synth_rows(971 + b, 0, b, dims, normalize=True)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, k)
+    t1, f1 = eng.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == b
+    assert got == _single(eng, qs, k)
+    if n >= 1000:
+        assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"

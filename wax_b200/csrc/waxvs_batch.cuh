@@ -499,6 +499,286 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     }
 }
 
+
+// ---- TS + pair kernel: the queries live in TMEM ---------------------------------------------------------------------
+// Removes the shared-memory bandwidth bound of the SS shapes: the A operand (128 queries x dims
+// tf32 per CTA) is written ONCE into tensor memory (tcgen05.st, `dims` <= 384 columns) and every MMA reads it from
+// there (`tcgen05.mma ... [d], [a_tmem], b_desc`), so shared memory only carries the corpus: with the CTA pair each
+// CTA stages 32 rows x 32 floats = 4 KB per k-block per 128 MMA cycles (64 B/clk in + out instead of 192).
+//   TMEM columns: [0, dims) queries | [384, 448) accumulators 0 | [448, 512) accumulators 1   (N = 64 rows per tile)
+constexpr int kTsN = 64;                 // corpus rows per tile (UMMA N); each CTA of the pair stages half
+constexpr int kTsKbPerStage = 4;         // k-blocks per stage: 16 small MMAs per barrier round trip (a single thread
+                                         // cannot wait + commit every 128 cycles), so dims % 128 == 0
+constexpr int kTsStages = 6;
+constexpr uint32_t kTsBoxBytes = (kTsN / 2) * 128u;               // one k-block of this CTA's half tile: 4 KB
+constexpr uint32_t kTsStageBytes = kTsKbPerStage * kTsBoxBytes;  // 16 KB
+constexpr uint32_t kTsAccCol = 384;
+__host__ __device__ constexpr uint32_t batch_ts_smem_bytes(int heap) {
+    return kTsStages * kTsStageBytes + 2 * kTsN * 4 /*scales*/ + 1024 /*barriers*/ + kBatchStageSlots * kBatchM * 8 +
+           heap * kBatchM * 8 + 1024 /*align*/;
+}
+__host__ __device__ constexpr uint32_t umma_idesc_tf32_m256_n64() {
+    return (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((256u >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};\n" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]), "r"(v[18]),
+        "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]), "r"(v[27]),
+        "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+        : "memory");
+}
+
+template <int HEAP>
+__global__ void __launch_bounds__(kBatchThreads, 1)
+batch_tf32_ts_kernel(const __grid_constant__ CUtensorMap tmap_c, const float *__restrict__ queries, const BatchParams p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t *stages = smem;                                                            // [stage][32 rows x 128 B]
+    float *scale_smem = reinterpret_cast<float *>(smem + kTsStages * kTsStageBytes);   // [2][64]
+    uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kTsN);              // [stages]
+    uint64_t *empty = full + kTsStages;                                                // [stages]
+    uint64_t *tmem_full = empty + kTsStages;                                           // [2]
+    uint64_t *tmem_empty = tmem_full + 2;                                              // [2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
+    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + kTsStages * kTsStageBytes + 2 * kTsN * 4 + 1024);
+    uint64_t *heap_smem = stage_smem + kBatchStageSlots * kBatchM;
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t unit = blockIdx.x / 2u, units_per_slice = p.groups / 2u;
+    const uint32_t group = (unit % units_per_slice) * 2u + rank, slice = unit / units_per_slice;
+    const bool leader = rank == 0u;
+    const uint32_t tile_lo = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * slice / p.slices);
+    const uint32_t tile_hi = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * (slice + 1) / p.slices);
+    const uint32_t num_kb = p.dims / kBatchKBlock;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tmap_c);
+        for (int s = 0; s < kTsStages; ++s) { mbar_init(&full[s], 2); mbar_init(&empty[s], 1); }
+        for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], 8); }
+        mbar_fence_init();
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    __syncthreads();
+    tcgen05_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp < 4) {
+        // queries -> TMEM: thread t writes query (group*128 + t) into lane t, columns [0, dims) (zeros if out of range)
+        const uint32_t q = group * kBatchM + threadIdx.x;
+        const float4 *src = reinterpret_cast<const float4 *>(queries + static_cast<size_t>(q) * p.dims);
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        for (uint32_t c0 = 0; c0 < p.dims; c0 += 32u) {
+            uint32_t v[32];
+#pragma unroll
+            for (uint32_t j4 = 0; j4 < 8; ++j4) {
+                float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (q < p.n_queries) x = __ldg(src + (c0 >> 2) + j4);
+                v[4 * j4 + 0] = __float_as_uint(x.x); v[4 * j4 + 1] = __float_as_uint(x.y);
+                v[4 * j4 + 2] = __float_as_uint(x.z); v[4 * j4 + 3] = __float_as_uint(x.w);
+            }
+            tmem_st_32x32(tmem_base + lane_base + c0, v);
+        }
+        asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();            // barriers initialised and both CTAs' queries resident before any MMA / remote arrive
+    tcgen05_fence_after();
+
+    if (warp == 4) {
+        // ===== TMA producer (both CTAs: each stages its half of the corpus tile) =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (uint32_t tile = tile_lo; tile < tile_hi; ++tile) {
+                for (uint32_t kb = 0; kb < num_kb; kb += kTsKbPerStage) {
+                    mbar_wait_parity(&empty[stage], phase ^ 1u);
+                    if (leader) mbar_arrive_expect_tx(&full[stage], 2u * kTsStageBytes);
+                    else mbar_arrive_remote(&full[stage], 0u);
+#pragma unroll
+                    for (uint32_t i = 0; i < kTsKbPerStage; ++i)
+                        tma_load_2d_pair(stages + stage * kTsStageBytes + i * kTsBoxBytes, &tmap_c, &full[stage],
+                                         static_cast<int32_t>((kb + i) * kBatchKBlock),
+                                         static_cast<int32_t>(tile * kTsN + rank * (kTsN / 2)));
+                    if (++stage == kTsStages) { stage = 0; phase ^= 1u; }
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ===== MMA issuer: the leader CTA's single thread issues the 256-row MMAs for the pair =====
+        if (lane == 0 && leader) {
+            constexpr uint32_t idesc = umma_idesc_tf32_m256_n64();
+            uint32_t stage = 0, phase = 0, t = 0;
+            for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
+                const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+                mbar_wait_parity(&tmem_empty[acc], acc_phase ^ 1u);
+                tcgen05_fence_after();
+                const uint32_t d_tmem = tmem_base + kTsAccCol + acc * kTsN;
+                for (uint32_t kb = 0; kb < num_kb; kb += kTsKbPerStage) {
+                    mbar_wait_parity(&full[stage], phase);
+                    tcgen05_fence_after();
+#pragma unroll
+                    for (uint32_t i = 0; i < kTsKbPerStage; ++i) {
+                        const uint64_t db = umma_desc_k_sw128(stages + stage * kTsStageBytes + i * kTsBoxBytes);
+#pragma unroll
+                        for (uint32_t j = 0; j < kBatchKBlock / 8; ++j)   // A: 8 tf32 = 8 TMEM columns per K step
+                            umma_tf32_ts_pair(d_tmem, tmem_base + (kb + i) * kBatchKBlock + j * 8u, db + 2 * j, idesc,
+                                              (kb | i | j) != 0u ? 1u : 0u);
+                    }
+                    tcgen05_commit_pair(&empty[stage]);
+                    if (++stage == kTsStages) { stage = 0; phase ^= 1u; }
+                }
+                tcgen05_commit_pair(&tmem_full[acc]);
+            }
+        }
+    } else {
+        // ===== epilogue (same nomination scheme as batch_tf32_kernel, 64 columns per tile) =====
+        const uint32_t tid = threadIdx.x;
+        const uint32_t q = group * kBatchM + tid;
+        const bool q_valid = q < p.n_queries && !p.no_insert;
+        uint64_t *heap = heap_smem + tid;
+        for (uint32_t i = 0; i < HEAP; ++i) heap[i * kBatchM] = WAXVS_KEY_NONE;
+        uint64_t root = WAXVS_KEY_NONE;
+        float tau = -INFINITY;
+        uint64_t *stage = stage_smem + tid;
+        uint32_t cnt = 0;
+        bool improved = false;
+        auto flush = [&]() {
+            for (uint32_t i = 0; i < cnt; ++i) {
+                const uint64_t x = stage[i * kBatchM];
+                if (x < root) { root = heap_replace_root<HEAP>(heap, x); improved = true; }
+            }
+            cnt = 0;
+            if (root != WAXVS_KEY_NONE) tau = fmaxf(tau, nominee_score(root));
+        };
+        const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        // the row scales of the NEXT tile are fetched while the current one is processed
+        float next_scale = 0.0f;
+        if (p.row_scale && tid < kTsN && tile_lo < tile_hi) {
+            const uint32_t r = tile_lo * kTsN + tid;
+            next_scale = (r < p.n_rows) ? __ldg(p.row_scale + r) : 0.0f;
+        }
+        uint32_t t = 0;
+        for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
+            const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
+            const uint32_t row0 = tile * kTsN;
+            float *sc = scale_smem + acc * kTsN;
+            if (p.row_scale && tid < kTsN) {
+                sc[tid] = next_scale;
+                const uint32_t r = row0 + kTsN + tid;
+                next_scale = (tile + 1 < tile_hi && r < p.n_rows) ? __ldg(p.row_scale + r) : 0.0f;
+            }
+            if (q_valid && (t & 7u) == 0u) {
+                const uint32_t g = __ldcg(p.tau_global + q);
+                if (g) tau = fmaxf(tau, from_orderable_u32(g));
+            }
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            mbar_wait_parity(&tmem_full[acc], acc_phase);
+            tcgen05_fence_after();
+            const uint32_t rows_here = min(static_cast<uint32_t>(kTsN), p.n_rows - row0);
+#pragma unroll 1
+            for (uint32_t chunk = 0; chunk < kTsN / 32; ++chunk) {
+                uint32_t v[32];
+                tmem_ld_32x32(tmem_base + lane_base + kTsAccCol + acc * kTsN + chunk * 32u, v);
+                if (chunk * 32u >= rows_here) continue;
+                float sv[32];
+                if (p.row_scale) {
+                    const float4 *sc4 = reinterpret_cast<const float4 *>(sc + chunk * 32u);
+#pragma unroll
+                    for (uint32_t j4 = 0; j4 < 8; ++j4) {
+                        const float4 w = sc4[j4];
+                        sv[4 * j4 + 0] = __uint_as_float(v[4 * j4 + 0]) * w.x;
+                        sv[4 * j4 + 1] = __uint_as_float(v[4 * j4 + 1]) * w.y;
+                        sv[4 * j4 + 2] = __uint_as_float(v[4 * j4 + 2]) * w.z;
+                        sv[4 * j4 + 3] = __uint_as_float(v[4 * j4 + 3]) * w.w;
+                    }
+                } else {
+#pragma unroll
+                    for (uint32_t j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
+                }
+                float m16[16], m8[8], m4[4], m2[2];
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) m16[j] = fmaxf(sv[j], sv[j + 16]);
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) m8[j] = fmaxf(m16[j], m16[j + 8]);
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) m4[j] = fmaxf(m8[j], m8[j + 4]);
+#pragma unroll
+                for (uint32_t j = 0; j < 2; ++j) m2[j] = fmaxf(m4[j], m4[j + 2]);
+                if (fmaxf(m2[0], m2[1]) > tau && q_valid) {
+                    auto leaf = [&](uint32_t j, float sj) {
+                        const uint32_t col = chunk * 32u + j;
+                        if (sj > tau && col < rows_here) {
+                            if (cnt == kBatchStageSlots) flush();
+                            stage[cnt * kBatchM] = nominee_key(sj, row0 + col);
+                            ++cnt;
+                        }
+                    };
+#pragma unroll
+                    for (uint32_t a = 0; a < 2; ++a) {
+                        if (!(m2[a] > tau)) continue;
+#pragma unroll
+                        for (uint32_t b = 0; b < 2; ++b) {
+                            const uint32_t i4 = a + 2 * b;
+                            if (!(m4[i4] > tau)) continue;
+#pragma unroll
+                            for (uint32_t c = 0; c < 2; ++c) {
+                                const uint32_t i8 = i4 + 4 * c;
+                                if (!(m8[i8] > tau)) continue;
+#pragma unroll
+                                for (uint32_t d = 0; d < 2; ++d) {
+                                    const uint32_t i16 = i8 + 8 * d;
+                                    if (!(m16[i16] > tau)) continue;
+                                    leaf(i16, sv[i16]);
+                                    leaf(i16 + 16, sv[i16 + 16]);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            tcgen05_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_remote(&tmem_empty[acc], 0u);
+            if (__any_sync(WAXVS_FULL_MASK, cnt >= kBatchStageSlots / 2)) {
+                flush();
+                if (improved && q_valid && root != WAXVS_KEY_NONE) {
+                    atomicMax(p.tau_global + q, orderable_u32(nominee_score(root)));
+                    improved = false;
+                }
+            }
+        }
+        flush();
+        uint64_t *dst = p.heaps + static_cast<size_t>(slice * p.groups + group) * HEAP * kBatchM + tid;
+        for (uint32_t i = 0; i < HEAP; ++i) dst[i * kBatchM] = heap[i * kBatchM];
+    }
+    tcgen05_fence_before();
+    cluster_sync_all();
+    if (warp == 5) {
+        tcgen05_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512) : "memory");
+    }
+}
+
 // ---- exact re-score + proof ------------------------------------------------------------------------------------------
 // Exact distance of one row by one warp: the generic-dims code path of scan_ldg_kernel, same order, same bits.
 template <int METRIC>

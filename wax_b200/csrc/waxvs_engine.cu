@@ -116,7 +116,8 @@ struct Tuning {
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
     int time_overlap = 0;   // wax_vs_debug_time_search: alternate consecutive queries over two streams
-    int batch_pair = 0;     // 1: cta_group::2 CTA pairs (experimental until validated on hardware)
+    int batch_pair = 0;     // 1: cta_group::2 CTA pairs for the SS shapes (validated; no net gain)
+    int batch_ts = 0;       // 1: queries in TMEM + CTA pairs (dims <= 384, dims % 128 == 0)
     int batch_heap = 0;     // 0 auto, 16 or 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
 };
@@ -489,7 +490,6 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
-    const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + kBatchN - 1) / kBatchN);
     const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -497,6 +497,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 16)));
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<3, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(3, 64)));
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<6, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(6, 16, true)));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_ts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_ts_smem_bytes(16)));
+        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_ts_smem_bytes(64)));
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 64, true)));
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
         if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kDot>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
@@ -508,8 +510,12 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         uint32_t groups = (nq + kBatchM - 1) / kBatchM;
         // cta_group::2: CTA pairs (two query groups, one row slice) issue one 256-row MMA and each stages only half of
         // the corpus tile.  Needs at least two groups; an odd group count is padded with an all-out-of-range group.
-        const bool pair = e->tune.batch_pair != 0 && groups >= 2;
+        // TS shape: queries in TMEM + CTA pair (dims <= 384, dims % 128 == 0): shared memory carries only the corpus
+        const bool ts = e->tune.batch_ts != 0 && groups >= 2 && e->dims <= 384 && e->dims % 128u == 0;
+        const bool pair = ts || (e->tune.batch_pair != 0 && groups >= 2);
         if (pair) groups = (groups + 1u) & ~1u;
+        const uint32_t tile_rows = ts ? static_cast<uint32_t>(kTsN) : static_cast<uint32_t>(kBatchN);
+        const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + tile_rows - 1) / tile_rows);
         const uint32_t units = pair ? groups / 2u : groups;                       // clusters (or CTAs) per slice
         const uint32_t unit_slots = static_cast<uint32_t>(e->sm_count) / (pair ? 2u : 1u);
         uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(unit_slots / units, tiles_total));
@@ -524,7 +530,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         CUtensorMap map_q, map_c;
         const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
         if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
-        if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, pair ? kBatchN / 2 : kBatchN))) return rc;
+        if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, ts ? kTsN / 2 : (pair ? kBatchN / 2 : kBatchN)))) return rc;
 
         BatchParams bp{};
         bp.n_rows = static_cast<uint32_t>(e->n_rows); bp.dims = e->dims; bp.n_queries = nq; bp.groups = groups;
@@ -533,7 +539,16 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         bp.heaps = c->d_heaps;
         bp.tau_global = c->d_tau;
         bp.no_insert = e->tune.batch_noinsert ? 1u : 0u;
-        if (pair) {
+        if (ts) {
+            cudaLaunchConfig_t cfg{};
+            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBatchThreads); cfg.stream = stream;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            if (small_heap) { cfg.dynamicSmemBytes = batch_ts_smem_bytes(16); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<16>, map_c, qbase, bp)); }
+            else { cfg.dynamicSmemBytes = batch_ts_smem_bytes(64); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<64>, map_c, qbase, bp)); }
+        } else if (pair) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBatchThreads); cfg.stream = stream;
             cudaLaunchAttribute attr[1];
@@ -1342,6 +1357,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;
     else if (!strcmp(key, "batch_heap")) e->tune.batch_heap = v;
     else if (!strcmp(key, "batch_pair")) e->tune.batch_pair = v;
+    else if (!strcmp(key, "batch_ts")) e->tune.batch_ts = v;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);
