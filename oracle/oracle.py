@@ -88,7 +88,22 @@ def _p(a: np.ndarray, t):
 
 
 def host_threads() -> int:
-    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    """Host cores this process can really use: the affinity mask, capped by the cgroup CPU quota when there is one
+    (a container may see 128 CPUs in its mask and still be limited to a few cores' worth of time)."""
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        quota, period = Path("/sys/fs/cgroup/cpu.max").read_text().split()[:2]
+        if quota != "max":
+            n = max(1, min(n, int(float(quota) / float(period) + 0.5)))
+    except Exception:
+        try:
+            q = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read_text())
+            per = int(Path("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read_text())
+            if q > 0 and per > 0:
+                n = max(1, min(n, int(q / per + 0.5)))
+        except Exception:
+            pass
+    return n
 
 
 def score_from_distance(metric: int, d: float) -> float:

@@ -57,12 +57,12 @@ static void stats_f64(const float *a, const float *b, uint32_t n, int metric, do
 
 /* 128 interleaved accumulators -> ((a0+a1)+(a2+a3)) per lane -> xor butterfly over 32 lanes.    */
 static float tree_reduce128(const float *acc) {
-    float t[32], u[32];
+    float t[32];
     for (int l = 0; l < 32; ++l) t[l] = (acc[4 * l] + acc[4 * l + 1]) + (acc[4 * l + 2] + acc[4 * l + 3]);
-    for (int off = 16; off >= 1; off >>= 1) {
-        for (int l = 0; l < 32; ++l) u[l] = t[l] + t[l ^ off];
-        memcpy(t, u, sizeof t);
-    }
+    /* lane 0 of the xor butterfly (16,8,4,2,1): at every level lane l < off holds t[l] + t[l ^ off]; only those
+       lanes feed the next level, so the other half need not be computed. */
+    for (int off = 16; off >= 1; off >>= 1)
+        for (int l = 0; l < off; ++l) t[l] = t[l] + t[l + off];
     return t[0];
 }
 
