@@ -24,8 +24,9 @@ for rows in (10_000, 100_000, 1_250_000, 2_500_000, 5_000_000, 10_000_000):
         eng.search(q, 10)
     e2e_us = (time.perf_counter() - t0) / n * 1e6
     ms, _ = eng.time_search(10, n, warmup=5, n_queries=8)
+    ms72, _ = eng.time_search(72, n, warmup=5, n_queries=8)
     rec = {"rows": rows, "kernel_us_back_to_back": round(ms / n * 1e3, 2), "e2e_us_sync_call": round(e2e_us, 2),
-           "gbs_kernel": round(rows * 384 * 4 / (ms / n) / 1e6, 1)}
+           "gbs_kernel": round(rows * 384 * 4 / (ms / n) / 1e6, 1), "kernel_us_k72": round(ms72 / n * 1e3, 2)}
     out.append(rec); print(json.dumps(rec), flush=True)
     eng.close()
 Path(sys.argv[1] if len(sys.argv) > 1 else ROOT / "gpurun_out" / "latency.json").write_text(json.dumps(out, indent=1))

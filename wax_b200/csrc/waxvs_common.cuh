@@ -91,15 +91,129 @@ __device__ __forceinline__ void warp_reduce_scatter(float (&v)[R], int lane) {
     for (; off >= 1; off >>= 1) v[0] = __fadd_rn(v[0], __shfl_xor_sync(WAXVS_FULL_MASK, v[0], off));
 }
 
+// ---- bitonic merge of two sorted distributed lists (entry i in key[i / 32] of lane i % 32) ---------------------------
+// min(mine[i], other[W-1-i]) holds the W smallest keys of the union as a bitonic sequence; a log2(W)-stage
+// compare-exchange network sorts it (strides >= 32 are register-to-register between slots, smaller strides one shuffle
+// pair per slot): ~12 E shuffles however many entries change, against one ~10 E-shuffle insertion per entering key.
+// Keys are unique (row in the low bits), so the k smallest of the union do not depend on how they were merged: same
+// bits as sequential insertion.
+template <int E>
+__device__ __forceinline__ void bitonic_merge_lists(uint64_t (&key)[E], uint64_t &thresh, const uint64_t (&other)[E],
+                                                    int lane, int k) {
+    static_assert(E == 1 || E == 2 || E == 4 || E == 8, "E must be a power of two");
+    if (shfl_u64(other[0], 0) >= thresh) return;  // warp-uniform: nothing of `other` beats the current k-th
+    uint64_t m[E];
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        const uint64_t r = shfl_u64(other[E - 1 - j], 31 - lane);
+        m[j] = key[j] < r ? key[j] : r;
+    }
+#pragma unroll
+    for (int sj = E / 2; sj >= 1; sj >>= 1) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            if ((j & sj) == 0) {
+                const uint64_t lo = m[j] < m[j + sj] ? m[j] : m[j + sj];
+                const uint64_t hi = m[j] < m[j + sj] ? m[j + sj] : m[j];
+                m[j] = lo; m[j + sj] = hi;
+            }
+        }
+    }
+#pragma unroll
+    for (int s = 16; s >= 1; s >>= 1) {
+        const bool upper = (lane & s) != 0;
+#pragma unroll
+        for (int j = 0; j < E; ++j) {
+            const uint32_t plo = __shfl_xor_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(m[j]), s);
+            const uint32_t phi = __shfl_xor_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(m[j] >> 32), s);
+            const uint64_t partner = (static_cast<uint64_t>(phi) << 32) | plo;
+            const bool take = upper ? (partner > m[j]) : (partner < m[j]);
+            if (take) m[j] = partner;
+        }
+    }
+    uint64_t t = WAXVS_KEY_NONE;
+#pragma unroll
+    for (int j = 0; j < E; ++j) {
+        key[j] = (j * 32 + lane < k) ? m[j] : WAXVS_KEY_NONE;
+        const uint64_t cand = shfl_u64(key[j], (k - 1) & 31);
+        if (((k - 1) >> 5) == j) t = cand;
+    }
+    thresh = t;
+}
+
+// In-warp bitonic sort of one key per lane, ascending over the lane index (15 compare-exchange stages).
+__device__ __forceinline__ uint64_t warp_sort_ascending(uint64_t v, int lane) {
+#pragma unroll
+    for (int size = 2; size <= 32; size <<= 1) {
+#pragma unroll
+        for (int stride = size / 2; stride >= 1; stride >>= 1) {
+            const uint32_t plo = __shfl_xor_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(v), stride);
+            const uint32_t phi = __shfl_xor_sync(WAXVS_FULL_MASK, static_cast<uint32_t>(v >> 32), stride);
+            const uint64_t partner = (static_cast<uint64_t>(phi) << 32) | plo;
+            const bool ascending = (lane & size) == 0;          // size == 32: the whole warp ascends
+            const bool lower = (lane & stride) == 0;
+            const bool take = (lower == ascending) ? (partner < v) : (partner > v);
+            if (take) v = partner;
+        }
+    }
+    return v;
+}
+
+// Out-of-line forms for the wide lists (E > 1): the merge is ~150 instructions and is reached from several places of
+// kernels whose main loop the compiler clones; inlined, the copies made a 10 K-instruction kernel whose one-shot tail
+// ran at instruction-cache-miss speed.  Values travel by value (registers / param space), nothing stays in local memory.
+template <int E> struct TopKRegs { uint64_t key[E]; uint64_t thresh; };
+
+template <int E>
+__device__ __noinline__ TopKRegs<E> merge_lists_call(TopKRegs<E> mine, TopKRegs<E> other, int lane, int k) {
+    bitonic_merge_lists<E>(mine.key, mine.thresh, other.key, lane, k);
+    return mine;
+}
+template <int E>
+__device__ __noinline__ TopKRegs<E> flush_call(TopKRegs<E> mine, uint64_t pend, int npend, int lane, int k) {
+    uint64_t other[E];
+    const uint64_t v = warp_sort_ascending((lane < npend) ? pend : WAXVS_KEY_NONE, lane);
+#pragma unroll
+    for (int j = 0; j < E; ++j) other[j] = (j == 0) ? v : WAXVS_KEY_NONE;
+    bitonic_merge_lists<E>(mine.key, mine.thresh, other, lane, k);
+    return mine;
+}
+
 // ---- per-warp sorted top-k list in registers: k <= 32*E, entry i lives in key[i / 32] of lane i % 32 ------------
 template <int E>
 struct WarpTopK {
     uint64_t key[E];   // sorted ascending over the entry index; WAXVS_KEY_NONE beyond k
     uint64_t thresh;   // key of entry k-1 (warp-uniform): only strictly smaller keys enter
+    uint64_t pend;     // E > 1: candidates waiting for the next batched merge, one per lane (lanes < npend)
+    int npend;         // warp-uniform
     __device__ __forceinline__ void init() {
 #pragma unroll
         for (int j = 0; j < E; ++j) key[j] = WAXVS_KEY_NONE;
         thresh = WAXVS_KEY_NONE;
+        pend = WAXVS_KEY_NONE;
+        npend = 0;
+    }
+    // Batched insertion (used for E > 1, where a single insertion is a ~30-shuffle dependent chain): candidates that
+    // beat the current threshold are parked one per lane; when 32 are waiting (or at the end of the scan) they are
+    // sorted in-warp (15 compare-exchange stages) and bitonic-merged into the list.  The threshold is a little stale
+    // between flushes, so a few more candidates are parked than strictly enter -- the merge discards them.  The
+    // list after the last flush is the k smallest keys seen, whatever the batching: same bits as one-by-one insertion.
+    __device__ __forceinline__ void park(uint64_t x, int lane) {   // x warp-uniform, npend < 32
+        if (lane == npend) pend = x;
+        ++npend;
+    }
+    __device__ __forceinline__ void flush(int lane, int k) {
+        if (npend == 0) return;
+        TopKRegs<E> a;
+#pragma unroll
+        for (int j = 0; j < E; ++j) a.key[j] = key[j];
+        a.thresh = thresh;
+        a = flush_call<E>(a, pend, npend, lane, k);
+#pragma unroll
+        for (int j = 0; j < E; ++j) key[j] = a.key[j];
+        thresh = a.thresh;
+        pend = WAXVS_KEY_NONE;
+        npend = 0;
     }
     // x is warp-uniform and x < thresh.  One ballot + one shuffle pair per slot.
     __device__ __forceinline__ void insert(uint64_t x, int lane, int k) {
@@ -133,14 +247,17 @@ struct WarpTopK {
     }
     // Merge a sorted list held in the same distributed layout by `other` (entries beyond its length KEY_NONE).
     __device__ __forceinline__ void merge_sorted(const uint64_t (&other)[E], int lane, int k) {
+        if constexpr (E == 1) {
+            bitonic_merge_lists<E>(key, thresh, other, lane, k);
+        } else {
+            TopKRegs<E> a, b;
 #pragma unroll
-        for (int j = 0; j < E; ++j) {
-            for (int l = 0; l < 32; ++l) {
-                if (j * 32 + l >= k) return;
-                const uint64_t x = shfl_u64(other[j], l);
-                if (x >= thresh) return;  // sorted: the rest are worse (KEY_NONE never passes)
-                insert(x, lane, k);
-            }
+            for (int j = 0; j < E; ++j) { a.key[j] = key[j]; b.key[j] = other[j]; }
+            a.thresh = thresh; b.thresh = WAXVS_KEY_NONE;
+            a = merge_lists_call<E>(a, b, lane, k);
+#pragma unroll
+            for (int j = 0; j < E; ++j) key[j] = a.key[j];
+            thresh = a.thresh;
         }
     }
 };

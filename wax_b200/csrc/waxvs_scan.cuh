@@ -82,6 +82,7 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
     for (int j = 0; j < E; ++j) lists[warp * W + j * 32 + lane] = tk.key[j];
     __syncthreads();
     if (warp == 0) {
+#pragma unroll 1
         for (int w = 1; w < warps; ++w) {
             uint64_t other[E];
             load_list(lists + w * W, other);
@@ -98,7 +99,10 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
     __threadfence();
     tk.init();
     // Block lists come from L2 (~1 us each if loaded one by one): fetch four at a time, then merge.
+    // (the merge loops are kept rolled: every inlined merge is ~150 instructions and this code runs once, so unrolled
+    // copies only buy instruction-cache misses -- the E = 4 tail was 80 us of them at 10 K rows)
     constexpr int U = (E == 1) ? 4 : 2;
+#pragma unroll 1
     for (uint32_t b0 = warp; b0 < gridDim.x; b0 += warps * U) {
         uint64_t other[U][E];
 #pragma unroll
@@ -117,6 +121,7 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
     for (int j = 0; j < E; ++j) lists[warp * W + j * 32 + lane] = tk.key[j];
     __syncthreads();
     if (warp == 0) {
+#pragma unroll 1
         for (int w = 1; w < warps; ++w) {
             uint64_t other[E];
             load_list(lists + w * W, other);
@@ -300,16 +305,28 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
             // the filter is consulted only for rows that would enter the list (rare once the list is warm)
             const bool cand = leader && key < tk.thresh && row_allowed(p, my_row);
             uint32_t m = __ballot_sync(WAXVS_FULL_MASK, cand);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const uint64_t x = shfl_u64(key, src);
-                if (x < tk.thresh) tk.insert(x, lane, k);
+            if (E == 1) {
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    const uint64_t x = shfl_u64(key, src);
+                    if (x < tk.thresh) tk.insert(x, lane, k);
+                }
+            } else if (m) {                             // batched insertion (WarpTopK::flush)
+                if (tk.npend + __popc(m) > 32) tk.flush(lane, k);
+                while (m) {
+                    const int src = __ffs(m) - 1;
+                    m &= m - 1;
+                    tk.park(shfl_u64(key, src), lane);
+                }
             }
         }
     }
 
-    if (!EMIT) finish_topk<E>(p, tk, lists, warp, lane, warps);
+    if (!EMIT) {
+        if (E > 1) tk.flush(lane, k);
+        finish_topk<E>(p, tk, lists, warp, lane, warps);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -384,10 +401,19 @@ __global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
             if (lane == 0) p.dist_keys[row] = (ok && row_allowed(p, row)) ? orderable_u32(d) : WAXVS_UKEY_NONE;
         } else if (ok) {
             const uint64_t key = make_key(d, row);
-            if (key < tk.thresh && row_allowed(p, row)) tk.insert(key, lane, k);
+            if (key < tk.thresh && row_allowed(p, row)) {
+                if (E == 1) tk.insert(key, lane, k);
+                else {
+                    if (tk.npend == 32) tk.flush(lane, k);
+                    tk.park(key, lane);
+                }
+            }
         }
     }
-    if (!EMIT) finish_topk<E>(p, tk, lists, warp, lane, warps);
+    if (!EMIT) {
+        if (E > 1) tk.flush(lane, k);
+        finish_topk<E>(p, tk, lists, warp, lane, warps);
+    }
 }
 
 }  // namespace waxvs
