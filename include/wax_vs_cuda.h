@@ -185,6 +185,11 @@ int32_t wax_vs_debug_time_search(wax_vs_engine *engine, uint32_t n_queries, int6
    completed exactness proof, and how many had to be re-run on the exact single-query path. */
 int32_t wax_vs_debug_batch_stats(wax_vs_engine *engine, uint64_t *tensor_queries, uint64_t *fallback_queries);
 
+/* Named instrumentation counters: "batch_tensor_queries", "batch_fallback_queries", "batch_bf16_queries" (queries
+   nominated from the bf16 shadow), "batch_retry_queries" (bf16-unproven queries retried on the TF32 nominations),
+   "shadow_bytes" (HBM held by the bf16 shadow), "pool_allocs", "pool_reuses". */
+int32_t wax_vs_debug_counter(wax_vs_engine *engine, const char *name, uint64_t *out);
+
 /* Device-only timing of the batched path (n_queries synthetic unit queries per step, everything resident):
    total milliseconds of `iters` steps (CUDA events on the launching stream), kernel launches in the bracket and
    the number of queries of the last step whose proof did not complete (they would be re-run exactly). */

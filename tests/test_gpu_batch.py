@@ -26,8 +26,10 @@ def _single(eng, qs, k):
                                         (768, 30_001, 64, 100), (128, 70_000, 17, 32), (32, 9_999, 8, 1),
                                         (384, 255, 6, 10), (384, 257, 6, 10), (384, 1, 4, 10), (1024, 20_000, 33, 10)])
 @pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
-def test_batch_equals_single_query_path(oracle, metric, dims, n, b, k):
+@pytest.mark.parametrize("bf16", [1, 0])
+def test_batch_equals_single_query_path(oracle, metric, dims, n, b, k, bf16):
     eng = _engine(oracle, metric, n, dims, seed=900 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_bf16", bf16)      # 1 (the default): bf16 shadow nominations where dims % 64 == 0; 0: TF32
     qs = oracle.synth_rows(901 + b, 0, b, dims, normalize=True)
     t0, f0 = eng.batch_stats()
     got = eng.search_batch(qs, k)
@@ -101,6 +103,7 @@ def test_cta_pair_mode_equals_single_query_path(oracle, metric, dims, n, b, k):
     """cta_group::2 shape (two CTAs of a cluster issue one 256-row MMA; each stages half of the corpus tile):
     same nominees -> same proof -> identical results."""
     eng = _engine(oracle, metric, n, dims, seed=950 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_bf16", 0)
     eng.set_option("batch_pair", 1)
     qs = oracle.synth_rows(951 + b, 0, b, dims, normalize=True)
     t0, f0 = eng.batch_stats()
@@ -119,6 +122,7 @@ def test_queries_in_tmem_shape_equals_single_query_path(oracle, metric, dims, n,
     """TS + pair shape: the queries are written once into tensor memory (tcgen05.st) and every MMA reads its A
     operand from there, so shared memory only carries the corpus.  Same nominees -> same proof -> identical results."""
     eng = _engine(oracle, metric, n, dims, seed=970 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_bf16", 0)
     eng.set_option("batch_ts", 1)
     qs = oracle.synth_rows(971 + b, 0, b, dims, normalize=True)
     t0, f0 = eng.batch_stats()
@@ -128,3 +132,97 @@ def test_queries_in_tmem_shape_equals_single_query_path(oracle, metric, dims, n,
     assert got == _single(eng, qs, k)
     if n >= 1000:
         assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"
+
+
+@pytest.mark.parametrize("dims,n,b,k", [(384, 100_003, 256, 10), (384, 100_003, 300, 10), (768, 30_001, 200, 100),
+                                        (384, 50_000, 1024, 72), (128, 257, 129, 10), (64, 9_999, 8, 1),
+                                        (512, 40_000, 140, 32), (384, 1, 4, 10), (1024, 20_000, 33, 10)])
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+@pytest.mark.parametrize("pair,ares", [(0, 1), (0, 0), (1, 1), (1, 0)])
+def test_bf16_shadow_nominations_equal_single_query_path(oracle, metric, dims, n, b, k, pair, ares):
+    """bf16 nominations (kind::f16 MMAs over a bf16 shadow of the corpus, queries resident in shared memory or
+    streamed, single CTA or cta_group::2): the nominees differ from the TF32 ones, the RESULTS may not -- the exact
+    fp32 re-score and the completeness proof (with the coarser 2^-7 bound) make them identical to the single-query
+    path, ids and score bits."""
+    eng = _engine(oracle, metric, n, dims, seed=990 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_bf16", 1)
+    eng.set_option("batch_pair", pair)
+    eng.set_option("batch_ares", ares)
+    qs = oracle.synth_rows(991 + b, 0, b, dims, normalize=True)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, k)
+    t1, f1 = eng.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == b
+    assert eng.counter("batch_bf16_queries") == b, "the batch was not nominated from the bf16 shadow"
+    assert eng.counter("shadow_bytes") == n * dims * 2
+    assert got == _single(eng, qs, k)
+    if n >= 1000:
+        assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"
+
+
+def _planted(oracle, dims, n, n_planted, top, step, seed, stride):
+    """Random unit corpus; row i*stride (i < n_planted) has cosine top - i*step to a unit query q.  The planted rows
+    are spread out so that no row slice's 16-entry nominee heap fills up with them."""
+    rng = np.random.default_rng(seed)
+    q = oracle.synth_row(seed, 0, dims, True).astype(np.float64)
+    q /= np.linalg.norm(q)
+    corpus = oracle.synth_rows(seed + 1, 0, n, dims)
+    for i in range(n_planted):
+        r = rng.standard_normal(dims)
+        r -= r.dot(q) * q
+        r /= np.linalg.norm(r)
+        c = top - i * step
+        corpus[i * stride] = (c * q + np.sqrt(1.0 - c * c) * r).astype(np.float32)
+    return q.astype(np.float32), corpus
+
+
+def test_bf16_unproven_queries_retry_on_tf32_before_the_exact_scan(oracle):
+    """600 planted neighbours 2e-5 apart: the 10th result clears the 257th nominee by 0.005 -- inside the bf16
+    bound (0.008), outside the TF32 one (0.0025).  The bf16 pass must flag those queries, the TF32 retry must prove
+    them, nothing reaches the exact scan, and the results are identical to the single-query path."""
+    dims, n = 384, 60_000
+    q, corpus = _planted(oracle, dims, n, 600, 0.95, 2e-5, seed=4100, stride=100)
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.add_batch(list(range(n)), corpus)
+    eng.set_option("batch_bf16", 1)
+    qs = np.stack([q, q * np.float32(2.0), q * np.float32(0.5), q * np.float32(3.0), q * np.float32(1.5),
+                   oracle.synth_row(4200, 0, dims, True)])
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, 10)
+    t1, f1 = eng.batch_stats()
+    assert got == _single(eng, qs, 10)
+    assert [i for i, _ in got[0]] == [100 * i for i in range(10)]
+    assert eng.counter("batch_retry_queries") >= 5
+    assert f1 - f0 == 0, "the TF32 retry level should have proven every query"
+    # adaptive level choice: most of that batch failed the bf16 bound, so the next batches start at TF32
+    n_bf16 = eng.counter("batch_bf16_queries")
+    assert eng.search_batch(qs, 10) == got
+    assert eng.counter("batch_bf16_queries") == n_bf16
+    assert eng.batch_stats()[1] - f0 == 0
+    # retry disabled (setting batch_bf16 re-arms the bf16 level): the same queries go straight to the exact scan
+    eng.set_option("batch_bf16", 1)
+    eng.set_option("batch_retry", 0)
+    got2 = eng.search_batch(qs, 10)
+    assert got2 == got
+    assert eng.counter("batch_bf16_queries") == n_bf16 + len(qs)
+    assert eng.batch_stats()[1] - f0 >= 5
+
+
+def test_bf16_shadow_follows_mutations(oracle):
+    dims = 384
+    corpus = oracle.synth_rows(85, 0, 6000, dims)
+    corpus[7] = 0.0
+    corpus[8, 5] = np.nan
+    corpus[9, 6] = np.inf
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.add_batch(list(range(6000)), corpus)
+    eng.set_option("batch_bf16", 1)
+    qs = oracle.synth_rows(86, 0, 8, dims)
+    assert eng.search_batch(qs, 10) == _single(eng, qs, 10)
+    eng.add(11, corpus[11] * np.float32(1000.0))
+    eng.add_batch([7000, 7001], np.stack([qs[0], qs[1] * np.float32(3.0)]))
+    eng.remove(3)
+    got = eng.search_batch(qs, 10)
+    assert got == _single(eng, qs, 10)
+    assert got[0][0][0] == 7000 and got[1][0][0] == 7001
+    assert eng.counter("shadow_bytes") == 6001 * dims * 2

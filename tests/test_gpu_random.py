@@ -70,6 +70,10 @@ def test_random_batch_and_filter_cases(oracle, seed):
     for opt in ("batch_pair", "batch_ts"):
         eng.set_option(opt, int(rng.integers(0, 2)))
     b = int(rng.choice([4, 9, 130, 257]))
+    # drawn AFTER the shapes above so the earlier draws (and cases) of each seed stay what they were
+    for opt in ("batch_bf16", "batch_ares"):
+        eng.set_option(opt, int(np.random.default_rng(30_000 + seed).integers(0, 2)) if opt == "batch_bf16"
+                       else int(np.random.default_rng(31_000 + seed).integers(0, 2)))
     k = int(rng.choice([1, 10, 72, 100]))
     qs = rng.standard_normal((b, dims)).astype(np.float32)
     got = eng.search_batch(qs, k)

@@ -24,6 +24,7 @@
 // "batched-query case where it is a genuine dense contraction" of BASELINE.json's north_star.
 #pragma once
 #include <cuda.h>
+#include <cuda_bf16.h>
 
 #include "waxvs_common.cuh"
 #include "waxvs_scan.cuh"
@@ -33,6 +34,7 @@ namespace waxvs {
 constexpr int kBatchM = 128;            // queries per CTA  (UMMA M)
 constexpr int kBatchN = 256;            // corpus rows per tile (UMMA N)
 constexpr int kBatchKBlock = 32;        // floats per k-block = one 128-byte swizzle atom
+constexpr int kBatchKBlockBf16 = 64;    // bf16 elements per k-block (the same 128 bytes)
 // Two shapes of the same kernel share the 227 KB of shared memory differently (template <STAGES, HEAP>):
 //   <4, 16>: four TMA stages (192 KB) + 16-entry nominee heaps (16 KB)  -- the pipeline is latency-bound on TMA
 //            (profiles/ncu_batch_tf32_r01b_summary.csv: 3 stages keep the tensor pipe 54 % busy), so the 4th stage
@@ -41,7 +43,8 @@ constexpr int kBatchKBlock = 32;        // floats per k-block = one 128-byte swi
 // PAIR = true is the cta_group::2 form: two CTAs of a cluster (two query groups, the same row slice) issue ONE
 // 256 x 256 x 8 MMA; each CTA stages only its own 128 query rows and HALF of the corpus tile (16 + 16 KB per
 // k-block instead of 16 + 32), so six stages fit where four did and the L2->SM traffic per SM drops by a third.
-constexpr int kBatchRescore = 256;       // nominees of the union re-scored exactly per query
+constexpr int kBatchRescore = 256;       // nominees of the union re-scored exactly per query (TF32 nominations)
+constexpr int kBatchRescoreMax = 1024;   // upper bound (BF16 nominations with larger k re-score more, see eps)
 constexpr uint32_t kBatchABytes = kBatchM * 128u;   // 16 KB
 constexpr uint32_t kBatchBBytes = kBatchN * 128u;   // 32 KB
 constexpr uint32_t kBatchStageBytes = kBatchABytes + kBatchBBytes;
@@ -51,8 +54,20 @@ __host__ __device__ constexpr uint32_t batch_smem_bytes(int stages, int heap, bo
     return stages * batch_stage_bytes(pair) + 2048 /*scales*/ + 256 /*barriers*/ + kBatchStageSlots * kBatchM * 8 /*staging*/ +
            heap * kBatchM * 8 /*heaps*/ + 1024 /*align*/;
 }
+// ARES (queries resident in shared memory): `ares_kb` k-blocks of the 128 queries stay in shared memory for the whole
+// kernel (16 KB each: 6 k-blocks = 96 KB at 384 bf16 dims) and the ring stages carry the corpus only.
+__host__ __device__ constexpr uint32_t batch_ares_stage_bytes(bool pair) { return pair ? kBatchBBytes / 2 : kBatchBBytes; }
+__host__ __device__ constexpr uint32_t batch_ares_smem_bytes(int stages, int heap, bool pair, int ares_kb) {
+    return ares_kb * kBatchABytes + stages * batch_ares_stage_bytes(pair) + 2048 + 256 + kBatchStageSlots * kBatchM * 8 +
+           heap * kBatchM * 8 + 1024;
+}
 constexpr int kBatchThreads = 192;
 constexpr float kTf32Eps = 1.25f * 0x1p-9f;
+// BF16 nominations: both operands are ROUNDED to nearest; bf16 keeps 8 significand bits (7 stored), so the unit
+// round-off is 2^-8: |x~ - x| <= 2^-8 |x| each, |q~ v~ - q v| <= (2^-7 + 2^-16) |q v| termwise, hence
+// |err| <= (2^-7 + 2^-16) sum |q_i v_i| <= (2^-7 + 2^-16) |q||v|; the fp32 accumulation adds O(dims * 2^-24) and the
+// pre-normalisation of the cosine shadow rows O(2^-23).  1.03 * 2^-7 covers all of it.
+constexpr float kBf16Eps = 1.03f * 0x1p-7f;
 
 struct BatchParams {
     uint32_t n_rows, dims, n_queries;
@@ -96,6 +111,18 @@ __device__ __forceinline__ void umma_tf32_ss(uint32_t tmem_d, uint64_t desc_a, u
         ".reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// kind::f16 (here: bf16 x bf16 -> fp32), one CTA: K = 16 elements = the same 32 bytes per MMA as tf32's K = 8.
+__device__ __forceinline__ void umma_bf16_ss(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
         "}\n" ::"r"(tmem_d),
         "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
         : "memory");
@@ -162,6 +189,18 @@ __device__ __forceinline__ void umma_tf32_ss_pair(uint32_t tmem_d, uint64_t desc
         : "memory");
 }
 
+__device__ __forceinline__ void umma_bf16_ss_pair(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // Shared-memory matrix descriptor, K-major, 128-byte swizzle (canonical layout ((8,n),2):((8,SBO),1) in 16-byte
 // units; rows 128 B apart, 8-row groups SBO = 1024 B apart).  Field layout: cute::UMMA::SmemDescriptor.
 __device__ __forceinline__ uint64_t umma_desc_k_sw128(const void *smem_tile) {
@@ -180,6 +219,14 @@ __host__ __device__ constexpr uint32_t umma_idesc_tf32_m128_n256() {
 // cta_group::2: M = 256 (128 rows per CTA of the pair), N = 256.
 __host__ __device__ constexpr uint32_t umma_idesc_tf32_m256_n256() {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
+}
+
+// kind::f16 with A = B = BF16 (format 1), D = F32.
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_m128_n256() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((128u >> 4) << 24);
+}
+__host__ __device__ constexpr uint32_t umma_idesc_bf16_m256_n256() {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 }
 
 // ---- per-thread nominee heap (max-heap on the ordering key: root = worst nominee) ----------------------------
@@ -246,25 +293,59 @@ __global__ void __launch_bounds__(256) row_norms_kernel(const float *corpus, uin
     if (lane == 0 && local_max > 0.0f) atomicMax(max_norm_bits, __float_as_uint(local_max));
 }
 
+// ---- bf16 shadow of the corpus (cached per corpus version, like the norms) ------------------------------------------
+// dst[row][d] = bf16_rn(src[row][d] * scale[row]) (cosine: scale = 1/|v|, so the nomination scores need no epilogue
+// scaling; dot: scale == nullptr).  Only ever NOMINATES: every returned score is recomputed from the fp32 corpus.
+__global__ void __launch_bounds__(256) shadow_bf16_kernel(const float *__restrict__ src, const float *__restrict__ scale,
+                                                          uint64_t n_rows, uint32_t dims, __nv_bfloat16 *__restrict__ dst) {
+    const uint32_t d4 = dims >> 2;                       // dims % 4 == 0 (the tensor path needs dims % 64 == 0)
+    const uint64_t total = n_rows * d4;
+    const float4 *s4 = reinterpret_cast<const float4 *>(src);
+    uint2 *o = reinterpret_cast<uint2 *>(dst);
+    for (uint64_t i = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x; i < total;
+         i += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        float4 x = __ldcs(s4 + i);
+        if (scale) {
+            const float w = __ldg(scale + i / d4);
+            x.x *= w; x.y *= w; x.z *= w; x.w *= w;
+        }
+        const __nv_bfloat162 lo = __floats2bfloat162_rn(x.x, x.y), hi = __floats2bfloat162_rn(x.z, x.w);
+        uint2 v;
+        v.x = *reinterpret_cast<const uint32_t *>(&lo);
+        v.y = *reinterpret_cast<const uint32_t *>(&hi);
+        o[i] = v;
+    }
+}
+
 // ---- the tensor-core kernel ---------------------------------------------------------------------------------------
-template <int STAGES, int HEAP, bool PAIR>
+// BF16: operands are bf16 (the corpus shadow + converted queries; 64 elements per 128-byte k-block, kind::f16 MMAs at
+//       twice the TF32 rate for the same bytes per cycle) -- nominations only, exactness comes from the finish kernel.
+// ARES: the CTA's 128 queries stay resident in shared memory (dims/64 bf16 k-blocks of 16 KB, loaded once), the ring
+//       stages carry only corpus tiles: a third less L2->SM and TMA->smem traffic per MMA.
+template <int STAGES, int HEAP, bool PAIR, bool BF16 = false, bool ARES = false>
 __global__ void __launch_bounds__(kBatchThreads, 1)
-batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
-                  const BatchParams p) {
+batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
+                      const BatchParams p) {
     extern __shared__ uint8_t smem_raw[];
     // 1024-byte alignment for the 128B-swizzled tiles, computed as an OFFSET into the shared array so the compiler
     // keeps the shared address space (LDS/STS, not generic LD/ST).
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    constexpr uint32_t STAGE_BYTES = batch_stage_bytes(PAIR);
+    constexpr uint32_t STAGE_BYTES = ARES ? batch_ares_stage_bytes(PAIR) : batch_stage_bytes(PAIR);
+    constexpr uint32_t B_OFF = ARES ? 0u : kBatchABytes;            // corpus tile offset inside a stage
     constexpr uint32_t B_ROWS = PAIR ? kBatchN / 2 : kBatchN;       // corpus rows this CTA stages per tile
-    uint8_t *stages = smem;                                            // [stage][A 16 KB | B 32 KB], 1024-aligned
-    float *scale_smem = reinterpret_cast<float *>(smem + STAGES * STAGE_BYTES);   // [2][256]
+    constexpr uint32_t KB_ELEMS = BF16 ? kBatchKBlockBf16 : kBatchKBlock;   // elements per 128-byte k-block
+    const uint32_t num_kb = p.dims / KB_ELEMS;
+    const uint32_t ares_bytes = ARES ? num_kb * kBatchABytes : 0u;   // resident queries: [kb][128 rows x 128 B]
+    uint8_t *a_res = smem;
+    uint8_t *stages = smem + ares_bytes;                               // [stage][A 16 KB | B 32 KB], 1024-aligned
+    float *scale_smem = reinterpret_cast<float *>(stages + STAGES * STAGE_BYTES);   // [2][256]
     uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kBatchN);                 // [stages]
     uint64_t *empty = full + STAGES;                                                   // [stages]
     uint64_t *tmem_full = empty + STAGES;                                              // [2]
     uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(tmem_empty + 2);
-    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(smem + STAGES * STAGE_BYTES + 2048 + 256);  // [slots][128]
+    uint64_t *a_full = tmem_empty + 2;                                                       // [1] (ARES)
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
+    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(stages + STAGES * STAGE_BYTES + 2048 + 256);  // [slots][128]
     uint64_t *heap_smem = stage_smem + kBatchStageSlots * kBatchM;                                            // [64][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -277,7 +358,6 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     const bool leader = rank == 0u;
     const uint32_t tile_lo = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * slice / p.slices);
     const uint32_t tile_hi = static_cast<uint32_t>(static_cast<uint64_t>(p.tiles_total) * (slice + 1) / p.slices);
-    const uint32_t num_kb = p.dims / kBatchKBlock;
 
     if (warp == 4 && lane == 0) {
         tma_prefetch_desc(&tmap_q);
@@ -286,6 +366,7 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
         // its tmem_empty[] collects the 4 epilogue warps of both CTAs.
         for (int s = 0; s < STAGES; ++s) { mbar_init(&full[s], PAIR ? 2 : 1); mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(&tmem_full[a], 1); mbar_init(&tmem_empty[a], PAIR ? 8 : 4); }
+        mbar_init(a_full, PAIR ? 2 : 1);
         mbar_fence_init();
     }
     if (warp == 5) {  // whole warp: allocate all 512 TMEM columns (2 accumulator buffers of 256)
@@ -309,6 +390,20 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     if (warp == 4) {
         // ===== TMA producer =====
         if (lane == 0) {
+            if (ARES && tile_lo < tile_hi) {      // the CTA's queries, once: num_kb boxes of 128 rows x 128 B
+                if (PAIR) {
+                    if (leader) mbar_arrive_expect_tx(a_full, 2u * ares_bytes);
+                    else mbar_arrive_remote(a_full, 0u);
+                } else {
+                    mbar_arrive_expect_tx(a_full, ares_bytes);
+                }
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    if (PAIR) tma_load_2d_pair(a_res + kb * kBatchABytes, &tmap_q, a_full, static_cast<int32_t>(kb * KB_ELEMS),
+                                               static_cast<int32_t>(group * kBatchM));
+                    else tma_load_2d(a_res + kb * kBatchABytes, &tmap_q, a_full, static_cast<int32_t>(kb * KB_ELEMS),
+                                     static_cast<int32_t>(group * kBatchM));
+                }
+            }
             uint32_t stage = 0, phase = 0;
             for (uint32_t tile = tile_lo; tile < tile_hi; ++tile) {
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
@@ -317,15 +412,15 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     if (PAIR) {
                         if (leader) mbar_arrive_expect_tx(&full[stage], 2u * STAGE_BYTES);   // both CTAs' bytes
                         else mbar_arrive_remote(&full[stage], 0u);
-                        tma_load_2d_pair(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
-                                         static_cast<int32_t>(group * kBatchM));
-                        tma_load_2d_pair(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                        if (!ARES) tma_load_2d_pair(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * KB_ELEMS),
+                                                    static_cast<int32_t>(group * kBatchM));
+                        tma_load_2d_pair(a + B_OFF, &tmap_c, &full[stage], static_cast<int32_t>(kb * KB_ELEMS),
                                          static_cast<int32_t>(tile * kBatchN + rank * B_ROWS));
                     } else {
                         mbar_arrive_expect_tx(&full[stage], STAGE_BYTES);
-                        tma_load_2d(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
-                                    static_cast<int32_t>(group * kBatchM));
-                        tma_load_2d(a + kBatchABytes, &tmap_c, &full[stage], static_cast<int32_t>(kb * kBatchKBlock),
+                        if (!ARES) tma_load_2d(a, &tmap_q, &full[stage], static_cast<int32_t>(kb * KB_ELEMS),
+                                               static_cast<int32_t>(group * kBatchM));
+                        tma_load_2d(a + B_OFF, &tmap_c, &full[stage], static_cast<int32_t>(kb * KB_ELEMS),
                                     static_cast<int32_t>(tile * kBatchN));
                     }
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -335,7 +430,9 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
     } else if (warp == 5) {
         // ===== MMA issuer (one thread) =====
         if (lane == 0 && leader) {      // PAIR: the leader CTA issues for both
-            constexpr uint32_t idesc = PAIR ? umma_idesc_tf32_m256_n256() : umma_idesc_tf32_m128_n256();
+            constexpr uint32_t idesc = BF16 ? (PAIR ? umma_idesc_bf16_m256_n256() : umma_idesc_bf16_m128_n256())
+                                            : (PAIR ? umma_idesc_tf32_m256_n256() : umma_idesc_tf32_m128_n256());
+            if (ARES && tile_lo < tile_hi) { mbar_wait_parity(a_full, 0u); tcgen05_fence_after(); }
             uint32_t stage = 0, phase = 0, t = 0;
             for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
                 const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
@@ -346,11 +443,19 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     mbar_wait_parity(&full[stage], phase);            // TMA bytes have landed
                     tcgen05_fence_after();
                     const uint8_t *a = stages + stage * STAGE_BYTES;
-                    const uint64_t da = umma_desc_k_sw128(a), db = umma_desc_k_sw128(a + kBatchABytes);
+                    const uint64_t da = umma_desc_k_sw128(ARES ? a_res + kb * kBatchABytes : a);
+                    const uint64_t db = umma_desc_k_sw128(a + B_OFF);
 #pragma unroll
-                    for (uint32_t j = 0; j < kBatchKBlock / 8; ++j)   // UMMA K = 8 tf32 = 32 bytes = +2 in the address field
-                        if (PAIR) umma_tf32_ss_pair(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
-                        else umma_tf32_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, (kb | j) != 0u ? 1u : 0u);
+                    for (uint32_t j = 0; j < 4; ++j) {   // UMMA K = 8 tf32 / 16 bf16 = 32 bytes = +2 in the address field
+                        const uint32_t accum = (kb | j) != 0u ? 1u : 0u;
+                        if (BF16) {
+                            if (PAIR) umma_bf16_ss_pair(d_tmem, da + 2 * j, db + 2 * j, idesc, accum);
+                            else umma_bf16_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, accum);
+                        } else {
+                            if (PAIR) umma_tf32_ss_pair(d_tmem, da + 2 * j, db + 2 * j, idesc, accum);
+                            else umma_tf32_ss(d_tmem, da + 2 * j, db + 2 * j, idesc, accum);
+                        }
+                    }
                     if (PAIR) tcgen05_commit_pair(&empty[stage]);     // frees the stage in both CTAs
                     else tcgen05_commit(&empty[stage]);               // frees the smem stage when the MMAs retire
                     if (++stage == STAGES) { stage = 0; phase ^= 1u; }
@@ -384,6 +489,9 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
             if (root != WAXVS_KEY_NONE) tau = fmaxf(tau, nominee_score(root));
         };
         const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+        // The shared threshold is read one tile AHEAD (the L2 round trip of __ldcg would otherwise sit on every
+        // tile's critical path: with bf16 MMAs a tile lasts ~3000 cycles and the epilogue has no slack to hide it).
+        uint32_t g_next = 0;
         uint32_t t = 0;
         for (uint32_t tile = tile_lo; tile < tile_hi; ++tile, ++t) {
             const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
@@ -395,14 +503,12 @@ batch_tf32_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_const
                     const uint32_t r = row0 + tid + h * 128u;
                     sc[tid + h * 128u] = (r < p.n_rows) ? __ldg(p.row_scale + r) : 0.0f;
                 }
+                asm volatile("bar.sync 1, 128;" ::: "memory");        // scales visible; previous use of sc[] finished
             }
-            if (q_valid) {                                            // adopt the best threshold any slice has published
-                const uint32_t g = __ldcg(p.tau_global + q);
-                if (g) tau = fmaxf(tau, from_orderable_u32(g));
-            }
-            asm volatile("bar.sync 1, 128;" ::: "memory");            // scales visible; previous use of sc[] finished
+            if (g_next) tau = fmaxf(tau, from_orderable_u32(g_next)); // adopt the best threshold any slice has published
             mbar_wait_parity(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
+            if (q_valid) g_next = __ldcg(p.tau_global + q);           // consumed at the next tile
             const uint32_t rows_here = min(static_cast<uint32_t>(kBatchN), p.n_rows - row0);
 #pragma unroll 1
             for (uint32_t chunk = 0; chunk < kBatchN / 32; ++chunk) {
@@ -872,6 +978,8 @@ struct FinishParams {
     const uint64_t *frame_ids;
     uint64_t id_base, row_offset;
     uint32_t pow2_all;          // next pow2 >= slices*kprime
+    uint32_t rescore;           // nominees re-scored exactly per query: a power of two in [256, kBatchRescoreMax]
+    float eps_rel;              // kTf32Eps or kBf16Eps: |score' - score| <= eps_rel * |q||v|
 };
 
 // One CTA per query.  Union of the slices' nominee heaps -> best kBatchRescore by score' -> exact re-score ->
@@ -882,7 +990,7 @@ template <int METRIC>
 __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p) {
     extern __shared__ uint64_t fsm[];
     uint64_t *sk = fsm;                 // [pow2_all] nominee keys of every slice
-    uint64_t *ek = fsm + p.pow2_all;    // [kBatchRescore] exact keys
+    uint64_t *ek = fsm + p.pow2_all;    // [rescore] exact keys
     __shared__ float s_a2, s_sqrt_a2;
     __shared__ uint32_t s_valid, s_excl;
     const uint32_t q = blockIdx.x, g = q / kBatchM, t = q % kBatchM;
@@ -922,12 +1030,12 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
     block_bitonic_sort(sk, p.pow2_all);   // best nominees first
 
     const uint32_t n_valid = s_valid;
-    const uint32_t kpp = min(static_cast<uint32_t>(kBatchRescore), n_valid);
+    const uint32_t kpp = min(p.rescore, n_valid);
     float tau = s_excl ? from_orderable_u32(s_excl) : -INFINITY;                     // never-nominated rows
-    if (n_valid > kBatchRescore) tau = fmaxf(tau, nominee_score(sk[kBatchRescore]));  // nominated, not re-scored
-    const bool excluded_any = (s_excl != 0u) || (n_valid > kBatchRescore);
+    if (n_valid > p.rescore) tau = fmaxf(tau, nominee_score(sk[p.rescore]));          // nominated, not re-scored
+    const bool excluded_any = (s_excl != 0u) || (n_valid > p.rescore);
 
-    for (uint32_t i = threadIdx.x; i < kBatchRescore; i += blockDim.x) ek[i] = WAXVS_KEY_NONE;
+    for (uint32_t i = threadIdx.x; i < p.rescore; i += blockDim.x) ek[i] = WAXVS_KEY_NONE;
     __syncthreads();
     for (uint32_t i = warp; i < kpp; i += (blockDim.x >> 5)) {
         const uint32_t row = static_cast<uint32_t>(sk[i]);
@@ -936,7 +1044,7 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
         if (lane == 0) ek[i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
     }
     __syncthreads();
-    block_bitonic_sort(ek, kBatchRescore);
+    block_bitonic_sort(ek, p.rescore);
 
     if (threadIdx.x == 0) {
         uint32_t n_exact = 0;
@@ -948,8 +1056,8 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
                 const float dk = from_orderable_u32(static_cast<uint32_t>(ek[p.k - 1] >> 32));
                 const float qn = s_sqrt_a2;
                 float sk_exact, eps;
-                if (METRIC == kCosine) { sk_exact = (1.0f - dk) * qn; eps = kTf32Eps * qn; }
-                else { sk_exact = 1.0f - dk; eps = kTf32Eps * qn * __uint_as_float(*p.max_norm_bits); }
+                if (METRIC == kCosine) { sk_exact = (1.0f - dk) * qn; eps = p.eps_rel * qn; }
+                else { sk_exact = 1.0f - dk; eps = p.eps_rel * qn * __uint_as_float(*p.max_norm_bits); }
                 eps = eps * 1.01f + 1e-30f;
                 if (!(sk_exact > tau + eps) || !finite_f32(eps)) ok = 0;
             }
@@ -960,7 +1068,7 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
     sp.out = p.out + static_cast<size_t>(q) * p.k;
     sp.frame_ids = p.frame_ids; sp.id_base = p.id_base; sp.row_offset = p.row_offset;
     for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x)
-        write_candidate(sp, static_cast<int>(i), i < kBatchRescore ? ek[i] : WAXVS_KEY_NONE);
+        write_candidate(sp, static_cast<int>(i), i < p.rescore ? ek[i] : WAXVS_KEY_NONE);
 }
 
 }  // namespace waxvs

@@ -120,6 +120,10 @@ struct Tuning {
     int batch_ts = 0;       // 1: queries in TMEM + CTA pairs (dims <= 384, dims % 128 == 0)
     int batch_heap = 0;     // 0 auto, 16 or 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
+    int batch_bf16 = 1;     // 1: nominate from a bf16 shadow of the corpus when HBM allows (kind::f16 MMAs, 2x the TF32 rate; +dims*2 B/row)
+    int batch_ares = 1;     // with batch_bf16: keep the CTA's queries resident in shared memory when they fit (dims <= 512)
+    int batch_rescore = 0;  // 0 auto; else nominees re-scored exactly per query (256, 512 or 1024)
+    int batch_retry = 1;    // with batch_bf16: queries the bf16 pass cannot prove are retried on the TF32 pass first
 };
 
 // Per-search scratch: the analogue of TransientBuffers (MetalVectorEngine.swift:36-41, :84-117).
@@ -140,6 +144,10 @@ struct SearchCtx {
     uint32_t *d_ok = nullptr; size_t ok_cap = 0;                  // batched path: per-query proof flags
     uint32_t *h_ok = nullptr; size_t h_ok_cap = 0;                // pinned
     uint32_t *d_tau = nullptr; size_t tau_cap = 0;                // batched path: shared per-query thresholds
+    __nv_bfloat16 *d_queries_bf16 = nullptr; size_t queries_bf16_cap = 0;   // batched bf16 path: converted queries
+    float *d_retry_q = nullptr; size_t retry_q_cap = 0;           // bf16 -> TF32 retry: compacted queries
+    wax_vs_candidate *d_retry_out = nullptr; size_t retry_out_cap = 0;
+    uint32_t *d_retry_ok = nullptr; size_t retry_ok_cap = 0;
     uint32_t *d_mask = nullptr; size_t mask_cap = 0;              // filtered search: row bitset / listed rows
     uint64_t *d_gather_keys = nullptr; size_t gather_cap = 0;     // filtered search: keys of the listed rows
 };
@@ -175,7 +183,14 @@ struct wax_vs_engine {
     uint32_t *d_max_norm = nullptr;
     bool norms_valid = false;
     std::mutex norms_mu;
+    // bf16 shadow of the corpus for the batched bf16 nominations (cached per corpus version, guarded by norms_mu)
+    __nv_bfloat16 *d_shadow = nullptr; size_t shadow_cap = 0;
+    bool shadow_valid = false, shadow_unavailable = false;
     uint64_t batch_tensor_queries = 0, batch_fallback_queries = 0;   // instrumentation
+    uint64_t batch_bf16_queries = 0, batch_retry_queries = 0;
+    // Adaptive level choice: when more than a quarter of a batch fails the coarse bf16 bound (tightly clustered
+    // neighbours), the next 16 batches nominate in TF32 straight away, then bf16 is probed again.
+    uint32_t bf16_skip_batches = 0;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -194,6 +209,10 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_heaps) cudaFree(c->d_heaps);
     if (c->d_ok) cudaFree(c->d_ok);
     if (c->d_tau) cudaFree(c->d_tau);
+    if (c->d_queries_bf16) cudaFree(c->d_queries_bf16);
+    if (c->d_retry_q) cudaFree(c->d_retry_q);
+    if (c->d_retry_out) cudaFree(c->d_retry_out);
+    if (c->d_retry_ok) cudaFree(c->d_retry_ok);
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_gather_keys) cudaFree(c->d_gather_keys);
     if (c->h_ok) cudaFreeHost(c->h_ok);
@@ -446,17 +465,20 @@ static PFN_cuTensorMapEncodeTiled_v12000 tensor_map_encoder() {
     return fn;
 }
 
-// Row-major [rows][dims] fp32 matrix, box = box_rows x 32 floats (128 B), 128-byte swizzle, OOB -> zeros.
-static int32_t make_tensor_map(CUtensorMap *map, const float *base, uint64_t rows, uint32_t dims, uint32_t box_rows) {
+// Row-major [rows][dims] matrix (fp32, or bf16 for the shadow path), box = box_rows x 128 bytes (32 floats / 64 bf16),
+// 128-byte swizzle, OOB -> zeros.
+static int32_t make_tensor_map(CUtensorMap *map, const void *base, uint64_t rows, uint32_t dims, uint32_t box_rows,
+                               bool bf16 = false) {
     auto enc = tensor_map_encoder();
     if (!enc) return fail(WAX_VS_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const size_t esize = bf16 ? sizeof(__nv_bfloat16) : sizeof(float);
     const cuuint64_t gdim[2] = {dims, rows};
-    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dims) * sizeof(float)};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(kBatchKBlock), box_rows};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(dims) * esize};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(bf16 ? kBatchKBlockBf16 : kBatchKBlock), box_rows};
     const cuuint32_t estr[2] = {1, 1};
-    const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), gdim, gstride, box, estr,
-                           CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    const CUresult r = enc(map, bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2,
+                           const_cast<void *>(base), gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return fail(WAX_VS_ERR_CUDA, "cuTensorMapEncodeTiled failed (CUresult %d)", static_cast<int>(r));
     return WAX_VS_OK;
 }
@@ -468,8 +490,7 @@ static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, ui
 }
 
 // 1/|v| per row + max |v|, cached until the corpus changes.
-static int32_t ensure_norms(wax_vs_engine *e, cudaStream_t stream) {
-    std::lock_guard<std::mutex> g(e->norms_mu);
+static int32_t ensure_norms_locked(wax_vs_engine *e, cudaStream_t stream) {
     if (e->norms_valid) return WAX_VS_OK;
     int32_t rc = ensure_dev(&e->d_inv_norm, &e->inv_norm_cap, static_cast<size_t>(std::max<uint64_t>(e->n_rows, 1)), "row norms");
     if (rc) return rc;
@@ -482,28 +503,130 @@ static int32_t ensure_norms(wax_vs_engine *e, cudaStream_t stream) {
     e->norms_valid = true;
     return WAX_VS_OK;
 }
+static int32_t ensure_norms(wax_vs_engine *e, cudaStream_t stream) {
+    std::lock_guard<std::mutex> g(e->norms_mu);
+    return ensure_norms_locked(e, stream);
+}
+
+// The bf16 nominations want dims % 64 == 0 (whole 128-byte k-blocks of bf16).
+static bool batch_bf16_wanted(const wax_vs_engine *e) {
+    return e->tune.batch_bf16 != 0 && e->dims % kBatchKBlockBf16 == 0 && !e->shadow_unavailable;
+}
+
+// bf16 shadow of the corpus (cosine: rows pre-scaled by 1/|v|), cached until the corpus changes.  Returns
+// WAX_VS_OK with e->shadow_valid == false when the extra dims*2 bytes per row do not fit in HBM (the caller then
+// nominates in TF32 from the fp32 corpus).
+static int32_t ensure_shadow(wax_vs_engine *e, cudaStream_t stream) {
+    std::lock_guard<std::mutex> g(e->norms_mu);
+    if (e->shadow_valid || e->shadow_unavailable) return WAX_VS_OK;
+    int32_t rc = ensure_norms_locked(e, stream);
+    if (rc) return rc;
+    const size_t need = static_cast<size_t>(e->n_rows) * e->dims;
+    if (e->shadow_cap < need) {
+        if (e->d_shadow) { cudaFree(e->d_shadow); e->d_shadow = nullptr; e->shadow_cap = 0; }
+        size_t free_b = 0, total_b = 0;
+        const size_t bytes = need * sizeof(__nv_bfloat16);
+        // keep headroom for scratch and growth: the shadow must leave max(2 GiB, 10 % of the device) free
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess ||
+            free_b < bytes + std::max<size_t>(size_t(2) << 30, total_b / 10) ||
+            cudaMalloc(&e->d_shadow, bytes) != cudaSuccess) {
+            cudaGetLastError();
+            e->shadow_unavailable = true;      // stays off for this engine: TF32 nominations need no extra memory
+            return WAX_VS_OK;
+        }
+        e->shadow_cap = need;
+    }
+    shadow_bf16_kernel<<<e->sm_count * 16, 256, 0, stream>>>(e->d_corpus, e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr,
+                                                             e->n_rows, e->dims, e->d_shadow);
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    e->shadow_valid = true;
+    return WAX_VS_OK;
+}
+
+template <typename K>
+static cudaError_t set_smem_attr(K kernel, uint32_t bytes) {
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+}
+
+template <typename K>
+static cudaError_t launch_nominate(K kernel, uint32_t grid, uint32_t smem, bool pair, cudaStream_t stream,
+                                   const CUtensorMap &map_q, const CUtensorMap &map_c, const BatchParams &bp) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBatchThreads); cfg.stream = stream; cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    if (pair) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, map_q, map_c, bp);
+}
+
+// ring depth of the ARES shapes: what is left of the 227 KB after the resident queries
+static int ares_stages(bool pair, int heap, uint32_t num_kb, int want) {
+    int st = want;
+    while (st > 2 && batch_ares_smem_bytes(st, heap, pair, static_cast<int>(num_kb)) > 227u * 1024u) --st;
+    return batch_ares_smem_bytes(st, heap, pair, static_cast<int>(num_kb)) <= 227u * 1024u ? st : 0;
+}
 
 // Enqueue the tensor-core nomination + exact finish for n_queries device-resident queries.  d_ok[i] = 1 when
-// query i's result is proven exact; the caller re-runs the others through enqueue_search.
+// query i's result is proven exact; the caller re-runs the others (TF32 retry, then enqueue_search).
+// allow_bf16 = false forces the TF32 nominations (the retry level).  *used_bf16 reports what ran.
 static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
                                     uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, uint32_t *d_ok,
-                                    const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
+                                    const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
+                                    bool allow_bf16 = true, bool *used_bf16 = nullptr) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
+    bool bf16 = allow_bf16 && batch_bf16_wanted(e);
+    if (bf16) {
+        if ((rc = ensure_shadow(e, stream))) return rc;
+        bf16 = e->shadow_valid;
+    }
+    if (used_bf16) *used_bf16 = bf16;
     const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 16, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 16)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<3, 64, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(3, 64)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<6, 16, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(6, 16, true)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_ts_kernel<16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_ts_smem_bytes(16)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_ts_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_ts_smem_bytes(64)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_tf32_kernel<4, 64, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(batch_smem_bytes(4, 64, true)));
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kCosine>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
-        if (attr_err == cudaSuccess) attr_err = cudaFuncSetAttribute(batch_finish_kernel<kDot>, cudaFuncAttributeMaxDynamicSharedMemorySize, (16384 + 256) * 8);
+        auto chk = [&](cudaError_t r) { if (attr_err == cudaSuccess) attr_err = r; };
+        chk(set_smem_attr(batch_nominate_kernel<4, 16, false>, batch_smem_bytes(4, 16)));
+        chk(set_smem_attr(batch_nominate_kernel<3, 64, false>, batch_smem_bytes(3, 64)));
+        chk(set_smem_attr(batch_nominate_kernel<6, 16, true>, batch_smem_bytes(6, 16, true)));
+        chk(set_smem_attr(batch_nominate_kernel<4, 64, true>, batch_smem_bytes(4, 64, true)));
+        chk(set_smem_attr(batch_nominate_kernel<4, 16, false, true>, batch_smem_bytes(4, 16)));
+        chk(set_smem_attr(batch_nominate_kernel<3, 64, false, true>, batch_smem_bytes(3, 64)));
+        chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true>, batch_smem_bytes(6, 16, true)));
+        chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true>, batch_smem_bytes(4, 64, true)));
+        // ARES shapes: the ring depth is chosen at run time (<= the template's STAGES is what the kernel uses)
+        chk(set_smem_attr(batch_nominate_kernel<3, 16, false, true, true>, 227u * 1024u));
+        chk(set_smem_attr(batch_nominate_kernel<2, 16, false, true, true>, 227u * 1024u));
+        chk(set_smem_attr(batch_nominate_kernel<2, 64, false, true, true>, 227u * 1024u));
+        chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true, true>, 227u * 1024u));
+        chk(set_smem_attr(batch_nominate_kernel<4, 16, true, true, true>, 227u * 1024u));
+        chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true, true>, 227u * 1024u));
+        chk(set_smem_attr(batch_tf32_ts_kernel<16>, batch_ts_smem_bytes(16)));
+        chk(set_smem_attr(batch_tf32_ts_kernel<64>, batch_ts_smem_bytes(64)));
+        chk(set_smem_attr(batch_finish_kernel<kCosine>, (16384 + kBatchRescoreMax) * 8));
+        chk(set_smem_attr(batch_finish_kernel<kDot>, (16384 + kBatchRescoreMax) * 8));
     });
     if (attr_err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
+
+    // bf16 nominations: convert the queries once per call (n_queries x dims, tiny next to the corpus pass)
+    if (bf16) {
+        const size_t qn = static_cast<size_t>(n_queries) * e->dims;
+        if ((rc = ensure_dev(&c->d_queries_bf16, &c->queries_bf16_cap, qn, "bf16 queries"))) return rc;
+        const int g = static_cast<int>(std::min<size_t>((qn / 4 + 255) / 256, static_cast<size_t>(e->sm_count) * 8));
+        shadow_bf16_kernel<<<std::max(g, 1), 256, 0, stream>>>(d_queries, nullptr, n_queries, e->dims, c->d_queries_bf16);
+        CUDA_TRY(cudaGetLastError());
+        ++*launches;
+    }
+    // how many nominees the finish kernel re-scores exactly: the (rescore+1)-th nominee bounds the rows it skips, and
+    // the coarser bf16 bound needs more distance between it and the k-th result
+    uint32_t rescore = static_cast<uint32_t>(kBatchRescore);
+    if (e->tune.batch_rescore > 0) rescore = static_cast<uint32_t>(e->tune.batch_rescore);
+    else if (bf16) rescore = k_eff <= 16 ? 256u : (k_eff <= 48 ? 512u : 1024u);
+    rescore = rescore <= 256u ? 256u : (rescore <= 512u ? 512u : static_cast<uint32_t>(kBatchRescoreMax));
 
     for (uint32_t q0 = 0; q0 < n_queries; q0 += max_groups * kBatchM) {
         const uint32_t nq = std::min<uint32_t>(n_queries - q0, max_groups * kBatchM);
@@ -511,7 +634,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         // cta_group::2: CTA pairs (two query groups, one row slice) issue one 256-row MMA and each stages only half of
         // the corpus tile.  Needs at least two groups; an odd group count is padded with an all-out-of-range group.
         // TS shape: queries in TMEM + CTA pair (dims <= 384, dims % 128 == 0): shared memory carries only the corpus
-        const bool ts = e->tune.batch_ts != 0 && groups >= 2 && e->dims <= 384 && e->dims % 128u == 0;
+        const bool ts = !bf16 && e->tune.batch_ts != 0 && groups >= 2 && e->dims <= 384 && e->dims % 128u == 0;
         const bool pair = ts || (e->tune.batch_pair != 0 && groups >= 2);
         if (pair) groups = (groups + 1u) & ~1u;
         const uint32_t tile_rows = ts ? static_cast<uint32_t>(kTsN) : static_cast<uint32_t>(kBatchN);
@@ -529,16 +652,24 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         CUDA_TRY(cudaMemsetAsync(c->d_tau, 0, static_cast<size_t>(groups) * kBatchM * sizeof(uint32_t), stream));
         CUtensorMap map_q, map_c;
         const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
-        if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
-        if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, ts ? kTsN / 2 : (pair ? kBatchN / 2 : kBatchN)))) return rc;
+        const uint32_t c_box = ts ? kTsN / 2 : (pair ? kBatchN / 2 : kBatchN);
+        if (bf16) {
+            if ((rc = make_tensor_map(&map_q, c->d_queries_bf16 + static_cast<size_t>(q0) * e->dims, nq, e->dims, kBatchM, true))) return rc;
+            if ((rc = make_tensor_map(&map_c, e->d_shadow, e->n_rows, e->dims, c_box, true))) return rc;
+        } else {
+            if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
+            if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, c_box))) return rc;
+        }
 
         BatchParams bp{};
         bp.n_rows = static_cast<uint32_t>(e->n_rows); bp.dims = e->dims; bp.n_queries = nq; bp.groups = groups;
         bp.slices = slices; bp.tiles_total = tiles_total; bp.kprime = kprime; bp.metric = e->similarity;
-        bp.row_scale = e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr;
+        // the cosine shadow rows are pre-normalised: no epilogue scaling on the bf16 path
+        bp.row_scale = (e->similarity == WAX_VS_COSINE && !bf16) ? e->d_inv_norm : nullptr;
         bp.heaps = c->d_heaps;
         bp.tau_global = c->d_tau;
         bp.no_insert = e->tune.batch_noinsert ? 1u : 0u;
+        cudaError_t lerr = cudaSuccess;
         if (ts) {
             cudaLaunchConfig_t cfg{};
             cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBatchThreads); cfg.stream = stream;
@@ -546,22 +677,41 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
             attr[0].id = cudaLaunchAttributeClusterDimension;
             attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
-            if (small_heap) { cfg.dynamicSmemBytes = batch_ts_smem_bytes(16); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<16>, map_c, qbase, bp)); }
-            else { cfg.dynamicSmemBytes = batch_ts_smem_bytes(64); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<64>, map_c, qbase, bp)); }
+            if (small_heap) { cfg.dynamicSmemBytes = batch_ts_smem_bytes(16); lerr = cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<16>, map_c, qbase, bp); }
+            else { cfg.dynamicSmemBytes = batch_ts_smem_bytes(64); lerr = cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<64>, map_c, qbase, bp); }
+        } else if (bf16) {
+            const uint32_t num_kb = e->dims / kBatchKBlockBf16;
+            const int heap = small_heap ? 16 : 64;
+            // resident queries when they leave room for a useful ring: >= 3 corpus stages (pair: >= 4 half-tile stages)
+            const int st = e->tune.batch_ares ? ares_stages(pair, heap, num_kb, pair ? 6 : 3) : 0;
+            const bool ares = st >= (pair ? 4 : 2) && !(pair && heap == 64 && st < 4);
+            if (ares) {
+                const uint32_t smem = batch_ares_smem_bytes(st, heap, pair, static_cast<int>(num_kb));
+                if (pair) {
+                    if (heap == 64) lerr = launch_nominate(batch_nominate_kernel<4, 64, true, true, true>, grid, batch_ares_smem_bytes(4, 64, true, static_cast<int>(num_kb)), true, stream, map_q, map_c, bp);
+                    else if (st >= 6) lerr = launch_nominate(batch_nominate_kernel<6, 16, true, true, true>, grid, smem, true, stream, map_q, map_c, bp);
+                    else lerr = launch_nominate(batch_nominate_kernel<4, 16, true, true, true>, grid, batch_ares_smem_bytes(4, 16, true, static_cast<int>(num_kb)), true, stream, map_q, map_c, bp);
+                } else {
+                    if (heap == 64) lerr = launch_nominate(batch_nominate_kernel<2, 64, false, true, true>, grid, batch_ares_smem_bytes(2, 64, false, static_cast<int>(num_kb)), false, stream, map_q, map_c, bp);
+                    else if (st >= 3) lerr = launch_nominate(batch_nominate_kernel<3, 16, false, true, true>, grid, smem, false, stream, map_q, map_c, bp);
+                    else lerr = launch_nominate(batch_nominate_kernel<2, 16, false, true, true>, grid, batch_ares_smem_bytes(2, 16, false, static_cast<int>(num_kb)), false, stream, map_q, map_c, bp);
+                }
+            } else if (pair) {
+                if (small_heap) lerr = launch_nominate(batch_nominate_kernel<6, 16, true, true>, grid, batch_smem_bytes(6, 16, true), true, stream, map_q, map_c, bp);
+                else lerr = launch_nominate(batch_nominate_kernel<4, 64, true, true>, grid, batch_smem_bytes(4, 64, true), true, stream, map_q, map_c, bp);
+            } else {
+                if (small_heap) lerr = launch_nominate(batch_nominate_kernel<4, 16, false, true>, grid, batch_smem_bytes(4, 16), false, stream, map_q, map_c, bp);
+                else lerr = launch_nominate(batch_nominate_kernel<3, 64, false, true>, grid, batch_smem_bytes(3, 64), false, stream, map_q, map_c, bp);
+            }
         } else if (pair) {
-            cudaLaunchConfig_t cfg{};
-            cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kBatchThreads); cfg.stream = stream;
-            cudaLaunchAttribute attr[1];
-            attr[0].id = cudaLaunchAttributeClusterDimension;
-            attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-            cfg.attrs = attr; cfg.numAttrs = 1;
-            if (small_heap) { cfg.dynamicSmemBytes = batch_smem_bytes(6, 16, true); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_kernel<6, 16, true>, map_q, map_c, bp)); }
-            else { cfg.dynamicSmemBytes = batch_smem_bytes(4, 64, true); CUDA_TRY(cudaLaunchKernelEx(&cfg, batch_tf32_kernel<4, 64, true>, map_q, map_c, bp)); }
+            if (small_heap) lerr = launch_nominate(batch_nominate_kernel<6, 16, true>, grid, batch_smem_bytes(6, 16, true), true, stream, map_q, map_c, bp);
+            else lerr = launch_nominate(batch_nominate_kernel<4, 64, true>, grid, batch_smem_bytes(4, 64, true), true, stream, map_q, map_c, bp);
         } else if (small_heap) {
-            batch_tf32_kernel<4, 16, false><<<grid, kBatchThreads, batch_smem_bytes(4, 16), stream>>>(map_q, map_c, bp);
+            lerr = launch_nominate(batch_nominate_kernel<4, 16, false>, grid, batch_smem_bytes(4, 16), false, stream, map_q, map_c, bp);
         } else {
-            batch_tf32_kernel<3, 64, false><<<grid, kBatchThreads, batch_smem_bytes(3, 64), stream>>>(map_q, map_c, bp);
+            lerr = launch_nominate(batch_nominate_kernel<3, 64, false>, grid, batch_smem_bytes(3, 64), false, stream, map_q, map_c, bp);
         }
+        CUDA_TRY(lerr);
         CUDA_TRY(cudaGetLastError());
 
         FinishParams fp{};
@@ -573,7 +723,9 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         uint32_t pow2 = 512;
         while (pow2 < slices * kprime) pow2 <<= 1;
         fp.pow2_all = pow2;
-        const size_t fsmem = static_cast<size_t>(pow2 + kBatchRescore) * sizeof(uint64_t);
+        fp.rescore = rescore;
+        fp.eps_rel = bf16 ? kBf16Eps : kTf32Eps;
+        const size_t fsmem = static_cast<size_t>(pow2 + rescore) * sizeof(uint64_t);
         if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 256, fsmem, stream>>>(fp);
         else batch_finish_kernel<kDot><<<nq, 256, fsmem, stream>>>(fp);
         CUDA_TRY(cudaGetLastError());
@@ -600,9 +752,17 @@ static int32_t set_capacity(wax_vs_engine *e, uint64_t rows) {
     if (rows <= e->cap_rows) return WAX_VS_OK;
     float *n = nullptr;
     const size_t bytes = static_cast<size_t>(rows) * e->dims * sizeof(float);
-    if (cudaMalloc(&n, bytes) != cudaSuccess)
-        return fail(WAX_VS_ERR_CUDA, "Failed to resize vectors buffer (%zu bytes): %s", bytes,
-                    cudaGetErrorString(cudaGetLastError()));
+    if (cudaMalloc(&n, bytes) != cudaSuccess) {
+        // the bf16 shadow is derived data: give its HBM back before giving up (mutators hold the write lock)
+        cudaGetLastError();
+        if (e->d_shadow) {
+            cudaFree(e->d_shadow); e->d_shadow = nullptr; e->shadow_cap = 0; e->shadow_valid = false;
+            e->shadow_unavailable = true;
+        }
+        if (cudaMalloc(&n, bytes) != cudaSuccess)
+            return fail(WAX_VS_ERR_CUDA, "Failed to resize vectors buffer (%zu bytes): %s", bytes,
+                        cudaGetErrorString(cudaGetLastError()));
+    }
     if (e->n_rows) {
         cudaError_t err = cudaMemcpy(n, e->d_corpus, static_cast<size_t>(e->n_rows) * e->dims * sizeof(float),
                                      cudaMemcpyDeviceToDevice);
@@ -718,6 +878,7 @@ void wax_vs_destroy(wax_vs_engine *e) {
         if (e->d_ids) cudaFree(e->d_ids);
         if (e->d_inv_norm) cudaFree(e->d_inv_norm);
         if (e->d_max_norm) cudaFree(e->d_max_norm);
+        if (e->d_shadow) cudaFree(e->d_shadow);
     }
     delete e;
 }
@@ -779,7 +940,7 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
         if (row != n0 + i) pure_append = false;
     }
     e->d_ids_dirty = true;
-    e->norms_valid = false;
+    e->norms_valid = false; e->shadow_valid = false;
     const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
     if (pure_append) {
         CUDA_TRY(cudaMemcpy(e->d_corpus + n0 * e->dims, rows, n * row_bytes, cudaMemcpyHostToDevice));
@@ -850,7 +1011,7 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
     --e->n_rows;
     e->map_valid = false;
     e->d_ids_dirty = true;
-    e->norms_valid = false;
+    e->norms_valid = false; e->shadow_valid = false;
     return WAX_VS_OK;
 }
 
@@ -896,22 +1057,59 @@ static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_qu
         // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
         if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
         if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
-        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches);
+        bool used_bf16 = false, allow_bf16 = true;
+        {
+            std::lock_guard<std::mutex> pg(e->pool_mu);
+            if (e->bf16_skip_batches > 0) { --e->bf16_skip_batches; allow_bf16 = false; }
+        }
+        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches,
+                                  allow_bf16, &used_bf16);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
-        uint64_t failed = 0;
-        for (uint32_t qi = 0; qi < n_queries; ++qi) {
-            if (c->h_ok[qi]) continue;
-            ++failed;
+        std::vector<uint32_t> unproven;
+        for (uint32_t qi = 0; qi < n_queries; ++qi) if (!c->h_ok[qi]) unproven.push_back(qi);
+        if (used_bf16 && unproven.size() * 4 > n_queries) {
+            std::lock_guard<std::mutex> pg(e->pool_mu);
+            e->bf16_skip_batches = 16;
+        }
+        uint64_t retried = 0;
+        if (used_bf16 && e->tune.batch_retry && batch_tensor_eligible(e, static_cast<uint32_t>(unproven.size()), k_eff)) {
+            // Second level: the queries the coarse bf16 bound could not prove go through the TF32 nominations
+            // (4x tighter bound) as one compacted sub-batch; only what is still unproven pays for an exact scan.
+            const uint32_t nf = static_cast<uint32_t>(unproven.size());
+            retried = nf;
+            if ((rc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "retry queries"))) return rc;
+            if ((rc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "retry results"))) return rc;
+            if ((rc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "retry flags"))) return rc;
+            for (uint32_t i = 0; i < nf; ++i)
+                CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
+                                         c->d_queries + static_cast<size_t>(unproven[i]) * e->dims, e->dims * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, c->stream));
+            rc = enqueue_batch_tensor(e, c, c->d_retry_q, nf, k_eff, 0, c->d_retry_out, c->d_retry_ok, nullptr, c->stream,
+                                      &launches, false, nullptr);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+            for (uint32_t i = 0; i < nf; ++i)
+                CUDA_TRY(cudaMemcpyAsync(c->d_out + static_cast<size_t>(unproven[i]) * k_eff,
+                                         c->d_retry_out + static_cast<size_t>(i) * k_eff, k_eff * sizeof(wax_vs_candidate),
+                                         cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            std::vector<uint32_t> still;
+            for (uint32_t i = 0; i < nf; ++i) if (!c->h_ok[i]) still.push_back(unproven[i]);
+            unproven.swap(still);
+        }
+        for (uint32_t qi : unproven) {
             rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
                                 c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
             if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         }
         {
             std::lock_guard<std::mutex> pg(e->pool_mu);
-            e->batch_tensor_queries += n_queries - failed;
-            e->batch_fallback_queries += failed;
+            e->batch_tensor_queries += n_queries - unproven.size();
+            e->batch_fallback_queries += unproven.size();
+            if (used_bf16) e->batch_bf16_queries += n_queries;
+            e->batch_retry_queries += retried;
         }
     } else {
         for (uint32_t qi = 0; qi < n_queries; ++qi) {
@@ -1167,7 +1365,7 @@ int32_t wax_vs_deserialize(wax_vs_engine *e, const uint8_t *src, uint64_t len) {
     e->ids_identity = false;
     e->map_valid = false;
     e->d_ids_dirty = true;
-    e->norms_valid = false;
+    e->norms_valid = false; e->shadow_valid = false;
     return WAX_VS_OK;
 }
 
@@ -1200,7 +1398,7 @@ int32_t wax_vs_debug_fill_synthetic(wax_vs_engine *e, uint64_t seed, uint64_t fi
     e->ids_identity = true; e->id_base = id_base;
     e->map = IdMap(); e->map_valid = true;
     e->d_ids_dirty = true;
-    e->norms_valid = false;
+    e->norms_valid = false; e->shadow_valid = false;
     return WAX_VS_OK;
 }
 
@@ -1299,6 +1497,20 @@ int32_t wax_vs_debug_batch_stats(wax_vs_engine *e, uint64_t *tensor_queries, uin
     return WAX_VS_OK;
 }
 
+int32_t wax_vs_debug_counter(wax_vs_engine *e, const char *name, uint64_t *out) {
+    if (!e || !name || !out) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::lock_guard<std::mutex> g(e->pool_mu);
+    if (!strcmp(name, "batch_tensor_queries")) *out = e->batch_tensor_queries;
+    else if (!strcmp(name, "batch_fallback_queries")) *out = e->batch_fallback_queries;
+    else if (!strcmp(name, "batch_bf16_queries")) *out = e->batch_bf16_queries;
+    else if (!strcmp(name, "batch_retry_queries")) *out = e->batch_retry_queries;
+    else if (!strcmp(name, "shadow_bytes")) *out = e->shadow_valid ? e->shadow_cap * sizeof(__nv_bfloat16) : 0;
+    else if (!strcmp(name, "pool_allocs")) *out = e->pool_allocs;
+    else if (!strcmp(name, "pool_reuses")) *out = e->pool_reuses;
+    else return fail(WAX_VS_ERR_ARGUMENT, "unknown counter '%s'", name);
+    return WAX_VS_OK;
+}
+
 int32_t wax_vs_debug_time_search_batch(wax_vs_engine *e, uint32_t n_queries, int64_t top_k, uint64_t seed,
                                        uint32_t warmup, uint32_t iters, float *out_ms_total,
                                        uint64_t *out_launches, uint32_t *out_unproven) {
@@ -1321,6 +1533,7 @@ int32_t wax_vs_debug_time_search_batch(wax_vs_engine *e, uint32_t n_queries, int
     synth_fill_kernel<<<(n_queries + 255) / 256, 256, 0, c->stream>>>(c->d_queries, n_queries, e->dims, seed, 0, 1);
     CUDA_TRY(cudaGetLastError());
     if ((rc = ensure_norms(e, c->stream))) return rc;   // cached per corpus version: outside the timed region
+    if (batch_bf16_wanted(e) && (rc = ensure_shadow(e, c->stream))) return rc;   // likewise
     uint64_t launches = 0;
     for (uint32_t it = 0; it < warmup + iters; ++it) {
         if (it == warmup) { launches = 0; CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); }
@@ -1358,6 +1571,10 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_heap")) e->tune.batch_heap = v;
     else if (!strcmp(key, "batch_pair")) e->tune.batch_pair = v;
     else if (!strcmp(key, "batch_ts")) e->tune.batch_ts = v;
+    else if (!strcmp(key, "batch_bf16")) { e->tune.batch_bf16 = v; e->shadow_unavailable = false; e->bf16_skip_batches = 0; }
+    else if (!strcmp(key, "batch_ares")) e->tune.batch_ares = v;
+    else if (!strcmp(key, "batch_rescore")) e->tune.batch_rescore = v;
+    else if (!strcmp(key, "batch_retry")) e->tune.batch_retry = v;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);

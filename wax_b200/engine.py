@@ -321,6 +321,12 @@ class CUDAVectorEngine:
         _check(L.lib().wax_vs_debug_batch_stats(self._h, C.byref(a), C.byref(b)))
         return a.value, b.value
 
+    def counter(self, name: str) -> int:
+        """Named instrumentation counter (wax_vs_debug_counter): batch_bf16_queries, batch_retry_queries, shadow_bytes, ..."""
+        v = C.c_uint64(0)
+        _check(L.lib().wax_vs_debug_counter(self._h, name.encode(), C.byref(v)))
+        return v.value
+
     def time_search_batch(self, n_queries: int, top_k: int, iters: int, warmup: int = 2, seed: int = 7):
         """Device-only timing of the batched path. Returns (ms_total, launches, unproven_in_last_step)."""
         ms, launches, bad = C.c_float(0), C.c_uint64(0), C.c_uint32(0)
