@@ -229,6 +229,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16_m256_n256() {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((256u >> 3) << 17) | ((256u >> 4) << 24);
 }
 
+// max of three (FMNMX3 on sm_100; like fmaxf, a NaN input is dropped).
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
+}
+
 // ---- per-thread nominee heap (max-heap on the ordering key: root = worst nominee) ----------------------------
 // key = (orderable(-score') << 32) | row  -- smaller is better, exactly like the exact keys.
 __device__ __forceinline__ uint64_t nominee_key(float score, uint32_t row) {
@@ -515,8 +522,11 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 uint32_t v[32];
                 tmem_ld_32x32(tmem_base + lane_base + acc * kBatchN + chunk * 32u, v);
                 if (chunk * 32u >= rows_here) continue;               // warp-uniform
-                // Hot path, branch-free: scale the 32 scores and take their max (fmaxf drops NaNs); only a chunk
-                // whose max beats tau (rare once the heap has warmed up) is examined element by element.
+                // Hot path, branch-free: scale the 32 scores and take their max (max.f32 drops NaNs: FMNMX3, 17
+                // instructions for 32 values); only a chunk whose max beats tau (rare once the heap has warmed up)
+                // is examined column by column.  The rare path is deliberately COMPACT: the first version walked a
+                // fully unrolled max tree with the flush inlined at every leaf -- 200 KB of SASS, so every entry
+                // missed the instruction cache, which cost a quarter of the kernel once bf16 halved the MMA time.
                 float sv[32];
                 if (p.row_scale) {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + chunk * 32u);
@@ -532,46 +542,33 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
 #pragma unroll
                     for (uint32_t j = 0; j < 32; ++j) sv[j] = __uint_as_float(v[j]);
                 }
-                // max tree with the intermediate levels kept (strided pairing: node j of a level covers columns
-                // j, j+W, j+2W, ... of the level below)
-                float m16[16], m8[8], m4[4], m2[2];
+                float t11[11];
 #pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) m16[j] = fmaxf(sv[j], sv[j + 16]);
+                for (uint32_t j = 0; j < 10; ++j) t11[j] = fmax3(sv[3 * j], sv[3 * j + 1], sv[3 * j + 2]);
+                t11[10] = fmaxf(sv[30], sv[31]);
+                const float u0 = fmax3(t11[0], t11[1], t11[2]), u1 = fmax3(t11[3], t11[4], t11[5]);
+                const float u2 = fmax3(t11[6], t11[7], t11[8]), u3 = fmaxf(t11[9], t11[10]);
+                const float cmax = fmaxf(fmax3(u0, u1, u2), u3);
+                if (cmax > tau && q_valid) {
+                    uint32_t mask = 0;
 #pragma unroll
-                for (uint32_t j = 0; j < 8; ++j) m8[j] = fmaxf(m16[j], m16[j + 8]);
-#pragma unroll
-                for (uint32_t j = 0; j < 4; ++j) m4[j] = fmaxf(m8[j], m8[j + 4]);
-#pragma unroll
-                for (uint32_t j = 0; j < 2; ++j) m2[j] = fmaxf(m4[j], m4[j + 2]);
-                if (fmaxf(m2[0], m2[1]) > tau && q_valid) {
-                    // Rare slow path (per lane): walk down only the branches whose max beats tau -- about ten
-                    // compares for the usual single winner instead of testing all 32 columns.
-                    auto leaf = [&](uint32_t j, float sj) {
-                        const uint32_t col = chunk * 32u + j;
-                        if (sj > tau && col < rows_here) {
-                            if (cnt == kBatchStageSlots) flush();     // rarer still: this lane alone filled its slots
-                            stage[cnt * kBatchM] = nominee_key(sj, row0 + col);
-                            ++cnt;
+                    for (uint32_t j = 0; j < 32; ++j) mask |= (sv[j] > tau ? 1u : 0u) << j;
+                    const uint32_t cols = rows_here - chunk * 32u;                 // >= 1 here
+                    if (cols < 32u) mask &= (1u << cols) - 1u;
+                    while (mask) {
+                        if (cnt + __popc(mask) > kBatchStageSlots) flush();       // empties the slots, may raise tau
+                        uint32_t take = mask;
+                        if (__popc(mask) > kBatchStageSlots) {                     // warm-up only: lowest 8 set bits
+                            take = 0;
+#pragma unroll 1
+                            for (int i = 0; i < kBatchStageSlots; ++i) { const uint32_t bit = mask & (0u - mask); take |= bit; mask ^= bit; }
+                        } else {
+                            mask = 0;
                         }
-                    };
 #pragma unroll
-                    for (uint32_t a = 0; a < 2; ++a) {
-                        if (!(m2[a] > tau)) continue;
-#pragma unroll
-                        for (uint32_t b = 0; b < 2; ++b) {
-                            const uint32_t i4 = a + 2 * b;
-                            if (!(m4[i4] > tau)) continue;
-#pragma unroll
-                            for (uint32_t c = 0; c < 2; ++c) {
-                                const uint32_t i8 = i4 + 4 * c;
-                                if (!(m8[i8] > tau)) continue;
-#pragma unroll
-                                for (uint32_t d = 0; d < 2; ++d) {
-                                    const uint32_t i16 = i8 + 8 * d;
-                                    if (!(m16[i16] > tau)) continue;
-                                    leaf(i16, sv[i16]);
-                                    leaf(i16 + 16, sv[i16 + 16]);
-                                }
+                        for (uint32_t j = 0; j < 32; ++j) {
+                            if ((take >> j) & 1u) {
+                                if (sv[j] > tau) { stage[cnt * kBatchM] = nominee_key(sv[j], row0 + chunk * 32u + j); ++cnt; }
                             }
                         }
                     }
