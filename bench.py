@@ -251,10 +251,45 @@ def run_single(args):
         "clocks": clocks,
         "check": {"top1_frame_id": last[0][0] if last else None, "top1_score": last[0][1] if last else None},
     }
+    if not args.no_shadow and not small:
+        line["shadow_filtered"] = shadow_filtered_arm(eng, args, qs, n_distinct)
     if not args.no_cpu_baseline:
         base = cpu_reference_arm(args.rows, steps=5, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
+
+
+def shadow_filtered_arm(eng, args, qs, n_distinct):
+    """NOT the headline (`value` / `e2e` above are the fused fp32 scan north_star names): the same single-query
+    workload with the opt-in `single_shadow` mode -- the query is first ranked against the bf16 shadow of the corpus
+    (half the HBM bytes), the best nominees are re-scored exactly in fp32 and a completeness proof
+    guards the result, so ids and score bits are identical to the fp32 scan (checked here on every step)."""
+    import torch
+    expect = [eng.search(qs[i % n_distinct], TOP_K) for i in range(min(args.steps, n_distinct))]
+    eng.set_option("single_shadow", 1)
+    try:
+        ms, launches, unproven = eng.time_search_batch(1, TOP_K, args.steps, warmup=3, seed=QUERY_SEED)
+        for i in range(3):
+            eng.search(qs[i % n_distinct], TOP_K)
+        f0 = eng.batch_stats()[1]
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        got = [eng.search(qs[i % n_distinct], TOP_K) for i in range(args.steps)]
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - t0
+        same = all(got[i] == expect[i % len(expect)] for i in range(args.steps))
+        return {
+            "value": args.steps / (ms / 1e3), "unit": "queries/s", "ms_per_step": ms / args.steps,
+            "e2e": {"value": args.steps / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s / args.steps * 1e3},
+            "gpu_launches_per_query": launches / args.steps, "identical_to_fp32_scan": bool(same),
+            "exact_fallbacks": eng.batch_stats()[1] - f0, "shadow_gb": eng.counter("shadow_bytes") / 1e9,
+            "hbm_bytes_per_query": args.rows * DIMS * 2,
+            "achieved_gbs_on_shadow_bytes": args.rows * DIMS * 2 / (ms / args.steps / 1e3) / 1e9,
+            "note": "opt-in mode (wax_vs_debug_set_option single_shadow=1); bf16 shadow nominates on the tensor path, "
+                    "fp32 re-score + proof make the result identical; costs dims*2 B/row of extra HBM",
+        }
+    finally:
+        eng.set_option("single_shadow", 0)
 
 
 def run_sharded(args, rank: int, world: int, local_rank: int):
@@ -371,6 +406,7 @@ def main():
     ap.add_argument("--rows", type=int, default=ROWS, help="override the corpus size (experiments only)")
     ap.add_argument("--opt", action="append", default=[], help="engine tuning option key=value (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-shadow", action="store_true", help="skip the extra `shadow_filtered` (opt-in mode) measurement")
     ap.add_argument("--pipeline", type=int, default=2, help="N>1: micro-batches in flight per rank")
     ap.add_argument("--micro", type=int, default=4, help="N>1: queries per exchange (one all-gather carries them all)")
     args = ap.parse_args()

@@ -226,3 +226,38 @@ def test_bf16_shadow_follows_mutations(oracle):
     assert got == _single(eng, qs, 10)
     assert got[0][0][0] == 7000 and got[1][0][0] == 7001
     assert eng.counter("shadow_bytes") == 6001 * dims * 2
+
+
+def test_single_shadow_mode_routes_single_queries_through_the_shadow(oracle):
+    """Opt-in `single_shadow`: one query is ranked against the bf16 shadow on the tensor path, re-scored exactly and
+    proven -- same ids and score bits as the fused fp32 scan; an unprovable query (near-duplicates) falls back to the
+    scan and switches the mode off for the next queries (adaptive level choice)."""
+    dims, n = 384, 80_000
+    eng = _engine(oracle, VectorMetric.cosine, n, dims, seed=1200)
+    qs = oracle.synth_rows(1201, 0, 5, dims)
+    expect = [eng.search(q, 10) for q in qs]
+    assert eng.counter("batch_bf16_queries") == 0
+    eng.set_option("single_shadow", 1)
+    assert [eng.search(q, 10) for q in qs] == expect
+    assert eng.counter("batch_bf16_queries") == 5 and eng.batch_stats() == (5, 0)
+    assert eng.search_batch(qs[:2], 10) == expect[:2]            # below batch_min: the shadow path as well
+    assert eng.counter("batch_bf16_queries") == 7
+    # k > 128 is not eligible: the scan answers
+    got200 = eng.search(qs[0], 200)
+    assert eng.counter("batch_bf16_queries") == 7
+    eng.set_option("single_shadow", 0)
+    assert got200 == eng.search(qs[0], 200)
+    eng.set_option("single_shadow", 1)
+    # near-duplicates of the query: unprovable at bf16 -> exact scan, identical result, bf16 level suspended
+    base = oracle.synth_row(1202, 0, dims, True)
+    rng = np.random.default_rng(9)
+    dup = base + rng.standard_normal((400, dims)).astype(np.float32) * np.float32(1e-6)
+    eng.add_batch(list(range(400)), dup)
+    eng.set_option("single_shadow", 0)
+    want = eng.search(base, 10)
+    eng.set_option("single_shadow", 1)
+    n0 = eng.counter("batch_bf16_queries")
+    assert eng.search(base, 10) == want
+    assert eng.counter("batch_bf16_queries") == n0 + 1 and eng.batch_stats()[1] == 1
+    assert eng.search(qs[1], 10) == expect[1]
+    assert eng.counter("batch_bf16_queries") == n0 + 1          # suspended: answered by the fp32 scan

@@ -175,6 +175,38 @@ def test_stage_for_commit_follows_the_dirty_flag():
     assert wax.calls[0]["bytes"][:4] == b"MV2V" and wax.calls[0]["similarity"] == 0
 
 
+def test_load_replays_pending_embeddings_over_the_committed_blob():
+    """`static load(from:)` (MetalVectorEngine.swift:318-328): committed blob first, then every pending embedding
+    as an upsert in order -- the situation of WaxSessionTests.swift:73-123 (search before and after commit)."""
+    from collections import namedtuple
+    PutEmbedding = namedtuple("PutEmbedding", "frame_id vector")
+    src = CUDAVectorEngine(VectorMetric.cosine, 4)
+    src.add_batch([0, 1, 2], [[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]])
+
+    class FakeWax:
+        def __init__(self, blob, pending): self.blob, self.pending = blob, pending
+        def read_committed_vec_index_bytes(self): return self.blob
+        def pending_embedding_mutations(self): return self.pending
+
+    pending = [PutEmbedding(3, [0.0, 0.0, 0.0, 1.0]), PutEmbedding(1, [0.6, 0.8, 0.0, 0.0]),   # 1: overwrite committed
+               PutEmbedding(3, [0.0, 0.0, 0.6, 0.8]), (9, [0.5, 0.5, 0.5, 0.5])]                # 3: twice, last wins
+    eng = CUDAVectorEngine.load(FakeWax(src.serialize(), pending), VectorMetric.cosine, 4)
+    ref = CUDAVectorEngine(VectorMetric.cosine, 4)
+    ref.deserialize(src.serialize())
+    for m in pending:                              # the reference's loop: one add per pending embedding
+        ref.add(m[0], m[1])
+    assert eng.count == ref.count == 5
+    assert eng.serialize() == ref.serialize()
+    assert eng.search([0.0, 0.0, 0.6, 0.8], 1)[0][0] == 3
+    assert eng.search([0.6, 0.8, 0.0, 0.0], 1)[0][0] == 1
+    # nothing committed yet, nothing pending
+    empty = CUDAVectorEngine.load(FakeWax(None, []), VectorMetric.cosine, 4)
+    assert empty.count == 0 and empty.search([1, 0, 0, 0], 3) == []
+    # a pending embedding of the wrong dimension surfaces as the reference's encodingError, engine released
+    with pytest.raises(wax_b200.EncodingError):
+        CUDAVectorEngine.load(FakeWax(None, [PutEmbedding(1, [1.0, 2.0])]), VectorMetric.cosine, 4)
+
+
 def test_concurrent_searches_are_reentrant(oracle):
     eng = CUDAVectorEngine(VectorMetric.cosine, 64)
     eng.fill_synthetic(3, 20_000)

@@ -124,6 +124,9 @@ struct Tuning {
     int batch_ares = 1;     // with batch_bf16: keep the CTA's queries resident in shared memory when they fit (dims <= 512)
     int batch_rescore = 0;  // 0 auto; else nominees re-scored exactly per query (256, 512 or 1024)
     int batch_retry = 1;    // with batch_bf16: queries the bf16 pass cannot prove are retried on the TF32 pass first
+    int single_shadow = 0;  // 1: single queries / batches below batch_min also take the bf16-shadow nominations
+                            // (half the HBM bytes per query: 1.19 vs 2.04 ms at 10 M x 384, same results); off by
+                            // default: the plain single-query path is the fused fp32 scan BASELINE's north_star names
 };
 
 // Per-search scratch: the analogue of TransientBuffers (MetalVectorEngine.swift:36-41, :84-117).
@@ -483,8 +486,10 @@ static int32_t make_tensor_map(CUtensorMap *map, const void *base, uint64_t rows
     return WAX_VS_OK;
 }
 
+static bool batch_bf16_wanted(const wax_vs_engine *e);
 static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, uint32_t k_eff) {
-    return e->tune.batch_tensor && n_queries >= static_cast<uint32_t>(std::max(e->tune.batch_min, 1)) &&
+    const uint32_t min_batch = (e->tune.single_shadow && batch_bf16_wanted(e)) ? 1u : static_cast<uint32_t>(std::max(e->tune.batch_min, 1));
+    return e->tune.batch_tensor && n_queries >= min_batch &&
            (e->similarity == WAX_VS_COSINE || e->similarity == WAX_VS_DOT) && e->dims % kBatchKBlock == 0 &&
            k_eff >= 1 && k_eff <= 128 && e->n_rows >= 1;
 }
@@ -1052,16 +1057,19 @@ static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_qu
     memcpy(c->h_queries, queries, qfloats * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     uint64_t launches = 0;
-    if (batch_tensor_eligible(e, n_queries, k_eff)) {
+    bool tensor_path = batch_tensor_eligible(e, n_queries, k_eff), allow_bf16 = true;
+    if (tensor_path) {
+        std::lock_guard<std::mutex> pg(e->pool_mu);
+        if (e->bf16_skip_batches > 0) { --e->bf16_skip_batches; allow_bf16 = false; }
+    }
+    // below batch_min the tensor path only pays off through the bf16 shadow (single_shadow): never TF32 for one query
+    if (tensor_path && !allow_bf16 && n_queries < static_cast<uint32_t>(std::max(e->tune.batch_min, 1))) tensor_path = false;
+    if (tensor_path) {
         // Batched: one tensor-core pass over the corpus nominates, the finish kernel re-scores exactly and
         // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
         if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
         if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
-        bool used_bf16 = false, allow_bf16 = true;
-        {
-            std::lock_guard<std::mutex> pg(e->pool_mu);
-            if (e->bf16_skip_batches > 0) { --e->bf16_skip_batches; allow_bf16 = false; }
-        }
+        bool used_bf16 = false;
         rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches,
                                   allow_bf16, &used_bf16);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
@@ -1074,7 +1082,8 @@ static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_qu
             e->bf16_skip_batches = 16;
         }
         uint64_t retried = 0;
-        if (used_bf16 && e->tune.batch_retry && batch_tensor_eligible(e, static_cast<uint32_t>(unproven.size()), k_eff)) {
+        if (used_bf16 && e->tune.batch_retry && unproven.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1)) &&
+            batch_tensor_eligible(e, static_cast<uint32_t>(unproven.size()), k_eff)) {
             // Second level: the queries the coarse bf16 bound could not prove go through the TF32 nominations
             // (4x tighter bound) as one compacted sub-batch; only what is still unproven pays for an exact scan.
             const uint32_t nf = static_cast<uint32_t>(unproven.size());
@@ -1575,6 +1584,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_ares")) e->tune.batch_ares = v;
     else if (!strcmp(key, "batch_rescore")) e->tune.batch_rescore = v;
     else if (!strcmp(key, "batch_retry")) e->tune.batch_retry = v;
+    else if (!strcmp(key, "single_shadow")) e->tune.single_shadow = v;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);

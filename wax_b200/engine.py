@@ -147,6 +147,29 @@ class CUDAVectorEngine:
         self._closed = False
         self._lock = threading.Lock()
 
+    @classmethod
+    def load(cls, wax, metric: VectorMetric, dimensions: int, device: Optional[int] = None) -> "CUDAVectorEngine":
+        """`static load(from:metric:dimensions:)` (MetalVectorEngine.swift:318-328): the committed vector-index blob,
+        then the pending (uncommitted) embedding mutations replayed in order as upserts.  `wax` needs
+        `read_committed_vec_index_bytes() -> bytes | None` and `pending_embedding_mutations() -> [(frameId, vector)]`
+        (objects with `.frame_id` / `.vector` are accepted too); the store behind them is out of scope.
+        The replay is ONE add_batch: the library resolves the rows sequentially, so a frameId that occurs twice keeps
+        its last vector exactly as the reference's per-embedding loop does."""
+        engine = cls(metric, dimensions, device)
+        try:
+            blob = wax.read_committed_vec_index_bytes()
+            if blob is not None:
+                engine.deserialize(blob)
+            pending = list(wax.pending_embedding_mutations())
+            if pending:
+                ids = [int(getattr(m, "frame_id", m[0] if isinstance(m, (tuple, list)) else None)) for m in pending]
+                vecs = [getattr(m, "vector", m[1] if isinstance(m, (tuple, list)) else None) for m in pending]
+                engine.add_batch(ids, vecs)
+        except Exception:
+            engine.close()
+            raise
+        return engine
+
     # -- lifetime
     def close(self) -> None:
         if not getattr(self, "_closed", True):
