@@ -145,6 +145,15 @@ int32_t wax_vs_search_device(wax_vs_engine *engine, const float *d_queries, uint
                              int64_t top_k, uint64_t row_offset, wax_vs_candidate *d_candidates,
                              void *cuda_stream);
 
+/* Batched device-resident form (the row-sharded engine's search_batch): same pointers and candidate layout as
+   wax_vs_search_device, but the queries go through the batched tensor-core levels (bf16-shadow nominations ->
+   TF32 retry -> exact scan; results identical to n_queries single-query calls) whenever the batch is eligible
+   (wax_vs_search_batch's rules).  Those levels read their proof flags back, so this call MAY synchronise
+   `cuda_stream` before it returns; d_candidates is complete in `cuda_stream` order. */
+int32_t wax_vs_search_batch_device(wax_vs_engine *engine, const float *d_queries, uint32_t n_queries,
+                                   int64_t top_k, uint64_t row_offset, wax_vs_candidate *d_candidates,
+                                   void *cuda_stream);
+
 /* ---- persistence: "MV2V" v1 encoding = 2, byte-identical to MetalVectorEngine.serialize ---------- */
 
 /* serialize() (MetalVectorEngine.swift:682-714). */

@@ -34,6 +34,17 @@ same = many == [eng.search(q, 10) for q in qs]
 ok = ok and same
 if rank == 0:
     print(f"micro-batched exchange (4 queries, one all-gather): {'OK' if same else 'MISMATCH'}", flush=True)
+# batched form: tensor-core levels per shard, one all-gather for the whole batch, vectorised merge
+qb = o.synth_rows(779, 0, 300, dims, normalize=True)
+batch = eng.search_batch(qb, 10)
+same = all(batch[i] == eng.search(qb[i], 10) for i in (0, 1, 127, 128, 299))
+rows, d, s = o.search_synth(o.COSINE, seed, 0, total, dims, True, qb[5], 10, mode=o.ACC_F32_TREE, threads=16)
+same = same and [g[0] for g in batch[5]] == rows.tolist() and \
+    np.array_equal(np.float32([g[1] for g in batch[5]]).view(np.uint32), s.view(np.uint32))
+ok = ok and same
+if rank == 0:
+    print(f"sharded search_batch (300 queries, bf16 queries {eng.engine.counter('batch_bf16_queries')}): "
+          f"{'OK' if same else 'MISMATCH'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

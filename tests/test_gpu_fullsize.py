@@ -117,3 +117,26 @@ def test_single_rank_micro_batched_exchange(oracle):
     h1 = eng.search_many_async(d_qs[:2], 10, slot=0)
     h2 = eng.search_many_async(d_qs[2:], 10, slot=1)             # two micro-batches in flight
     assert eng.finish_many(h1) + eng.finish_many(h2) == many
+
+
+def test_single_rank_sharded_search_batch(oracle):
+    """ShardedVectorEngine.search_batch (wax_vs_search_batch_device + vectorised merge): identical to one query at a
+    time, through the tensor-core levels (the counters say so), with a shard offset in the global rows."""
+    import torch
+    eng = sharded.ShardedVectorEngine(VectorMetric.cosine, DIMS, total_rows=90_000)
+    eng.fill_synthetic(13)
+    qs = oracle.synth_rows(1007, 0, 140, DIMS)
+    one_by_one = [eng.search(q, 10) for q in qs]
+    assert eng.search_batch(qs, 10) == one_by_one
+    assert eng.engine.counter("batch_bf16_queries") == 140
+    assert eng.search_batch(torch.from_numpy(qs).cuda(), 10) == one_by_one      # device-resident queries
+    # global rows: a second engine holding the same rows as rows [50_000, 140_000) of a larger corpus
+    eng.row_lo, eng.row_hi = 50_000, 140_000
+    ids, scores, ns = eng.search_batch_arrays(qs[:8], 10)
+    assert ns.tolist() == [10] * 8 and [int(i) for i in ids[0]] == [g[0] for g in one_by_one[0]]   # frame ids unchanged
+    assert np.array_equal(scores[0], np.float32([g[1] for g in one_by_one[0]]))
+    # k larger than the shard: padded by the scan path
+    tiny = sharded.ShardedVectorEngine(VectorMetric.cosine, DIMS, total_rows=6)
+    tiny.fill_synthetic(14)
+    got = tiny.search_batch(qs[:5], 10)
+    assert [len(g) for g in got] == [6] * 5 and got == [tiny.search(q, 10) for q in qs[:5]]

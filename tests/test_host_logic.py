@@ -49,3 +49,27 @@ def test_engine_argument_errors_are_wax_errors():
         wax_b200.CUDAVectorEngine(wax_b200.VectorMetric.cosine, 0)
     with pytest.raises(wax_b200.CapacityExceeded):
         wax_b200.CUDAVectorEngine(wax_b200.VectorMetric.cosine, 1_000_001)
+
+
+def test_batched_merge_equals_the_per_query_merge():
+    """merge_candidates_batch (vectorised, two stable sorts) == merge_candidates per query: ties on distance broken by
+    the global row, invalid candidates dropped, fewer than k valid results allowed."""
+    from wax_b200 import sharded
+    rng = np.random.default_rng(5)
+    world, batch, k = 4, 9, 12
+    c = np.zeros((world, batch, k), sharded.CAND_DTYPE)
+    c["distance"] = rng.integers(0, 6, size=c.shape).astype(np.float32) / 4          # many exact ties
+    c["row"] = rng.permutation(c.size).reshape(c.shape)
+    c["frame_id"] = c["row"] + 1000
+    c["valid"] = rng.integers(0, 3, size=c.shape) > 0
+    c["valid"][:, 0, :] = 0                                                           # a query with no valid candidate
+    c["valid"][1:, 1, :] = 0; c["valid"][0, 1, 3:] = 0; c["valid"][0, 1, :3] = 1     # a query with 3
+    for top in (1, 5, 12, 40):
+        best, n = sharded.merge_candidates_batch(c, top)
+        assert best.shape == (batch, min(top, world * k))
+        for i in range(batch):
+            ref = sharded.merge_candidates(c[:, i, :], top)
+            assert n[i] == ref.size
+            assert np.array_equal(best[i, : ref.size]["row"], ref["row"])
+            assert np.array_equal(best[i, : ref.size]["frame_id"], ref["frame_id"])
+    assert sharded.merge_candidates_batch(c, 5)[1][0] == 0 and sharded.merge_candidates_batch(c, 5)[1][1] == 3

@@ -44,6 +44,13 @@ def _worker(rank, world, port, total, dims, k, seed, q, out_dir):
         assert (eng.row_lo, eng.row_hi) == (lo, hi)
         hits = eng.search(q, k)
         np.save(Path(out_dir) / f"r{rank}.npy", np.array(hits, dtype=np.float64))
+        # the batched form: one exchange for the whole batch, vectorised merge -- the same answer per query
+        qs = np.stack([q, o.synth_row(78, 0, dims, True), q * np.float32(2.0)])
+        batch = eng.search_batch(qs, k)
+        assert batch[0] == hits and batch[2] == hits
+        ids, scores, ns = eng.search_batch_arrays(qs, k)
+        assert ids.shape == (3, min(k, total)) and ns.tolist() == [len(b) for b in batch]
+        np.save(Path(out_dir) / f"b{rank}.npy", np.array(batch[1], dtype=np.float64))
     finally:
         dist.destroy_process_group()
 
@@ -58,3 +65,9 @@ def test_two_rank_sharded_search_equals_single_scan(tmp_path, oracle, total, k):
         got = np.load(tmp_path / f"r{rank}.npy").reshape(-1, 2)
         assert got[:, 0].astype(np.int64).tolist() == (rows.astype(np.int64) + 7).tolist()
         assert np.array_equal(got[:, 1].astype(np.float32), s)
+    q2 = o.synth_row(78, 0, dims, True)
+    rows2, _, s2 = o.search_synth(o.COSINE, seed, 0, total, dims, True, q2, k, mode=o.ACC_F32_TREE)
+    for rank in range(2):
+        got = np.load(tmp_path / f"b{rank}.npy").reshape(-1, 2)
+        assert got[:, 0].astype(np.int64).tolist() == (rows2.astype(np.int64) + 7).tolist()
+        assert np.array_equal(got[:, 1].astype(np.float32), s2)

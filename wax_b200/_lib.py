@@ -47,6 +47,8 @@ SIGNATURES = {
                                         C.c_uint32, _u32p]),
     "wax_vs_search_device": (C.c_int32, [_eng, C.c_void_p, C.c_uint32, C.c_int64, C.c_uint64, C.c_void_p,
                                          C.c_void_p]),
+    "wax_vs_search_batch_device": (C.c_int32, [_eng, C.c_void_p, C.c_uint32, C.c_int64, C.c_uint64, C.c_void_p,
+                                               C.c_void_p]),
     "wax_vs_serialized_length": (C.c_int32, [_eng, _u64p]),
     "wax_vs_serialize": (C.c_int32, [_eng, _u8p, C.c_uint64, _u64p]),
     "wax_vs_deserialize": (C.c_int32, [_eng, _u8p, C.c_uint64]),

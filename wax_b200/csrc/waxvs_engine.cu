@@ -1021,6 +1021,86 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
 }
 
 // ---- search ---------------------------------------------------------------------------------------------------
+// n_queries device-resident queries -> d_out[n_queries][k_eff] on c->stream: the tensor-core levels (bf16 shadow ->
+// TF32 retry -> exact scan) when the batch is eligible, else one fused scan per query.  The tensor
+// levels read their proof flags back, so they synchronise c->stream; the scan loop only enqueues.
+static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
+                                     uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, const uint64_t *d_ids,
+                                     uint64_t *launches) {
+    int32_t rc = WAX_VS_OK;
+    bool tensor_path = batch_tensor_eligible(e, n_queries, k_eff), allow_bf16 = true;
+    if (tensor_path) {
+        std::lock_guard<std::mutex> pg(e->pool_mu);
+        if (e->bf16_skip_batches > 0) { --e->bf16_skip_batches; allow_bf16 = false; }
+    }
+    // below batch_min the tensor path only pays off through the bf16 shadow (single_shadow): never TF32 for one query
+    if (tensor_path && !allow_bf16 && n_queries < static_cast<uint32_t>(std::max(e->tune.batch_min, 1))) tensor_path = false;
+    if (tensor_path) {
+        // Batched: one tensor-core pass over the corpus nominates, the finish kernel re-scores exactly and
+        // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
+        if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
+        if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
+        bool used_bf16 = false;
+        rc = enqueue_batch_tensor(e, c, d_queries, n_queries, k_eff, row_offset, d_out, c->d_ok, d_ids, c->stream, launches,
+                                  allow_bf16, &used_bf16);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaStreamSynchronize(c->stream));
+        std::vector<uint32_t> unproven;
+        for (uint32_t qi = 0; qi < n_queries; ++qi) if (!c->h_ok[qi]) unproven.push_back(qi);
+        if (used_bf16 && unproven.size() * 4 > n_queries) {
+            std::lock_guard<std::mutex> pg(e->pool_mu);
+            e->bf16_skip_batches = 16;
+        }
+        uint64_t retried = 0;
+        if (used_bf16 && e->tune.batch_retry && unproven.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1)) &&
+            batch_tensor_eligible(e, static_cast<uint32_t>(unproven.size()), k_eff)) {
+            // Second level: the queries the coarse bf16 bound could not prove go through the TF32 nominations
+            // (4x tighter bound) as one compacted sub-batch; only what is still unproven pays for an exact scan.
+            const uint32_t nf = static_cast<uint32_t>(unproven.size());
+            retried = nf;
+            if ((rc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "retry queries"))) return rc;
+            if ((rc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "retry results"))) return rc;
+            if ((rc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "retry flags"))) return rc;
+            for (uint32_t i = 0; i < nf; ++i)
+                CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
+                                         d_queries + static_cast<size_t>(unproven[i]) * e->dims, e->dims * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, c->stream));
+            rc = enqueue_batch_tensor(e, c, c->d_retry_q, nf, k_eff, row_offset, c->d_retry_out, c->d_retry_ok, d_ids, c->stream,
+                                      launches, false, nullptr);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+            for (uint32_t i = 0; i < nf; ++i)
+                CUDA_TRY(cudaMemcpyAsync(d_out + static_cast<size_t>(unproven[i]) * k_eff,
+                                         c->d_retry_out + static_cast<size_t>(i) * k_eff, k_eff * sizeof(wax_vs_candidate),
+                                         cudaMemcpyDeviceToDevice, c->stream));
+            CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            std::vector<uint32_t> still;
+            for (uint32_t i = 0; i < nf; ++i) if (!c->h_ok[i]) still.push_back(unproven[i]);
+            unproven.swap(still);
+        }
+        for (uint32_t qi : unproven) {
+            rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
+                                d_out + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, launches);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        }
+        {
+            std::lock_guard<std::mutex> pg(e->pool_mu);
+            e->batch_tensor_queries += n_queries - unproven.size();
+            e->batch_fallback_queries += unproven.size();
+            if (used_bf16) e->batch_bf16_queries += n_queries;
+            e->batch_retry_queries += retried;
+        }
+    } else {
+        for (uint32_t qi = 0; qi < n_queries; ++qi) {
+            rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
+                                d_out + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, launches);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        }
+    }
+    return WAX_VS_OK;
+}
+
 static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_queries, uint32_t query_len,
                            int64_t top_k, uint64_t *out_ids, float *out_scores, uint32_t out_stride,
                            uint32_t *out_n) {
@@ -1057,76 +1137,7 @@ static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_qu
     memcpy(c->h_queries, queries, qfloats * sizeof(float));
     CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     uint64_t launches = 0;
-    bool tensor_path = batch_tensor_eligible(e, n_queries, k_eff), allow_bf16 = true;
-    if (tensor_path) {
-        std::lock_guard<std::mutex> pg(e->pool_mu);
-        if (e->bf16_skip_batches > 0) { --e->bf16_skip_batches; allow_bf16 = false; }
-    }
-    // below batch_min the tensor path only pays off through the bf16 shadow (single_shadow): never TF32 for one query
-    if (tensor_path && !allow_bf16 && n_queries < static_cast<uint32_t>(std::max(e->tune.batch_min, 1))) tensor_path = false;
-    if (tensor_path) {
-        // Batched: one tensor-core pass over the corpus nominates, the finish kernel re-scores exactly and
-        // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
-        if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
-        if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
-        bool used_bf16 = false;
-        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches,
-                                  allow_bf16, &used_bf16);
-        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-        CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaStreamSynchronize(c->stream));
-        std::vector<uint32_t> unproven;
-        for (uint32_t qi = 0; qi < n_queries; ++qi) if (!c->h_ok[qi]) unproven.push_back(qi);
-        if (used_bf16 && unproven.size() * 4 > n_queries) {
-            std::lock_guard<std::mutex> pg(e->pool_mu);
-            e->bf16_skip_batches = 16;
-        }
-        uint64_t retried = 0;
-        if (used_bf16 && e->tune.batch_retry && unproven.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1)) &&
-            batch_tensor_eligible(e, static_cast<uint32_t>(unproven.size()), k_eff)) {
-            // Second level: the queries the coarse bf16 bound could not prove go through the TF32 nominations
-            // (4x tighter bound) as one compacted sub-batch; only what is still unproven pays for an exact scan.
-            const uint32_t nf = static_cast<uint32_t>(unproven.size());
-            retried = nf;
-            if ((rc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "retry queries"))) return rc;
-            if ((rc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "retry results"))) return rc;
-            if ((rc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "retry flags"))) return rc;
-            for (uint32_t i = 0; i < nf; ++i)
-                CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
-                                         c->d_queries + static_cast<size_t>(unproven[i]) * e->dims, e->dims * sizeof(float),
-                                         cudaMemcpyDeviceToDevice, c->stream));
-            rc = enqueue_batch_tensor(e, c, c->d_retry_q, nf, k_eff, 0, c->d_retry_out, c->d_retry_ok, nullptr, c->stream,
-                                      &launches, false, nullptr);
-            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-            for (uint32_t i = 0; i < nf; ++i)
-                CUDA_TRY(cudaMemcpyAsync(c->d_out + static_cast<size_t>(unproven[i]) * k_eff,
-                                         c->d_retry_out + static_cast<size_t>(i) * k_eff, k_eff * sizeof(wax_vs_candidate),
-                                         cudaMemcpyDeviceToDevice, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            std::vector<uint32_t> still;
-            for (uint32_t i = 0; i < nf; ++i) if (!c->h_ok[i]) still.push_back(unproven[i]);
-            unproven.swap(still);
-        }
-        for (uint32_t qi : unproven) {
-            rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
-                                c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
-            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-        }
-        {
-            std::lock_guard<std::mutex> pg(e->pool_mu);
-            e->batch_tensor_queries += n_queries - unproven.size();
-            e->batch_fallback_queries += unproven.size();
-            if (used_bf16) e->batch_bf16_queries += n_queries;
-            e->batch_retry_queries += retried;
-        }
-    } else {
-        for (uint32_t qi = 0; qi < n_queries; ++qi) {
-            rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(qi) * e->dims, k_eff, 0,
-                                c->d_out + static_cast<size_t>(qi) * k_eff, nullptr, c->stream, &launches);
-            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-        }
-    }
+    if ((rc = run_queries_on_device(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, nullptr, &launches))) return rc;
     CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, ncand * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));
 
@@ -1189,6 +1200,46 @@ int32_t wax_vs_search_device(wax_vs_engine *e, const float *d_queries, uint32_t 
         if (rc) return rc;
     }
     return WAX_VS_OK;
+}
+
+// Batched form of wax_vs_search_device: the tensor-core levels on the caller's stream for the rank's shard.  Unlike
+// the single-query form it may SYNCHRONISE the stream (the proof flags are read back before the unproven queries
+// are re-run), so on return d_candidates is complete on `cuda_stream` order and usually already materialised.
+int32_t wax_vs_search_batch_device(wax_vs_engine *e, const float *d_queries, uint32_t n_queries, int64_t top_k,
+                                   uint64_t row_offset, wax_vs_candidate *d_candidates, void *cuda_stream) {
+    if (!e || !d_queries || !d_candidates) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (n_queries == 0) return WAX_VS_OK;
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    const uint32_t k_eff = clamp_topk(top_k);
+    SearchCtx *c = nullptr;
+    {
+        std::lock_guard<std::mutex> pg(e->pool_mu);
+        auto it = e->stream_ctx.find(cuda_stream);
+        if (it != e->stream_ctx.end()) c = it->second;
+    }
+    if (!c) {
+        int32_t rc = ctx_new(e, &c, false);
+        if (rc) return rc;
+        c->stream = static_cast<cudaStream_t>(cuda_stream);
+        std::lock_guard<std::mutex> pg(e->pool_mu);
+        e->stream_ctx[cuda_stream] = c;
+        ++e->pool_allocs;
+    }
+    const uint64_t *d_ids = nullptr;
+    int32_t rc = sync_device_ids(e, &d_ids);
+    if (rc) return rc;
+    uint64_t launches = 0;
+    if (k_eff > e->n_rows) {   // a shard smaller than k: the scan pads with invalid candidates, the tensor path does not
+        for (uint32_t qi = 0; qi < n_queries; ++qi) {
+            rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
+                                d_candidates + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, &launches);
+            if (rc) return rc;
+        }
+        return WAX_VS_OK;
+    }
+    return run_queries_on_device(e, c, d_queries, n_queries, k_eff, row_offset, d_candidates, d_ids, &launches);
 }
 
 // ---- filtered search -------------------------------------------------------------------

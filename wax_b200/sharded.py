@@ -43,6 +43,20 @@ def merge_candidates(gathered: np.ndarray, top_k: int) -> np.ndarray:
     return flat[order[:top_k]]
 
 
+def merge_candidates_batch(gathered: np.ndarray, top_k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """Vectorised R-way merge for a batch: `gathered` is [world, batch, k] CAND_DTYPE; returns ([batch, top_k]
+    records ordered by (distance, global row) with the invalid ones last, [batch] count of valid results).
+    Same total order as merge_candidates (two stable sorts: by row, then by distance)."""
+    world, batch, k = gathered.shape
+    flat = np.ascontiguousarray(gathered.transpose(1, 0, 2)).reshape(batch, world * k)
+    dist = np.where(flat["valid"] != 0, flat["distance"], np.float32(np.inf))
+    by_row = np.argsort(flat["row"], axis=1, kind="stable")
+    by_dist = np.argsort(np.take_along_axis(dist, by_row, 1), axis=1, kind="stable")
+    order = np.take_along_axis(by_row, by_dist, 1)[:, :top_k]
+    best = np.take_along_axis(flat, order, 1)
+    return best, (best["valid"] != 0).sum(axis=1).astype(np.uint32)
+
+
 def score_from_distance(similarity: int, d: np.ndarray) -> np.ndarray:
     """VectorMetric.score(fromDistance:) (VectorMetric.swift:32-43), vectorised, fp32."""
     d = d.astype(np.float32)
@@ -201,6 +215,51 @@ class ShardedVectorEngine:
             scores = score_from_distance(sim, best["distance"])
             out.append([(int(best["frame_id"][j]), float(scores[j])) for j in range(best.size)])
         return out
+
+    def search_batch_arrays(self, queries, top_k: int):
+        """A batch of independent queries against the sharded corpus: every rank runs the batched tensor-core levels
+        (wax_vs_search_batch_device: bf16-shadow nominations -> TF32 retry -> exact scan, results identical to
+        single-query scans) on its shard, ONE all-gather carries batch x k candidates per rank, one vectorised host
+        merge.  `queries`: [batch, dims] host array or device tensor (identical on every rank).  Returns
+        (ids [batch, k_eff] uint64, scores [batch, k_eff] float32, n_valid [batch] uint32)."""
+        torch, dist = self._torch, self._dist
+        k = clamp_topk(top_k)
+        k_eff = min(k, self.total_rows) if self.total_rows else k
+        if self._local_search is not None:
+            qs = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dimensions)
+            b = qs.shape[0]
+            local_np = np.zeros((b, k), CAND_DTYPE)
+            for i in range(b):
+                local_np[i] = np.ascontiguousarray(self._local_search(qs[i], k), dtype=CAND_DTYPE)
+            local = torch.from_numpy(local_np.view(np.uint8).reshape(-1).copy())
+        else:
+            from . import _lib as L
+            if isinstance(queries, torch.Tensor):
+                d_qs = queries.to(self.device, dtype=torch.float32).contiguous().reshape(-1, self.dimensions)
+            else:
+                d_qs = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dimensions)).to(self.device)
+            b = int(d_qs.shape[0])
+            local = torch.empty(b * k * 24, dtype=torch.uint8, device=self.device)
+            stream = torch.cuda.current_stream(self.device)
+            rc = L.lib().wax_vs_search_batch_device(self.engine.handle, C.c_void_p(d_qs.data_ptr()), b, k, self.row_lo,
+                                                    C.c_void_p(local.data_ptr()), C.c_void_p(stream.cuda_stream))
+            if rc != 0:
+                raise RuntimeError(f"wax_vs_search_batch_device rc={rc}: {L.last_error()}")
+        if b == 0 or self.total_rows == 0:
+            return np.zeros((b, 0), np.uint64), np.zeros((b, 0), np.float32), np.zeros(b, np.uint32)
+        if self.world_size > 1:
+            gathered = torch.empty(self.world_size * b * k * 24, dtype=torch.uint8, device=local.device)
+            dist.all_gather_into_tensor(gathered, local, group=self.group)
+        else:
+            gathered = local
+        cands = gathered.cpu().numpy().view(CAND_DTYPE).reshape(self.world_size, b, k)
+        best, n_valid = merge_candidates_batch(cands, k_eff)
+        scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
+        return best["frame_id"].astype(np.uint64), scores, n_valid
+
+    def search_batch(self, queries, top_k: int) -> List[List[Tuple[int, float]]]:
+        ids, scores, ns = self.search_batch_arrays(queries, top_k)
+        return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(ids.shape[0])]
 
     def finish(self, handle) -> List[Tuple[int, float]]:
         host, ev, k = handle
