@@ -261,3 +261,45 @@ def test_single_shadow_mode_routes_single_queries_through_the_shadow(oracle):
     assert eng.counter("batch_bf16_queries") == n0 + 1 and eng.batch_stats()[1] == 1
     assert eng.search(qs[1], 10) == expect[1]
     assert eng.counter("batch_bf16_queries") == n0 + 1          # suspended: answered by the fp32 scan
+
+
+def _clustered(n, dims, n_centres, sigma, seed, normalize=True):
+    rng = np.random.default_rng(seed)
+    centres = rng.standard_normal((n_centres, dims)).astype(np.float32)
+    centres /= np.linalg.norm(centres, axis=1, keepdims=True)
+    corpus = centres[rng.integers(0, n_centres, n)] + np.float32(sigma / np.sqrt(dims)) * rng.standard_normal((n, dims)).astype(np.float32)
+    if normalize:
+        corpus /= np.linalg.norm(corpus, axis=1, keepdims=True)
+    else:
+        corpus *= rng.uniform(0.5, 2.0, size=(n, 1)).astype(np.float32)
+    qs = corpus[rng.integers(0, n, 96)] + np.float32(0.2 / np.sqrt(dims)) * rng.standard_normal((96, dims)).astype(np.float32)
+    return corpus.astype(np.float32), qs.astype(np.float32)
+
+
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+@pytest.mark.parametrize("bf16", [1, 0])
+def test_filter_level_answers_tight_clusters_without_exact_scans(oracle, metric, bf16):
+    """Tightly clustered rows (2 000 per cluster, pairwise cosine > 0.98): the k-th result is closer to the 257th
+    nominee than any tensor-core bound, so level 1 cannot prove anything.  The filter level (one TF32 pass that
+    collects EVERY row above `exact k-th score of the nominees - eps`, exact re-score of all of them) must answer those
+    queries -- identical ids and score bits, no exact scan."""
+    dims, n = 384, 60_000
+    corpus, qs = _clustered(n, dims, 30, 0.1, seed=77)          # unit rows for both metrics (dot then ranks like cosine)
+    eng = CUDAVectorEngine(metric, dims)
+    eng.add_batch(list(range(n)), corpus)
+    eng.set_option("batch_bf16", bf16)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, 10)
+    t1, f1 = eng.batch_stats()
+    assert got == _single(eng, qs, 10)
+    r, d, s = oracle.search(metric.value, corpus, qs[3], 10, mode=oracle.ACC_F32_TREE, threads=4)
+    assert [g[0] for g in got[3]] == r.tolist()
+    assert np.array_equal(np.float32([g[1] for g in got[3]]).view(np.uint32), s.view(np.uint32))
+    assert eng.counter("batch_retry_queries") >= 48, "the filter level was not exercised"
+    assert f1 - f0 == 0, f"{f1 - f0} queries needed an exact scan"
+    # a list that overflows is reported, not truncated: those queries take the exact scan, same answers
+    eng.set_option("batch_bf16", bf16)
+    eng.set_option("filter_cap", 64)
+    got2 = eng.search_batch(qs, 10)
+    assert got2 == got
+    assert eng.batch_stats()[1] - f1 >= 48

@@ -80,6 +80,12 @@ struct BatchParams {
     uint64_t *heaps;        // [slices*groups][HEAP][128]: each CTA's heaps, dumped entry-major at the end
     uint32_t *tau_global;   // [n_queries] orderable(score') of the best k'-th nominee any slice has reached (0 = none)
     uint32_t no_insert;     // instrumentation: skip nominations (timing floor of the GEMM pipeline)
+    // FILTER form (level 2): no heaps -- every row whose score' beats the query's FIXED threshold is appended to the
+    // query's candidate list (complete by construction, see filter level below)
+    const float *tau_fixed; // [n_queries]
+    uint32_t *cand_count;   // [n_queries] appended so far (may exceed cand_cap: overflow)
+    uint32_t *cand_rows;    // [n_queries][cand_cap]
+    uint32_t cand_cap;
 };
 
 // ---- PTX wrappers (tcgen05 / TMA tensor) ---------------------------------------------------------------------
@@ -329,7 +335,9 @@ __global__ void __launch_bounds__(256) shadow_bf16_kernel(const float *__restric
 //       twice the TF32 rate for the same bytes per cycle) -- nominations only, exactness comes from the finish kernel.
 // ARES: the CTA's 128 queries stay resident in shared memory (dims/64 bf16 k-blocks of 16 KB, loaded once), the ring
 //       stages carry only corpus tiles: a third less L2->SM and TMA->smem traffic per MMA.
-template <int STAGES, int HEAP, bool PAIR, bool BF16 = false, bool ARES = false>
+// FILTER: the epilogue appends every row beating the query's fixed threshold to a per-query list instead of keeping
+//       the k' best in a heap (the filter level: complete by construction).
+template <int STAGES, int HEAP, bool PAIR, bool BF16 = false, bool ARES = false, bool FILTER = false>
 __global__ void __launch_bounds__(kBatchThreads, 1)
 batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_c,
                       const BatchParams p) {
@@ -481,13 +489,24 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
         const uint32_t q = group * kBatchM + tid;
         const bool q_valid = q < p.n_queries && !p.no_insert;
         uint64_t *heap = heap_smem + tid;
-        for (uint32_t i = 0; i < HEAP; ++i) heap[i * kBatchM] = WAXVS_KEY_NONE;
+        if (!FILTER) for (uint32_t i = 0; i < HEAP; ++i) heap[i * kBatchM] = WAXVS_KEY_NONE;
         uint64_t root = WAXVS_KEY_NONE;                               // heap[0]: this slice's k'-th best so far
         float tau = -INFINITY;
+        if (FILTER && q_valid) tau = __ldg(p.tau_fixed + q);          // never changes: the list is a pure filter
         uint64_t *stage = stage_smem + tid;                           // slot i at stage[i * 128]
         uint32_t cnt = 0;
         bool improved = false;
         auto flush = [&]() {
+            if (FILTER) {                                             // staged rows -> the query's global list
+                if (cnt) {
+                    const uint32_t base = atomicAdd(p.cand_count + q, cnt);
+                    for (uint32_t i = 0; i < cnt; ++i)
+                        if (base + i < p.cand_cap)
+                            p.cand_rows[static_cast<size_t>(q) * p.cand_cap + base + i] = static_cast<uint32_t>(stage[i * kBatchM]);
+                }
+                cnt = 0;
+                return;
+            }
             for (uint32_t i = 0; i < cnt; ++i) {
                 const uint64_t x = stage[i * kBatchM];
                 if (x < root) { root = heap_replace_root<HEAP>(heap, x); improved = true; }
@@ -512,10 +531,10 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 }
                 asm volatile("bar.sync 1, 128;" ::: "memory");        // scales visible; previous use of sc[] finished
             }
-            if (g_next) tau = fmaxf(tau, from_orderable_u32(g_next)); // adopt the best threshold any slice has published
+            if (!FILTER && g_next) tau = fmaxf(tau, from_orderable_u32(g_next)); // adopt the best threshold any slice has published
             mbar_wait_parity(&tmem_full[acc], acc_phase);
             tcgen05_fence_after();
-            if (q_valid) g_next = __ldcg(p.tau_global + q);           // consumed at the next tile
+            if (!FILTER && q_valid) g_next = __ldcg(p.tau_global + q); // consumed at the next tile
             const uint32_t rows_here = min(static_cast<uint32_t>(kBatchN), p.n_rows - row0);
 #pragma unroll 1
             for (uint32_t chunk = 0; chunk < kBatchN / 32; ++chunk) {
@@ -582,16 +601,18 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             }
             if (__any_sync(WAXVS_FULL_MASK, cnt >= kBatchStageSlots / 2)) {
                 flush();
-                if (improved && q_valid && root != WAXVS_KEY_NONE) {  // heap full: publish this slice's k'-th best
+                if (!FILTER && improved && q_valid && root != WAXVS_KEY_NONE) {  // heap full: publish this slice's k'-th best
                     atomicMax(p.tau_global + q, orderable_u32(nominee_score(root)));
                     improved = false;
                 }
             }
         }
         flush();
-        // dump this CTA's heaps (entry-major, coalesced) for batch_finish_kernel
-        uint64_t *dst = p.heaps + static_cast<size_t>(slice * p.groups + group) * HEAP * kBatchM + tid;
-        for (uint32_t i = 0; i < HEAP; ++i) dst[i * kBatchM] = heap[i * kBatchM];
+        if (!FILTER) {
+            // dump this CTA's heaps (entry-major, coalesced) for batch_finish_kernel
+            uint64_t *dst = p.heaps + static_cast<size_t>(slice * p.groups + group) * HEAP * kBatchM + tid;
+            for (uint32_t i = 0; i < HEAP; ++i) dst[i * kBatchM] = heap[i * kBatchM];
+        }
     }
     tcgen05_fence_before();
     if (PAIR) cluster_sync_all(); else __syncthreads();   // PAIR: the peer may still arrive on / read this CTA's shared memory
@@ -977,6 +998,9 @@ struct FinishParams {
     uint32_t pow2_all;          // next pow2 >= slices*kprime
     uint32_t rescore;           // nominees re-scored exactly per query: a power of two in [256, kBatchRescoreMax]
     float eps_rel;              // kTf32Eps or kBf16Eps: |score' - score| <= eps_rel * |q||v|
+    float *tau_star;            // [n_queries] or nullptr: threshold for the filter level, in score' units:
+                                // (exact k-th score of the re-scored nominees) - filter_eps_rel * |q| (* max|v|); -inf if none
+    float filter_eps_rel;       // bound of the operand type the FILTER pass will use (TF32)
 };
 
 // One CTA per query.  Union of the slices' nominee heaps -> best kBatchRescore by score' -> exact re-score ->
@@ -1047,25 +1071,93 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
         uint32_t n_exact = 0;
         while (n_exact < kpp && ek[n_exact] != WAXVS_KEY_NONE) ++n_exact;
         uint32_t ok = 1;
-        if (excluded_any) {
-            if (n_exact < p.k) ok = 0;
-            else {
-                const float dk = from_orderable_u32(static_cast<uint32_t>(ek[p.k - 1] >> 32));
-                const float qn = s_sqrt_a2;
-                float sk_exact, eps;
-                if (METRIC == kCosine) { sk_exact = (1.0f - dk) * qn; eps = p.eps_rel * qn; }
-                else { sk_exact = 1.0f - dk; eps = p.eps_rel * qn * __uint_as_float(*p.max_norm_bits); }
-                eps = eps * 1.01f + 1e-30f;
-                if (!(sk_exact > tau + eps) || !finite_f32(eps)) ok = 0;
-            }
+        float tau_star = -INFINITY;
+        if (n_exact >= p.k) {
+            const float dk = from_orderable_u32(static_cast<uint32_t>(ek[p.k - 1] >> 32));
+            const float qn = s_sqrt_a2;
+            const float scale = METRIC == kCosine ? qn : qn * __uint_as_float(*p.max_norm_bits);
+            const float sk_exact = METRIC == kCosine ? (1.0f - dk) * qn : 1.0f - dk;
+            const float eps = p.eps_rel * scale * 1.01f + 1e-30f;
+            if (excluded_any && (!(sk_exact > tau + eps) || !finite_f32(eps))) ok = 0;
+            // Filter level: the true top-k rows all have exact score >= the true k-th score >= sk_exact (the nominees
+            // are a subset of the corpus), hence score' >= sk_exact - eps_filter: a pass that collects EVERY row above
+            // that fixed threshold misses none of them.  A relative 2^-20 margin absorbs the rounding of this
+            // subtraction and of the fp32 products sk_exact was built from.
+            const float feps = p.filter_eps_rel * scale * 1.01f + 1e-30f;
+            const float t = sk_exact - feps;
+            tau_star = finite_f32(t) ? t - fabsf(t) * 0x1p-20f - 1e-30f : -INFINITY;
+        } else if (excluded_any) {
+            ok = 0;
         }
         p.ok[q] = ok;
+        if (p.tau_star) p.tau_star[q] = tau_star;
     }
     ScanParams sp{};
     sp.out = p.out + static_cast<size_t>(q) * p.k;
     sp.frame_ids = p.frame_ids; sp.id_base = p.id_base; sp.row_offset = p.row_offset;
     for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x)
         write_candidate(sp, static_cast<int>(i), i < p.rescore ? ek[i] : WAXVS_KEY_NONE);
+}
+
+// ---- filter level (level 2): exact re-score of EVERY candidate above the fixed threshold, then top-k ------------------
+// One warp per (query, candidate): exact distance in the kernels' order (bit-identical to the single-query path).
+template <int METRIC>
+__global__ void __launch_bounds__(256) filter_rescore_kernel(const float *corpus, const float *queries, uint32_t dims,
+                                                             const uint32_t *cand_count, const uint32_t *cand_rows,
+                                                             uint32_t cand_cap, uint64_t *keys) {
+    const uint32_t q = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const uint32_t n = min(cand_count[q], cand_cap);
+    const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
+    uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= n) return;
+    const float *qv = queries + static_cast<size_t>(q) * dims;
+    float a2 = 0.0f, sqrt_a2 = 0.0f;
+    if (METRIC == kCosine) {
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+        for (uint32_t base = 4u * lane; base < dims; base += 128u) {
+            const float x = __ldg(qv + base); s0 = __fmaf_rn(x, x, s0);
+            if (base + 1 < dims) { const float y = __ldg(qv + base + 1); s1 = __fmaf_rn(y, y, s1); }
+            if (base + 2 < dims) { const float z = __ldg(qv + base + 2); s2 = __fmaf_rn(z, z, s2); }
+            if (base + 3 < dims) { const float w = __ldg(qv + base + 3); s3 = __fmaf_rn(w, w, s3); }
+        }
+        a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
+        sqrt_a2 = __fsqrt_rn(a2);
+    }
+    for (; i < n; i += warps) {
+        const uint32_t row = cand_rows[static_cast<size_t>(q) * cand_cap + i];
+        const float d = exact_row_distance<METRIC>(qv, corpus + static_cast<size_t>(row) * dims, dims, a2, sqrt_a2, lane);
+        if (lane == 0) keys[static_cast<size_t>(q) * cand_cap + i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
+    }
+}
+
+struct FilterSelectParams {
+    const uint32_t *cand_count;
+    const uint64_t *keys;       // [n_queries][cand_cap]
+    uint32_t cand_cap, k;
+    wax_vs_candidate *out;      // [n_queries][k]
+    uint32_t *ok;               // [n_queries]: 1 = complete (the list did not overflow and holds >= k finite rows)
+    const uint64_t *frame_ids;
+    uint64_t id_base, row_offset;
+};
+
+// One CTA per query: sort its candidates' exact keys, the first k are the answer.
+__global__ void __launch_bounds__(1024) filter_select_kernel(const FilterSelectParams p) {
+    extern __shared__ uint64_t fsk[];
+    const uint32_t q = blockIdx.x;
+    const uint32_t total = p.cand_count[q];
+    const uint32_t n = min(total, p.cand_cap);
+    uint32_t pow2 = 64;
+    while (pow2 < n || pow2 < p.k) pow2 <<= 1;
+    for (uint32_t i = threadIdx.x; i < pow2; i += blockDim.x)
+        fsk[i] = (i < n) ? p.keys[static_cast<size_t>(q) * p.cand_cap + i] : WAXVS_KEY_NONE;
+    __syncthreads();
+    block_bitonic_sort(fsk, pow2);
+    if (threadIdx.x == 0) p.ok[q] = (total <= p.cand_cap && fsk[p.k - 1] != WAXVS_KEY_NONE) ? 1u : 0u;
+    ScanParams sp{};
+    sp.out = p.out + static_cast<size_t>(q) * p.k;
+    sp.frame_ids = p.frame_ids; sp.id_base = p.id_base; sp.row_offset = p.row_offset;
+    for (uint32_t i = threadIdx.x; i < p.k; i += blockDim.x) write_candidate(sp, static_cast<int>(i), fsk[i]);
 }
 
 }  // namespace waxvs

@@ -21,6 +21,7 @@
 #include <shared_mutex>
 #include <string>
 #include <unordered_map>
+#include <cmath>
 #include <vector>
 
 #include "../../include/wax_vs_cuda.h"
@@ -123,7 +124,8 @@ struct Tuning {
     int batch_bf16 = 1;     // 1: nominate from a bf16 shadow of the corpus when HBM allows (kind::f16 MMAs, 2x the TF32 rate; +dims*2 B/row)
     int batch_ares = 1;     // with batch_bf16: keep the CTA's queries resident in shared memory when they fit (dims <= 512)
     int batch_rescore = 0;  // 0 auto; else nominees re-scored exactly per query (256, 512 or 1024)
-    int batch_retry = 1;    // with batch_bf16: queries the bf16 pass cannot prove are retried on the TF32 pass first
+    int batch_retry = 1;    // queries level 1 cannot prove go through the filter level (TF32, complete by construction) before an exact scan
+    int filter_cap = 8192;  // candidates per query the filter level may collect (power of two <= 16384); overflow -> exact scan
     int single_shadow = 0;  // 1: single queries / batches below batch_min also take the bf16-shadow nominations
                             // (half the HBM bytes per query: 1.19 vs 2.04 ms at 10 M x 384, same results); off by
                             // default: the plain single-query path is the fused fp32 scan BASELINE's north_star names
@@ -151,6 +153,12 @@ struct SearchCtx {
     float *d_retry_q = nullptr; size_t retry_q_cap = 0;           // bf16 -> TF32 retry: compacted queries
     wax_vs_candidate *d_retry_out = nullptr; size_t retry_out_cap = 0;
     uint32_t *d_retry_ok = nullptr; size_t retry_ok_cap = 0;
+    float *d_tau_star = nullptr; size_t tau_star_cap = 0;         // level 1 -> filter level: per-query thresholds
+    float *h_tau_star = nullptr; size_t h_tau_star_cap = 0;       // pinned
+    float *d_filter_tau = nullptr; size_t filter_tau_cap = 0;     // compacted thresholds of the unproven queries
+    uint32_t *d_cand_count = nullptr; size_t cand_count_cap = 0;
+    uint32_t *d_cand_rows = nullptr; size_t cand_rows_cap = 0;
+    uint64_t *d_cand_keys = nullptr; size_t cand_keys_cap = 0;
     uint32_t *d_mask = nullptr; size_t mask_cap = 0;              // filtered search: row bitset / listed rows
     uint64_t *d_gather_keys = nullptr; size_t gather_cap = 0;     // filtered search: keys of the listed rows
 };
@@ -216,6 +224,12 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_retry_q) cudaFree(c->d_retry_q);
     if (c->d_retry_out) cudaFree(c->d_retry_out);
     if (c->d_retry_ok) cudaFree(c->d_retry_ok);
+    if (c->d_tau_star) cudaFree(c->d_tau_star);
+    if (c->h_tau_star) cudaFreeHost(c->h_tau_star);
+    if (c->d_filter_tau) cudaFree(c->d_filter_tau);
+    if (c->d_cand_count) cudaFree(c->d_cand_count);
+    if (c->d_cand_rows) cudaFree(c->d_cand_rows);
+    if (c->d_cand_keys) cudaFree(c->d_cand_keys);
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_gather_keys) cudaFree(c->d_gather_keys);
     if (c->h_ok) cudaFreeHost(c->h_ok);
@@ -581,7 +595,7 @@ static int ares_stages(bool pair, int heap, uint32_t num_kb, int want) {
 static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
                                     uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, uint32_t *d_ok,
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
-                                    bool allow_bf16 = true, bool *used_bf16 = nullptr) {
+                                    bool allow_bf16 = true, bool *used_bf16 = nullptr, float *d_tau_star = nullptr) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
     bool bf16 = allow_bf16 && batch_bf16_wanted(e);
@@ -612,6 +626,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true, true>, 227u * 1024u));
         chk(set_smem_attr(batch_tf32_ts_kernel<16>, batch_ts_smem_bytes(16)));
         chk(set_smem_attr(batch_tf32_ts_kernel<64>, batch_ts_smem_bytes(64)));
+        chk(set_smem_attr(batch_nominate_kernel<4, 16, false, false, false, true>, batch_smem_bytes(4, 16)));
+        chk(set_smem_attr(filter_select_kernel, 16384 * 8));
         chk(set_smem_attr(batch_finish_kernel<kCosine>, (16384 + kBatchRescoreMax) * 8));
         chk(set_smem_attr(batch_finish_kernel<kDot>, (16384 + kBatchRescoreMax) * 8));
     });
@@ -730,6 +746,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         fp.pow2_all = pow2;
         fp.rescore = rescore;
         fp.eps_rel = bf16 ? kBf16Eps : kTf32Eps;
+        fp.tau_star = d_tau_star ? d_tau_star + q0 : nullptr;
+        fp.filter_eps_rel = kTf32Eps;
         const size_t fsmem = static_cast<size_t>(pow2 + rescore) * sizeof(uint64_t);
         if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 256, fsmem, stream>>>(fp);
         else batch_finish_kernel<kDot><<<nq, 256, fsmem, stream>>>(fp);
@@ -1020,6 +1038,61 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
     return WAX_VS_OK;
 }
 
+// Filter level (level 2 of the batched path): for queries level 1 could not prove.  One TF32 tensor-core pass in
+// FILTER form appends EVERY row whose score' beats the query's fixed threshold tau* (= exact k-th score of level 1's
+// re-scored nominees - eps_tf32, so no true top-k row can be missing) to the query's candidate list; every candidate
+// is re-scored exactly, the k best are the answer.  Complete by construction -- d_ok[i] = 0 only if a list
+// overflowed (more than filter_cap rows within 2 eps of the k-th score: near-duplicates en masse).
+static int32_t enqueue_filter_level(wax_vs_engine *e, SearchCtx *c, const float *d_queries, const float *d_tau,
+                                    uint32_t n_queries, uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out,
+                                    uint32_t *d_ok, const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
+    int32_t rc = ensure_norms(e, stream);
+    if (rc) return rc;
+    uint32_t cap = 64;                      // a power of two in [64, 16384], at least k
+    while ((cap < static_cast<uint32_t>(std::max(e->tune.filter_cap, 64)) || cap < k_eff) && cap < 16384u) cap <<= 1;
+    if ((rc = ensure_dev(&c->d_cand_count, &c->cand_count_cap, static_cast<size_t>(n_queries), "filter counts"))) return rc;
+    if ((rc = ensure_dev(&c->d_cand_rows, &c->cand_rows_cap, static_cast<size_t>(n_queries) * cap, "filter candidates"))) return rc;
+    if ((rc = ensure_dev(&c->d_cand_keys, &c->cand_keys_cap, static_cast<size_t>(n_queries) * cap, "filter keys"))) return rc;
+    CUDA_TRY(cudaMemsetAsync(c->d_cand_count, 0, static_cast<size_t>(n_queries) * sizeof(uint32_t), stream));
+    const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
+    const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + kBatchN - 1) / kBatchN);
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += max_groups * kBatchM) {
+        const uint32_t nq = std::min<uint32_t>(n_queries - q0, max_groups * kBatchM);
+        const uint32_t groups = (nq + kBatchM - 1) / kBatchM;
+        const uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(e->sm_count) / groups, tiles_total));
+        CUtensorMap map_q, map_c;
+        const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
+        if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
+        if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, kBatchN))) return rc;
+        BatchParams bp{};
+        bp.n_rows = static_cast<uint32_t>(e->n_rows); bp.dims = e->dims; bp.n_queries = nq; bp.groups = groups;
+        bp.slices = slices; bp.tiles_total = tiles_total; bp.kprime = 16; bp.metric = e->similarity;
+        bp.row_scale = e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr;
+        bp.tau_fixed = d_tau + q0;
+        bp.cand_count = c->d_cand_count + q0;
+        bp.cand_rows = c->d_cand_rows + static_cast<size_t>(q0) * cap;
+        bp.cand_cap = cap;
+        CUDA_TRY(launch_nominate(batch_nominate_kernel<4, 16, false, false, false, true>, groups * slices, batch_smem_bytes(4, 16),
+                                 false, stream, map_q, map_c, bp));
+        const dim3 rgrid(32, nq);
+        if (e->similarity == WAX_VS_COSINE)
+            filter_rescore_kernel<kCosine><<<rgrid, 256, 0, stream>>>(e->d_corpus, qbase, e->dims, bp.cand_count, bp.cand_rows, cap,
+                                                                      c->d_cand_keys + static_cast<size_t>(q0) * cap);
+        else
+            filter_rescore_kernel<kDot><<<rgrid, 256, 0, stream>>>(e->d_corpus, qbase, e->dims, bp.cand_count, bp.cand_rows, cap,
+                                                                   c->d_cand_keys + static_cast<size_t>(q0) * cap);
+        CUDA_TRY(cudaGetLastError());
+        FilterSelectParams sp{};
+        sp.cand_count = bp.cand_count; sp.keys = c->d_cand_keys + static_cast<size_t>(q0) * cap; sp.cand_cap = cap; sp.k = k_eff;
+        sp.out = d_out + static_cast<size_t>(q0) * k_eff; sp.ok = d_ok + q0;
+        sp.frame_ids = d_ids; sp.id_base = e->id_base; sp.row_offset = row_offset;
+        filter_select_kernel<<<nq, 1024, static_cast<size_t>(cap) * sizeof(uint64_t), stream>>>(sp);
+        CUDA_TRY(cudaGetLastError());
+        *launches += 3;
+    }
+    return WAX_VS_OK;
+}
+
 // ---- search ---------------------------------------------------------------------------------------------------
 // n_queries device-resident queries -> d_out[n_queries][k_eff] on c->stream: the tensor-core levels (bf16 shadow ->
 // TF32 retry -> exact scan) when the batch is eligible, else one fused scan per query.  The tensor
@@ -1040,11 +1113,14 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
         if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
         if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
+        if ((rc = ensure_dev(&c->d_tau_star, &c->tau_star_cap, static_cast<size_t>(n_queries), "filter thresholds"))) return rc;
+        if ((rc = ensure_pinned(&c->h_tau_star, &c->h_tau_star_cap, static_cast<size_t>(n_queries), "filter threshold staging"))) return rc;
         bool used_bf16 = false;
         rc = enqueue_batch_tensor(e, c, d_queries, n_queries, k_eff, row_offset, d_out, c->d_ok, d_ids, c->stream, launches,
-                                  allow_bf16, &used_bf16);
+                                  allow_bf16, &used_bf16, c->d_tau_star);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_tau_star, c->d_tau_star, n_queries * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         std::vector<uint32_t> unproven;
         for (uint32_t qi = 0; qi < n_queries; ++qi) if (!c->h_ok[qi]) unproven.push_back(qi);
@@ -1053,31 +1129,38 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
             e->bf16_skip_batches = 16;
         }
         uint64_t retried = 0;
-        if (used_bf16 && e->tune.batch_retry && unproven.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1)) &&
-            batch_tensor_eligible(e, static_cast<uint32_t>(unproven.size()), k_eff)) {
-            // Second level: the queries the coarse bf16 bound could not prove go through the TF32 nominations
-            // (4x tighter bound) as one compacted sub-batch; only what is still unproven pays for an exact scan.
-            const uint32_t nf = static_cast<uint32_t>(unproven.size());
-            retried = nf;
-            if ((rc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "retry queries"))) return rc;
-            if ((rc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "retry results"))) return rc;
-            if ((rc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "retry flags"))) return rc;
-            for (uint32_t i = 0; i < nf; ++i)
-                CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
-                                         d_queries + static_cast<size_t>(unproven[i]) * e->dims, e->dims * sizeof(float),
-                                         cudaMemcpyDeviceToDevice, c->stream));
-            rc = enqueue_batch_tensor(e, c, c->d_retry_q, nf, k_eff, row_offset, c->d_retry_out, c->d_retry_ok, d_ids, c->stream,
-                                      launches, false, nullptr);
-            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-            for (uint32_t i = 0; i < nf; ++i)
-                CUDA_TRY(cudaMemcpyAsync(d_out + static_cast<size_t>(unproven[i]) * k_eff,
-                                         c->d_retry_out + static_cast<size_t>(i) * k_eff, k_eff * sizeof(wax_vs_candidate),
-                                         cudaMemcpyDeviceToDevice, c->stream));
-            CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-            CUDA_TRY(cudaStreamSynchronize(c->stream));
-            std::vector<uint32_t> still;
-            for (uint32_t i = 0; i < nf; ++i) if (!c->h_ok[i]) still.push_back(unproven[i]);
-            unproven.swap(still);
+        if (e->tune.batch_retry && unproven.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1))) {
+            // Level 2, the filter level: the unproven queries with a finite threshold, as one compacted sub-batch.
+            std::vector<uint32_t> sub, rest;
+            for (uint32_t qi : unproven) (std::isfinite(c->h_tau_star[qi]) ? sub : rest).push_back(qi);
+            const uint32_t nf = static_cast<uint32_t>(sub.size());
+            if (nf) {
+                retried = nf;
+                if ((rc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "filter-level queries"))) return rc;
+                if ((rc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "filter-level results"))) return rc;
+                if ((rc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "filter-level flags"))) return rc;
+                if ((rc = ensure_dev(&c->d_filter_tau, &c->filter_tau_cap, static_cast<size_t>(nf), "filter-level thresholds"))) return rc;
+                // compact on the host side of the pinned staging (h_tau_star is free again after the read above)
+                std::vector<float> taus(nf);
+                for (uint32_t i = 0; i < nf; ++i) taus[i] = c->h_tau_star[sub[i]];
+                memcpy(c->h_tau_star, taus.data(), nf * sizeof(float));
+                CUDA_TRY(cudaMemcpyAsync(c->d_filter_tau, c->h_tau_star, nf * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+                for (uint32_t i = 0; i < nf; ++i)
+                    CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
+                                             d_queries + static_cast<size_t>(sub[i]) * e->dims, e->dims * sizeof(float),
+                                             cudaMemcpyDeviceToDevice, c->stream));
+                rc = enqueue_filter_level(e, c, c->d_retry_q, c->d_filter_tau, nf, k_eff, row_offset, c->d_retry_out,
+                                          c->d_retry_ok, d_ids, c->stream, launches);
+                if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+                for (uint32_t i = 0; i < nf; ++i)
+                    CUDA_TRY(cudaMemcpyAsync(d_out + static_cast<size_t>(sub[i]) * k_eff,
+                                             c->d_retry_out + static_cast<size_t>(i) * k_eff, k_eff * sizeof(wax_vs_candidate),
+                                             cudaMemcpyDeviceToDevice, c->stream));
+                CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+                CUDA_TRY(cudaStreamSynchronize(c->stream));
+                for (uint32_t i = 0; i < nf; ++i) if (!c->h_ok[i]) rest.push_back(sub[i]);
+            }
+            unproven.swap(rest);
         }
         for (uint32_t qi : unproven) {
             rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
@@ -1635,6 +1718,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_ares")) e->tune.batch_ares = v;
     else if (!strcmp(key, "batch_rescore")) e->tune.batch_rescore = v;
     else if (!strcmp(key, "batch_retry")) e->tune.batch_retry = v;
+    else if (!strcmp(key, "filter_cap")) e->tune.filter_cap = v;
     else if (!strcmp(key, "single_shadow")) e->tune.single_shadow = v;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
