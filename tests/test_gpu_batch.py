@@ -303,3 +303,18 @@ def test_filter_level_answers_tight_clusters_without_exact_scans(oracle, metric,
     got2 = eng.search_batch(qs, 10)
     assert got2 == got
     assert eng.batch_stats()[1] - f1 >= 48
+
+
+def test_batch_larger_than_one_launch_of_query_groups(oracle):
+    """More than 148 query groups (148 x 128 = 18 944 queries): the batch is processed in several launches that
+    share the scratch (heaps, thresholds, converted queries) -- every slice of the batch must still be right."""
+    dims, n, b = 64, 5_000, 19_100
+    eng = _engine(oracle, VectorMetric.cosine, n, dims, seed=1300)
+    qs = oracle.synth_rows(1301, 0, b, dims, normalize=True)
+    ids, scores, ns = eng.search_batch_arrays(qs, 5)
+    assert eng.counter("batch_bf16_queries") == b and ns.tolist() == [5] * b
+    eng.set_option("batch_tensor", 0)
+    for qi in (0, 127, 128, 18_943, 18_944, 18_945, 19_099):
+        want = eng.search(qs[qi], 5)
+        assert [int(i) for i in ids[qi]] == [w[0] for w in want], qi
+        assert np.array_equal(scores[qi], np.float32([w[1] for w in want])), qi
