@@ -326,6 +326,13 @@ __global__ void __launch_bounds__(256) shadow_bf16_kernel(const float *__restric
         uint2 v;
         v.x = *reinterpret_cast<const uint32_t *>(&lo);
         v.y = *reinterpret_cast<const uint32_t *>(&hi);
+        // A finite fp32 within 2^-8 of FLT_MAX rounds to bf16 infinity: clamp it to the largest finite bf16 instead
+        // (relative error still <= 2^-8), so that rounding alone can never turn a finite row into inf / NaN scores.
+        auto clamp_half = [](uint32_t h, float src) -> uint32_t {   // h: one bf16 in the low 16 bits
+            return ((h & 0x7FFFu) == 0x7F80u && finite_f32(src)) ? ((h & 0x8000u) | 0x7F7Fu) : h;
+        };
+        v.x = clamp_half(v.x & 0xFFFFu, x.x) | (clamp_half(v.x >> 16, x.y) << 16);
+        v.y = clamp_half(v.y & 0xFFFFu, x.z) | (clamp_half(v.y >> 16, x.w) << 16);
         o[i] = v;
     }
 }
