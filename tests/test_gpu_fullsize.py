@@ -135,6 +135,14 @@ def test_single_rank_sharded_search_batch(oracle):
     ids, scores, ns = eng.search_batch_arrays(qs[:8], 10)
     assert ns.tolist() == [10] * 8 and [int(i) for i in ids[0]] == [g[0] for g in one_by_one[0]]   # frame ids unchanged
     assert np.array_equal(scores[0], np.float32([g[1] for g in one_by_one[0]]))
+    # pipelined form: two batches in flight on the worker thread, same answers
+    eng.row_lo, eng.row_hi = 0, 90_000
+    h1 = eng.search_batch_submit(qs[:70], 10)
+    h2 = eng.search_batch_submit(torch.from_numpy(qs[70:]).cuda(), 10)
+    i1, s1, n1 = eng.finish_batch(h1)
+    i2, s2, n2 = eng.finish_batch(h2)
+    got = [[(int(i), float(s)) for i, s in zip(ii, ss)] for ii, ss in zip(np.concatenate([i1, i2]), np.concatenate([s1, s2]))]
+    assert got == one_by_one and n1.tolist() == [10] * 70 and n2.tolist() == [10] * 70
     # k larger than the shard: padded by the scan path
     tiny = sharded.ShardedVectorEngine(VectorMetric.cosine, DIMS, total_rows=6)
     tiny.fill_synthetic(14)

@@ -257,6 +257,64 @@ class ShardedVectorEngine:
         scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
         return best["frame_id"].astype(np.uint64), scores, n_valid
 
+    # -- pipelined batches: the host merge of batch i overlaps the tensor-core pass of batch i+1 ----------------------
+    def search_batch_submit(self, queries, top_k: int):
+        """Start a batch on the engine's worker thread (ONE worker: batches, and therefore the all-gathers, are issued
+        in submission order on every rank) and return a future for finish_batch().  The worker does the shard's
+        tensor-core levels (a blocking C call that releases the GIL), the all-gather and the D2H copy; the caller is
+        free to merge the previous batch meanwhile.  Queries must stay alive until finish_batch()."""
+        if self._local_search is not None:
+            raise RuntimeError("search_batch_submit needs the CUDA engine (no injected local search)")
+        torch, dist = self._torch, self._dist
+        if getattr(self, "_worker", None) is None:
+            from concurrent.futures import ThreadPoolExecutor
+            self._worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="waxvs-shard")
+            self._batch_stream = torch.cuda.Stream(device=self.device)
+        k = clamp_topk(top_k)
+        if isinstance(queries, torch.Tensor):
+            d_qs = queries.to(self.device, dtype=torch.float32).contiguous().reshape(-1, self.dimensions)
+        else:
+            d_qs = torch.from_numpy(np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dimensions)).to(self.device)
+        ready = torch.cuda.Event()
+        ready.record()                                   # the queries were produced on the caller's stream
+        b = int(d_qs.shape[0])
+
+        def work():
+            from . import _lib as L
+            torch.cuda.set_device(self.device)
+            with torch.cuda.stream(self._batch_stream):
+                self._batch_stream.wait_event(ready)
+                local = torch.empty(b * k * 24, dtype=torch.uint8, device=self.device)
+                rc = L.lib().wax_vs_search_batch_device(self.engine.handle, C.c_void_p(d_qs.data_ptr()), b, k, self.row_lo,
+                                                        C.c_void_p(local.data_ptr()), C.c_void_p(self._batch_stream.cuda_stream))
+                if rc != 0:
+                    raise RuntimeError(f"wax_vs_search_batch_device rc={rc}: {L.last_error()}")
+                if self.world_size > 1:
+                    gathered = torch.empty(self.world_size * b * k * 24, dtype=torch.uint8, device=self.device)
+                    dist.all_gather_into_tensor(gathered, local, group=self.group)
+                else:
+                    gathered = local
+                host = torch.empty(gathered.numel(), dtype=torch.uint8, pin_memory=True)
+                host.copy_(gathered, non_blocking=True)
+                done = torch.cuda.Event()
+                done.record()
+            return host, done, gathered, d_qs            # keep the device buffers alive until the copy has finished
+
+        return (self._worker.submit(work), b, k)
+
+    def finish_batch(self, handle):
+        """Wait for a submitted batch and merge it: (ids [batch, k_eff], scores, n_valid) as search_batch_arrays."""
+        fut, b, k = handle
+        host, done, _gathered, _d_qs = fut.result()
+        done.synchronize()
+        k_eff = min(k, self.total_rows) if self.total_rows else k
+        if b == 0 or self.total_rows == 0:
+            return np.zeros((b, 0), np.uint64), np.zeros((b, 0), np.float32), np.zeros(b, np.uint32)
+        cands = host.numpy().view(CAND_DTYPE).reshape(self.world_size, b, k)
+        best, n_valid = merge_candidates_batch(cands, k_eff)
+        scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
+        return best["frame_id"].astype(np.uint64), scores, n_valid
+
     def search_batch(self, queries, top_k: int) -> List[List[Tuple[int, float]]]:
         ids, scores, ns = self.search_batch_arrays(queries, top_k)
         return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(ids.shape[0])]
