@@ -252,7 +252,10 @@ def run_single(args):
         "check": {"top1_frame_id": last[0][0] if last else None, "top1_score": last[0][1] if last else None},
     }
     if not args.no_shadow and not small:
-        line["shadow_filtered"] = shadow_filtered_arm(eng, args, qs, n_distinct)
+        try:                        # an extra measurement must never cost the headline line
+            line["shadow_filtered"] = shadow_filtered_arm(eng, args, qs, n_distinct)
+        except Exception as ex:     # noqa: BLE001
+            line["shadow_filtered"] = {"error": repr(ex)}
     if not args.no_cpu_baseline:
         base = cpu_reference_arm(args.rows, steps=5, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
