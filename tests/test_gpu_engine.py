@@ -252,3 +252,24 @@ def test_cpp_mirror_runs_the_reference_tests_on_the_gpu(tmp_path):
                     "-lwaxvs_cuda", f"-Wl,-rpath,{lib.parent}", "-o", str(exe)], check=True, capture_output=True)
     out = subprocess.run([str(exe)], capture_output=True, text=True)
     assert out.returncode == 0 and "cpp mirror ok" in out.stdout, (out.returncode, out.stdout, out.stderr)
+
+
+def test_engines_on_two_devices_in_one_process(oracle):
+    """`wax_vs_create(devices=[d])`: opt-in shared-memory limits (cudaFuncSetAttribute) are per device, so every
+    kernel family must work on a second device of the same process (skipped on single-GPU boxes)."""
+    import ctypes as C
+    from wax_b200 import _lib as L
+    n = C.c_int32(0)
+    assert L.lib().wax_vs_device_count(C.byref(n)) == 0
+    if n.value < 2:
+        pytest.skip("needs two GPUs")
+    dims, rows = 384, 30_000
+    qs = oracle.synth_rows(71, 0, 130, dims)
+    results = []
+    for dev in (0, 1):
+        eng = CUDAVectorEngine(VectorMetric.cosine, dims, device=dev)
+        eng.fill_synthetic(70, rows)
+        results.append((eng.search(qs[0], 10), eng.search(qs[0], 300), eng.search_batch(qs, 10),
+                        eng.search_filtered(qs[0], 5, allow=list(range(0, rows, 7)))))
+        eng.close()
+    assert results[0] == results[1]

@@ -202,6 +202,8 @@ struct wax_vs_engine {
     // Adaptive level choice: when more than a quarter of a batch fails the coarse bf16 bound (tightly clustered
     // neighbours), the next 16 batches nominate in TF32 straight away, then bf16 is probed again.
     uint32_t bf16_skip_batches = 0;
+    std::mutex attr_mu;            // cudaFuncSetAttribute bookkeeping (per engine = per device)
+    bool sort_attr_set = false, gather_attr_set = false, batch_attr_set = false;
 };
 
 // ---------------------------------------------------------------------------------------------------------
@@ -455,10 +457,12 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         select_compact_kernel<<<sgrid, 512, 0, stream>>>(c->d_dist_keys, n, c->d_select, c->d_sel_keys, 16384);
         uint32_t pow2 = 64;
         while (pow2 < k_eff) pow2 <<= 1;
-        static bool sort_attr = false;
-        if (!sort_attr) {
-            CUDA_TRY(cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
-            sort_attr = true;
+        {   // opt-in shared-memory limits are per function AND per device: once per engine, not once per process
+            std::lock_guard<std::mutex> ag(e->attr_mu);
+            if (!e->sort_attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(select_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+                e->sort_attr_set = true;
+            }
         }
         select_sort_kernel<<<1, 1024, pow2 * sizeof(uint64_t), stream>>>(c->d_select, c->d_sel_keys, pow2, p);
         CUDA_TRY(cudaGetLastError());
@@ -605,9 +609,10 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
     }
     if (used_bf16) *used_bf16 = bf16;
     const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
+    cudaError_t attr_err = cudaSuccess;
+    {   // per function and per DEVICE: once per engine
+        std::lock_guard<std::mutex> ag(e->attr_mu);
+        if (!e->batch_attr_set) {
         auto chk = [&](cudaError_t r) { if (attr_err == cudaSuccess) attr_err = r; };
         chk(set_smem_attr(batch_nominate_kernel<4, 16, false>, batch_smem_bytes(4, 16)));
         chk(set_smem_attr(batch_nominate_kernel<3, 64, false>, batch_smem_bytes(3, 64)));
@@ -630,7 +635,9 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         chk(set_smem_attr(filter_select_kernel, 16384 * 8));
         chk(set_smem_attr(batch_finish_kernel<kCosine>, (16384 + kBatchRescoreMax) * 8));
         chk(set_smem_attr(batch_finish_kernel<kDot>, (16384 + kBatchRescoreMax) * 8));
-    });
+        e->batch_attr_set = attr_err == cudaSuccess;
+        }
+    }
     if (attr_err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
 
     // bf16 nominations: convert the queries once per call (n_queries x dims, tiny next to the corpus pass)
@@ -1401,10 +1408,13 @@ int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t qu
         CUDA_TRY(cudaGetLastError());
         uint32_t pow2 = 64;
         while (pow2 < n) pow2 <<= 1;
-        static std::once_flag once;
-        static cudaError_t attr = cudaSuccess;
-        std::call_once(once, [] { attr = cudaFuncSetAttribute(gather_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8); });
-        if (attr != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr));
+        {
+            std::lock_guard<std::mutex> ag(e->attr_mu);
+            if (!e->gather_attr_set) {
+                CUDA_TRY(cudaFuncSetAttribute(gather_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 8));
+                e->gather_attr_set = true;
+            }
+        }
         ScanParams sp{};
         sp.k = k_eff; sp.out = c->d_out; sp.id_base = e->id_base;
         gather_sort_kernel<<<1, 1024, pow2 * sizeof(uint64_t), c->stream>>>(c->d_gather_keys, n, pow2, sp);
