@@ -54,6 +54,21 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def __enter__(self):
+        # NVML in-process first (a sample every 5 ms: the default timed region is only ~100 ms long), the
+        # nvidia-smi loop of the recipe as the fallback.
+        self.nvml = None
+        self.stop = threading.Event()
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            handle = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+            pynvml.nvmlDeviceGetClockInfo(handle, pynvml.NVML_CLOCK_SM)
+            self.nvml = (pynvml, handle)
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -64,11 +79,36 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll_nvml(self):
+        nv, h = self.nvml
+        bits = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
+        try:
+            mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            mx = 0
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            getattr(nv, "nvmlDeviceGetCurrentClocksThrottleReasons", None)
+        while not self.stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                mask = int(get_reasons(h)) if get_reasons else 0
+                self.rows.append([str(sm), str(mx)] + ["Active" if mask & b else "Not Active" for _, b in bits])
+            except Exception:
+                pass
+            self.stop.wait(0.005)
+
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append([x.strip() for x in line.split(",")])
 
     def __exit__(self, *exc):
+        self.stop.set()
+        if self.nvml:
+            try:
+                self.thread.join(timeout=1)
+                self.nvml[0].nvmlShutdown()
+            except Exception:
+                pass
         if self.proc:
             self.proc.terminate()
             try:
@@ -89,7 +129,7 @@ class ClockSampler:
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if getattr(self, "nvml", None) else "nvidia-smi"}
 
 
 def host_queries(n: int) -> np.ndarray:
