@@ -296,10 +296,44 @@ def run_single(args):
             line["shadow_filtered"] = shadow_filtered_arm(eng, args, qs, n_distinct)
         except Exception as ex:     # noqa: BLE001
             line["shadow_filtered"] = {"error": repr(ex)}
+    if not args.no_shadow and not small:
+        try:                        # BASELINE configs[2] on the same resident corpus: the tensor-bound companion number
+            line["batched"] = batched_arm(eng, args)
+        except Exception as ex:     # noqa: BLE001
+            line["batched"] = {"error": repr(ex)}
     if not args.no_cpu_baseline:
         base = cpu_reference_arm(args.rows, steps=5, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
     print(json.dumps(line), flush=True)
+
+
+def batched_arm(eng, args, batch: int = 1024, steps: int = 10):
+    """NOT the headline: BASELINE configs[2] (batch of 1024 queries, top-10 cosine) on the corpus already resident for
+    the headline -- tcgen05 nominations over the bf16 shadow + exact fp32 re-score + completeness proof,
+    results identical to 1024 single-query scans.  Device-only, CUDA events inside the library; the full companion
+    (end to end, configs[4], TF32) is scripts/bench_batch.py."""
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:  # noqa: BLE001
+        pass
+    ms, launches, unproven = eng.time_search_batch(batch, TOP_K, steps, warmup=2, seed=QUERY_SEED)
+    per = ms / steps
+    flops = 2.0 * batch * args.rows * DIMS
+    tf = flops / (per * 1e-3) / 1e12
+    bf16 = eng.counter("shadow_bytes") > 0
+    peak = float(peaks.get("bf16_tflops", 2250.0)) if bf16 else 1100.0
+    return {
+        "workload": f"{args.rows} x {DIMS} fp32 corpus (BASELINE configs[2]), batch {batch}, top-{TOP_K} cosine",
+        "value": batch / per * 1e3, "unit": "queries/s", "ms_per_step": per, "steps": steps,
+        "dtype": ("bf16" if bf16 else "tf32") + " nominations + f32 exact re-score",
+        "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
+                     "peak_source": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if bf16 and "bf16_tflops" in peaks
+                     else ("nominal dense bf16" if bf16 else "nominal dense TF32"),
+                     "frac_of_sustained": tf / float(peaks["bf16_tflops_sustained"]) if bf16 and "bf16_tflops_sustained" in peaks else None,
+                     "useful_flops_per_launch": flops},
+        "gpu_launches_per_step": launches / steps, "unproven_queries_last_step": unproven,
+    }
 
 
 def shadow_filtered_arm(eng, args, qs, n_distinct):
