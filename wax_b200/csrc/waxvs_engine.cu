@@ -594,8 +594,9 @@ static int ares_stages(bool pair, int heap, uint32_t num_kb, int want) {
 }
 
 // Enqueue the tensor-core nomination + exact finish for n_queries device-resident queries.  d_ok[i] = 1 when
-// query i's result is proven exact; the caller re-runs the others (TF32 retry, then enqueue_search).
-// allow_bf16 = false forces the TF32 nominations (the retry level).  *used_bf16 reports what ran.
+// query i's result is proven exact; the caller sends the others to the filter level, then to enqueue_search.
+// allow_bf16 = false forces TF32 nominations (adaptive level choice).  *used_bf16 reports what ran; d_tau_star
+// (optional) receives each query's threshold for the filter level.
 static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
                                     uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, uint32_t *d_ok,
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
@@ -613,29 +614,29 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
     {   // per function and per DEVICE: once per engine
         std::lock_guard<std::mutex> ag(e->attr_mu);
         if (!e->batch_attr_set) {
-        auto chk = [&](cudaError_t r) { if (attr_err == cudaSuccess) attr_err = r; };
-        chk(set_smem_attr(batch_nominate_kernel<4, 16, false>, batch_smem_bytes(4, 16)));
-        chk(set_smem_attr(batch_nominate_kernel<3, 64, false>, batch_smem_bytes(3, 64)));
-        chk(set_smem_attr(batch_nominate_kernel<6, 16, true>, batch_smem_bytes(6, 16, true)));
-        chk(set_smem_attr(batch_nominate_kernel<4, 64, true>, batch_smem_bytes(4, 64, true)));
-        chk(set_smem_attr(batch_nominate_kernel<4, 16, false, true>, batch_smem_bytes(4, 16)));
-        chk(set_smem_attr(batch_nominate_kernel<3, 64, false, true>, batch_smem_bytes(3, 64)));
-        chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true>, batch_smem_bytes(6, 16, true)));
-        chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true>, batch_smem_bytes(4, 64, true)));
-        // ARES shapes: the ring depth is chosen at run time (<= the template's STAGES is what the kernel uses)
-        chk(set_smem_attr(batch_nominate_kernel<3, 16, false, true, true>, 227u * 1024u));
-        chk(set_smem_attr(batch_nominate_kernel<2, 16, false, true, true>, 227u * 1024u));
-        chk(set_smem_attr(batch_nominate_kernel<2, 64, false, true, true>, 227u * 1024u));
-        chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true, true>, 227u * 1024u));
-        chk(set_smem_attr(batch_nominate_kernel<4, 16, true, true, true>, 227u * 1024u));
-        chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true, true>, 227u * 1024u));
-        chk(set_smem_attr(batch_tf32_ts_kernel<16>, batch_ts_smem_bytes(16)));
-        chk(set_smem_attr(batch_tf32_ts_kernel<64>, batch_ts_smem_bytes(64)));
-        chk(set_smem_attr(batch_nominate_kernel<4, 16, false, false, false, true>, batch_smem_bytes(4, 16)));
-        chk(set_smem_attr(filter_select_kernel, 16384 * 8));
-        chk(set_smem_attr(batch_finish_kernel<kCosine>, (16384 + kBatchRescoreMax) * 8));
-        chk(set_smem_attr(batch_finish_kernel<kDot>, (16384 + kBatchRescoreMax) * 8));
-        e->batch_attr_set = attr_err == cudaSuccess;
+            auto chk = [&](cudaError_t r) { if (attr_err == cudaSuccess) attr_err = r; };
+            chk(set_smem_attr(batch_nominate_kernel<4, 16, false>, batch_smem_bytes(4, 16)));
+            chk(set_smem_attr(batch_nominate_kernel<3, 64, false>, batch_smem_bytes(3, 64)));
+            chk(set_smem_attr(batch_nominate_kernel<6, 16, true>, batch_smem_bytes(6, 16, true)));
+            chk(set_smem_attr(batch_nominate_kernel<4, 64, true>, batch_smem_bytes(4, 64, true)));
+            chk(set_smem_attr(batch_nominate_kernel<4, 16, false, true>, batch_smem_bytes(4, 16)));
+            chk(set_smem_attr(batch_nominate_kernel<3, 64, false, true>, batch_smem_bytes(3, 64)));
+            chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true>, batch_smem_bytes(6, 16, true)));
+            chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true>, batch_smem_bytes(4, 64, true)));
+            // ARES shapes: the ring depth is chosen at run time (<= the template's STAGES is what the kernel uses)
+            chk(set_smem_attr(batch_nominate_kernel<3, 16, false, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<2, 16, false, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<2, 64, false, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<4, 16, true, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_tf32_ts_kernel<16>, batch_ts_smem_bytes(16)));
+            chk(set_smem_attr(batch_tf32_ts_kernel<64>, batch_ts_smem_bytes(64)));
+            chk(set_smem_attr(batch_nominate_kernel<4, 16, false, false, false, true>, batch_smem_bytes(4, 16)));
+            chk(set_smem_attr(filter_select_kernel, 16384 * 8));
+            chk(set_smem_attr(batch_finish_kernel<kCosine>, (16384 + kBatchRescoreMax) * 8));
+            chk(set_smem_attr(batch_finish_kernel<kDot>, (16384 + kBatchRescoreMax) * 8));
+            e->batch_attr_set = attr_err == cudaSuccess;
         }
     }
     if (attr_err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(attr_err));
