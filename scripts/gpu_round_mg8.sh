@@ -4,7 +4,7 @@ set -u
 mkdir -p gpurun_out; OUT=gpurun_out
 nvidia-smi -L | head -8
 run() { N=$1; shift; python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 "$@" 2>&1 | grep -v -i "warn\|OMP_NUM\|\*\*\*\*"; }
-echo "== sharded parity N=8"; timeout 600 bash -c "$(declare -f run); run 8 scripts/check_sharded.py" | tail -6 | tee $OUT/sharded_parity_n8.txt
+echo "== sharded parity N=8"; timeout 600 bash -c "$(declare -f run); run 8 tests/check_sharded_torchrun.py" | tail -6 | tee $OUT/sharded_parity_n8.txt
 echo "== bench N=8 (10M strong)"; timeout 600 bash -c "$(declare -f run); run 8 bench.py --gpus 8 --steps 1000 --warmup 50" | grep '^{' | tail -1 | tee $OUT/bench_n8.json | cut -c1-400
 echo "== bench N=8 depth 4"; timeout 600 bash -c "$(declare -f run); run 8 bench.py --gpus 8 --steps 1000 --warmup 50 --pipeline 4" | grep '^{' | tail -1 | tee $OUT/bench_n8_depth4.json | cut -c1-300
 echo "== bench N=8 depth 1"; timeout 600 bash -c "$(declare -f run); run 8 bench.py --gpus 8 --steps 1000 --warmup 50 --pipeline 1" | grep '^{' | tail -1 | tee $OUT/bench_n8_depth1.json | cut -c1-300

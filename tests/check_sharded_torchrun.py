@@ -1,4 +1,5 @@
-"""Multi-GPU parity check (run under torchrun, one rank per GPU, NCCL): the row-sharded search must return exactly
+"""Multi-GPU parity check (run under torchrun, one rank per GPU, NCCL; lives under tests/ because it uses the oracle
+as the checker -- not collected by pytest): the row-sharded search must return exactly
 what a single exact scan of the whole corpus returns (bit-exact against the streaming oracle)."""
 import os
 import sys

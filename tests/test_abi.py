@@ -86,6 +86,12 @@ def test_product_package_never_touches_the_oracle():
             for line in path.read_text().splitlines():
                 if line.lstrip().startswith("#include"):
                     assert "oracle" not in line, (path, line)
+    # helper scripts are not test infrastructure either: only tests/, __graft_entry__.smoke() and bench.py's CPU legs
+    for path in (ROOT / "scripts").glob("*.py"):
+        for line in path.read_text().splitlines():
+            code = line.split("#", 1)[0]
+            assert not re.search(r"^\s*(from|import)\s+oracle\b", code), (path, line)
+            assert "libwax_oracle" not in code, (path, line)
     needed = subprocess.run(["readelf", "-d", str(build.build())], capture_output=True, text=True).stdout
     assert "oracle" not in needed
     undefined = subprocess.run(["nm", "-D", "--undefined-only", str(build.build())], capture_output=True, text=True).stdout
