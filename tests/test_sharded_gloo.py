@@ -51,6 +51,12 @@ def _worker(rank, world, port, total, dims, k, seed, q, out_dir):
         ids, scores, ns = eng.search_batch_arrays(qs, k)
         assert ids.shape == (3, min(k, total)) and ns.tolist() == [len(b) for b in batch]
         np.save(Path(out_dir) / f"b{rank}.npy", np.array(batch[1], dtype=np.float64))
+        # pipelined form: three batches of different sizes in flight on the worker thread -- the all-gathers must
+        # line up across the ranks (submission order), and each batch must come back as the synchronous call has it
+        handles = [eng.search_batch_submit(qs[:n], k) for n in (3, 1, 2)]
+        for n, h in zip((3, 1, 2), handles):
+            ids2, scores2, ns2 = eng.finish_batch(h)
+            assert np.array_equal(ids2, ids[:n]) and np.array_equal(scores2, scores[:n]) and ns2.tolist() == ns[:n].tolist()
     finally:
         dist.destroy_process_group()
 

@@ -263,14 +263,31 @@ class ShardedVectorEngine:
         in submission order on every rank) and return a future for finish_batch().  The worker does the shard's
         tensor-core levels (a blocking C call that releases the GIL), the all-gather and the D2H copy; the caller is
         free to merge the previous batch meanwhile.  Queries must stay alive until finish_batch()."""
-        if self._local_search is not None:
-            raise RuntimeError("search_batch_submit needs the CUDA engine (no injected local search)")
         torch, dist = self._torch, self._dist
         if getattr(self, "_worker", None) is None:
             from concurrent.futures import ThreadPoolExecutor
             self._worker = ThreadPoolExecutor(max_workers=1, thread_name_prefix="waxvs-shard")
-            self._batch_stream = torch.cuda.Stream(device=self.device)
+            self._batch_stream = torch.cuda.Stream(device=self.device) if self._local_search is None else None
         k = clamp_topk(top_k)
+        if self._local_search is not None:
+            # CPU (gloo) form used by the tests of the host logic: the injected local search stands in for the GPU
+            # step; the worker thread, the submission-ordered all-gathers and the merge are the production ones.
+            qs = np.ascontiguousarray(queries, dtype=np.float32).reshape(-1, self.dimensions).copy()
+            b = qs.shape[0]
+
+            def work_cpu():
+                local_np = np.zeros((b, k), CAND_DTYPE)
+                for i in range(b):
+                    local_np[i] = np.ascontiguousarray(self._local_search(qs[i], k), dtype=CAND_DTYPE)
+                local = torch.from_numpy(local_np.view(np.uint8).reshape(-1).copy())
+                if self.world_size > 1:
+                    gathered = torch.empty(self.world_size * b * k * 24, dtype=torch.uint8)
+                    dist.all_gather_into_tensor(gathered, local, group=self.group)
+                else:
+                    gathered = local
+                return gathered, None, None, None
+
+            return (self._worker.submit(work_cpu), b, k)
         if isinstance(queries, torch.Tensor):
             d_qs = queries.to(self.device, dtype=torch.float32).contiguous().reshape(-1, self.dimensions)
         else:
@@ -306,7 +323,8 @@ class ShardedVectorEngine:
         """Wait for a submitted batch and merge it: (ids [batch, k_eff], scores, n_valid) as search_batch_arrays."""
         fut, b, k = handle
         host, done, _gathered, _d_qs = fut.result()
-        done.synchronize()
+        if done is not None:
+            done.synchronize()
         k_eff = min(k, self.total_rows) if self.total_rows else k
         if b == 0 or self.total_rows == 0:
             return np.zeros((b, 0), np.uint64), np.zeros((b, 0), np.float32), np.zeros(b, np.uint32)
