@@ -57,6 +57,48 @@ int main() {
         auto hits = engine.search({1, 2, 3}, 5);
         EXPECT(hits.size() == 1 && std::fabs(hits[0].second - (14.0f - 1.0f)) < 1e-5f);   // dot score = q.v - 1
     }
+    {   // searchBatch == one search per query (130 queries x 64 dims: the tensor-core levels), reserve, streaming add
+        CUDAVectorEngine engine(VectorMetric::cosine, 64);
+        engine.reserve(3000);
+        std::vector<uint64_t> ids;
+        std::vector<std::vector<float>> rows;
+        uint32_t state = 12345u;
+        auto rnd = [&]() { state = state * 1664525u + 1013904223u; return static_cast<float>(state >> 8) / 8388608.0f - 1.0f; };
+        for (uint64_t i = 0; i < 3000; ++i) {
+            std::vector<float> v(64);
+            for (auto &x : v) x = rnd();
+            ids.push_back(1000 + i);
+            rows.push_back(v);
+        }
+        engine.addBatchStreaming(ids, rows, 700);
+        EXPECT(engine.count() == 3000);
+        std::vector<std::vector<float>> qs(rows.begin() + 5, rows.begin() + 135);
+        auto batch = engine.searchBatch(qs, 10);
+        EXPECT(batch.size() == 130);
+        for (size_t q : {size_t(0), size_t(64), size_t(129)}) {
+            auto one = engine.search(qs[q], 10);
+            EXPECT(batch[q].size() == 10 && one.size() == 10 && batch[q][0].first == 1005 + q);
+            for (size_t i = 0; i < 10; ++i) EXPECT(batch[q][i].first == one[i].first && batch[q][i].second == one[i].second);
+        }
+        // filter pushed below the top-k (UnifiedSearchTests.swift:133-158: allow-list {id2, id3} with topK 2)
+        auto allowed = engine.searchFiltered(qs[0], 2, {1002, 1003}, true);
+        EXPECT(allowed.size() == 2 && (allowed[0].first == 1002 || allowed[0].first == 1003));
+        auto denied = engine.searchFiltered(qs[0], 3, {1005}, false);
+        EXPECT(denied.size() == 3 && !contains(denied, 1005));
+    }
+    {   // load(from:): committed blob + pending embeddings replayed as upserts (MetalVectorEngine.swift:318-328)
+        CUDAVectorEngine src(VectorMetric::cosine, 4);
+        src.addBatch({0, 1, 2}, {{1, 0, 0, 0}, {0, 1, 0, 0}, {0, 0, 1, 0}});
+        auto blob = src.serialize();
+        CUDAVectorEngine *loaded = CUDAVectorEngine::load(&blob, {3, 1, 3}, {{0, 0, 0, 1}, {0.6f, 0.8f, 0, 0}, {0, 0, 0.6f, 0.8f}},
+                                                          VectorMetric::cosine, 4);
+        EXPECT(loaded->count() == 4);
+        EXPECT(loaded->search({0, 0, 0.6f, 0.8f}, 1)[0].first == 3 && loaded->search({0.6f, 0.8f, 0, 0}, 1)[0].first == 1);
+        delete loaded;
+        CUDAVectorEngine *empty = CUDAVectorEngine::load(nullptr, {}, {}, VectorMetric::cosine, 4);
+        EXPECT(empty->count() == 0 && empty->search({1, 0, 0, 0}, 3).empty());
+        delete empty;
+    }
     std::printf("cpp mirror ok\n");
     return 0;
 }

@@ -66,7 +66,79 @@ public:
         }
         check(wax_vs_add_batch(h_, frameIds.data(), flat.data(), frameIds.size(), dimensions_));
     }
+    // addBatchStreaming (MetalVectorEngine.swift:404-421): chunks of `chunkSize` through addBatch.
+    void addBatchStreaming(const std::vector<uint64_t> &frameIds, const std::vector<std::vector<float>> &vectors,
+                           size_t chunkSize = 256) {
+        if (frameIds.empty()) return;
+        if (frameIds.size() != vectors.size()) throw EncodingError("addBatchStreaming: frameIds.count != vectors.count");
+        if (chunkSize == 0) chunkSize = 256;
+        for (size_t lo = 0; lo < frameIds.size(); lo += chunkSize) {
+            const size_t hi = lo + chunkSize < frameIds.size() ? lo + chunkSize : frameIds.size();
+            addBatch(std::vector<uint64_t>(frameIds.begin() + lo, frameIds.begin() + hi),
+                     std::vector<std::vector<float>>(vectors.begin() + lo, vectors.begin() + hi));
+        }
+    }
+    void reserve(uint64_t rows) { check(wax_vs_reserve(h_, rows)); }   // reserveIfNeeded (:857-871)
     void remove(uint64_t frameId) { check(wax_vs_remove(h_, frameId)); }
+
+    // A batch of independent queries (no reference counterpart: VectorSearchEngine.swift:13 takes one vector).  Eligible
+    // batches take the tensor-core levels; the results are identical to one search() per query.
+    std::vector<std::vector<Hit>> searchBatch(const std::vector<std::vector<float>> &vectors, int64_t topK) const {
+        std::vector<std::vector<Hit>> out(vectors.size());
+        if (vectors.empty()) return out;
+        std::vector<float> flat;
+        flat.reserve(vectors.size() * dimensions_);
+        for (const auto &v : vectors) {
+            if (v.size() != dimensions_)
+                throw EncodingError("vector dimension mismatch: expected " + std::to_string(dimensions_) + ", got " +
+                                    std::to_string(v.size()));
+            flat.insert(flat.end(), v.begin(), v.end());
+        }
+        const int64_t lim = topK < 1 ? 1 : (topK > WAX_VS_MAX_RESULTS ? WAX_VS_MAX_RESULTS : topK);
+        const uint64_t rows = count();
+        const uint32_t stride = static_cast<uint32_t>(rows < static_cast<uint64_t>(lim) ? (rows ? rows : 1) : lim);
+        std::vector<uint64_t> ids(vectors.size() * stride);
+        std::vector<float> scores(vectors.size() * stride);
+        std::vector<uint32_t> ns(vectors.size());
+        check(wax_vs_search_batch(h_, flat.data(), static_cast<uint32_t>(vectors.size()), dimensions_, topK, ids.data(),
+                                  scores.data(), stride, ns.data()));
+        for (size_t q = 0; q < vectors.size(); ++q) {
+            out[q].resize(ns[q]);
+            for (uint32_t i = 0; i < ns[q]; ++i) out[q][i] = {ids[q * stride + i], scores[q * stride + i]};
+        }
+        return out;
+    }
+
+    // The frame filter of UnifiedSearch (UnifiedSearch.swift:58,1195-1200,1241-1258) pushed below the top-k:
+    // allow == true: only the listed frameIds may be returned; false: they are excluded (deleted / superseded frames).
+    std::vector<Hit> searchFiltered(const std::vector<float> &vector, int64_t topK, const std::vector<uint64_t> &frameIds,
+                                    bool allow) const {
+        const int64_t lim = topK < 1 ? 1 : (topK > WAX_VS_MAX_RESULTS ? WAX_VS_MAX_RESULTS : topK);
+        std::vector<uint64_t> ids(static_cast<size_t>(lim));
+        std::vector<float> scores(static_cast<size_t>(lim));
+        uint32_t n = 0;
+        check(wax_vs_search_filtered(h_, vector.data(), static_cast<uint32_t>(vector.size()), topK, frameIds.data(),
+                                     frameIds.size(), allow ? 0 : 1, ids.data(), scores.data(), static_cast<uint32_t>(lim), &n));
+        std::vector<Hit> out(n);
+        for (uint32_t i = 0; i < n; ++i) out[i] = {ids[i], scores[i]};
+        return out;
+    }
+
+    // static load(from:metric:dimensions:) (MetalVectorEngine.swift:318-328): the committed blob (may be empty = none
+    // committed yet), then the pending embedding mutations as ONE upsert batch (sequential semantics in the library).
+    static CUDAVectorEngine *load(const std::vector<uint8_t> *committedBlob, const std::vector<uint64_t> &pendingIds,
+                                  const std::vector<std::vector<float>> &pendingVectors, VectorMetric metric,
+                                  uint32_t dimensions) {
+        auto *engine = new CUDAVectorEngine(metric, dimensions);
+        try {
+            if (committedBlob) engine->deserialize(*committedBlob);
+            engine->addBatch(pendingIds, pendingVectors);
+        } catch (...) {
+            delete engine;
+            throw;
+        }
+        return engine;
+    }
     std::vector<uint8_t> serialize() const {
         uint64_t len = 0;
         check(wax_vs_serialized_length(h_, &len));
