@@ -140,7 +140,10 @@ int32_t wax_vs_search_filtered(wax_vs_engine *engine, const float *query, uint32
    `d_candidates` (n_queries x k_eff entries, k_eff = min(clamp(top_k), 10000) -- NOT clipped to N, padding
    has valid = 0) are DEVICE pointers on the engine's device; the work is enqueued on `cuda_stream`
    (a cudaStream_t; NULL = legacy default stream) and the call returns without synchronising.
-   candidate.row = row_offset + local row. */
+   candidate.row = row_offset + local row.
+   Ordering against mutators: the library remembers that device-path work was enqueued and every mutator
+   (add / remove / reserve / deserialize / fill) drains the DEVICE (cudaDeviceSynchronize) under its write lock
+   before it touches the corpus, so an in-flight scan never reads rows that are being moved. */
 int32_t wax_vs_search_device(wax_vs_engine *engine, const float *d_queries, uint32_t n_queries,
                              int64_t top_k, uint64_t row_offset, wax_vs_candidate *d_candidates,
                              void *cuda_stream);
@@ -196,7 +199,8 @@ int32_t wax_vs_debug_batch_stats(wax_vs_engine *engine, uint64_t *tensor_queries
 
 /* Named instrumentation counters: "batch_tensor_queries", "batch_fallback_queries", "batch_bf16_queries" (queries
    nominated from the bf16 shadow), "batch_retry_queries" (bf16-unproven queries retried on the TF32 nominations),
-   "shadow_bytes" (HBM held by the bf16 shadow), "pool_allocs", "pool_reuses". */
+   "shadow_bytes" (HBM held by the bf16 shadow), "shadow_unavailable" (1 = the shadow did not fit in HBM, batches
+   nominate in TF32 at about half the rate), "batch_tf32_queries", "pool_allocs", "pool_reuses". */
 int32_t wax_vs_debug_counter(wax_vs_engine *engine, const char *name, uint64_t *out);
 
 /* Device-only timing of the batched path (n_queries synthetic unit queries per step, everything resident):

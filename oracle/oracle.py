@@ -61,6 +61,13 @@ def lib() -> C.CDLL:
         L.wax_oracle_search_synth.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
                                               C.c_uint32, C.c_int, f32p, C.c_int64, C.c_int, u64p, f32p,
                                               f32p, u32p]
+        L.wax_oracle_search_multi.restype = C.c_int
+        L.wax_oracle_search_multi.argtypes = [C.c_int, C.c_int, f32p, C.c_uint64, C.c_uint32, f32p, C.c_uint32,
+                                              C.c_int64, C.c_uint64, C.c_int, u64p, f32p, f32p, u32p]
+        L.wax_oracle_search_synth_multi.restype = C.c_int
+        L.wax_oracle_search_synth_multi.argtypes = [C.c_int, C.c_int, C.c_uint64, C.c_uint64, C.c_uint64,
+                                                    C.c_uint32, C.c_int, f32p, C.c_uint32, C.c_int64, C.c_int,
+                                                    u64p, f32p, f32p, u32p]
         L.wax_oracle_metal_cpu_topk.restype = C.c_uint32
         L.wax_oracle_metal_cpu_topk.argtypes = [f32p, C.c_uint64, C.c_uint32, u64p, f32p]
         L.wax_oracle_synth_row.restype = None
@@ -167,6 +174,41 @@ def search_synth(metric: int, seed: int, first_row: int, n_rows: int, dims: int,
     if rc != 0:
         raise RuntimeError(f"wax_oracle_search_synth rc={rc}")
     return rows[: n.value].copy(), d[: n.value].copy(), s[: n.value].copy()
+
+
+def search_multi(metric: int, corpus, queries, top_k: int, mode: int = ACC_F32_SEQ, row_base: int = 0,
+                 threads: int = 1):
+    """Exact scan for several queries in one pass.  Returns (rows u64[B,k], distances f32[B,k], scores f32[B,k],
+    counts u32[B])."""
+    corpus, queries = _f32(corpus), _f32(queries)
+    n_rows, dims = corpus.shape
+    queries = queries.reshape(-1, dims)
+    b = queries.shape[0]
+    cap = max(1, min(clamp_topk(top_k), max(n_rows, 1)))
+    rows = np.zeros((b, cap), np.uint64); d = np.zeros((b, cap), np.float32); s = np.zeros((b, cap), np.float32)
+    n = np.zeros(b, np.uint32)
+    rc = lib().wax_oracle_search_multi(metric, mode, _p(corpus, C.c_float), n_rows, dims, _p(queries, C.c_float), b,
+                                       int(top_k), row_base, threads, _p(rows, C.c_uint64), _p(d, C.c_float),
+                                       _p(s, C.c_float), _p(n, C.c_uint32))
+    if rc != 0:
+        raise RuntimeError(f"wax_oracle_search_multi rc={rc}")
+    return rows, d, s, n
+
+
+def search_synth_multi(metric: int, seed: int, first_row: int, n_rows: int, dims: int, normalize: bool, queries,
+                       top_k: int, mode: int = ACC_F32_SEQ, threads: int = 1):
+    """search_synth for several queries: each synthetic row is generated once and scored against all of them."""
+    queries = _f32(queries).reshape(-1, dims)
+    b = queries.shape[0]
+    cap = max(1, min(clamp_topk(top_k), max(n_rows, 1)))
+    rows = np.zeros((b, cap), np.uint64); d = np.zeros((b, cap), np.float32); s = np.zeros((b, cap), np.float32)
+    n = np.zeros(b, np.uint32)
+    rc = lib().wax_oracle_search_synth_multi(metric, mode, seed, first_row, n_rows, dims, int(normalize),
+                                             _p(queries, C.c_float), b, int(top_k), threads, _p(rows, C.c_uint64),
+                                             _p(d, C.c_float), _p(s, C.c_float), _p(n, C.c_uint32))
+    if rc != 0:
+        raise RuntimeError(f"wax_oracle_search_synth_multi rc={rc}")
+    return rows, d, s, n
 
 
 def metal_cpu_topk(distances, k: int):

@@ -365,6 +365,102 @@ int wax_oracle_search_synth(int metric, int mode, uint64_t seed, uint64_t first_
                        threads, out_rows, out_distances, out_scores, out_n);
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* Multi-query scan: every row (generated once when the corpus is synthetic) is scored against all  */
+/* n_queries queries; one heap per (thread, query).  Same arithmetic and total order as scan_common */
+/* -- it exists so that full-size batched parity tests pay the row generator once, not per query.   */
+typedef struct {
+    const query_ctx *qcs; uint32_t n_queries;
+    const float *corpus; uint64_t seed; int normalize;
+    uint64_t lo, hi, row_base;
+    topk_heap *heaps;               /* [n_queries] */
+} multi_job;
+
+static void *multi_worker(void *p) {
+    multi_job *j = (multi_job *)p;
+    uint32_t dims = j->qcs[0].dims;
+    float *tmp = NULL;
+    if (!j->corpus) tmp = (float *)malloc(sizeof(float) * (size_t)dims);
+    for (uint64_t r = j->lo; r < j->hi; ++r) {
+        const float *row;
+        if (j->corpus) row = j->corpus + r * (uint64_t)dims;
+        else { wax_oracle_synth_row(j->seed, j->row_base + r, dims, j->normalize, tmp); row = tmp; }
+        for (uint32_t q = 0; q < j->n_queries; ++q)
+            heap_push(&j->heaps[q], row_distance(&j->qcs[q], row), r + j->row_base);
+    }
+    free(tmp);
+    return NULL;
+}
+
+static int multi_common(int metric, int mode, const float *corpus, uint64_t seed, int normalize, uint64_t n_rows,
+                        uint32_t dims, const float *queries, uint32_t n_queries, int64_t top_k, uint64_t row_base,
+                        int threads, uint64_t *out_rows, float *out_d, float *out_s, uint32_t *out_n) {
+    if (!queries || !out_n || dims == 0 || dims > WAX_ORACLE_MAX_DIMS || n_queries == 0) return -1;
+    if (metric < 0 || metric > 2 || mode < 0 || mode > 2) return -1;
+    for (uint32_t q = 0; q < n_queries; ++q) out_n[q] = 0;
+    if (n_rows == 0) return 0;
+    uint32_t k = (uint32_t)wax_oracle_clamp_topk(top_k);
+    if ((uint64_t)k > n_rows) k = (uint32_t)n_rows;
+    if (threads < 1) threads = 1;
+    if ((uint64_t)threads > n_rows) threads = (int)n_rows;
+
+    query_ctx *qcs = (query_ctx *)malloc(sizeof(query_ctx) * n_queries);
+    for (uint32_t q = 0; q < n_queries; ++q) query_ctx_init(&qcs[q], metric, mode, queries + (size_t)q * dims, dims);
+    multi_job *jobs = (multi_job *)calloc((size_t)threads, sizeof(multi_job));
+    pthread_t *tid = (pthread_t *)malloc(sizeof(pthread_t) * (size_t)threads);
+    uint64_t per = (n_rows + (uint64_t)threads - 1) / (uint64_t)threads;
+    for (int t = 0; t < threads; ++t) {
+        uint64_t lo = per * (uint64_t)t, hi = lo + per; if (lo > n_rows) lo = n_rows; if (hi > n_rows) hi = n_rows;
+        jobs[t].qcs = qcs; jobs[t].n_queries = n_queries; jobs[t].corpus = corpus; jobs[t].seed = seed;
+        jobs[t].normalize = normalize; jobs[t].lo = lo; jobs[t].hi = hi; jobs[t].row_base = row_base;
+        jobs[t].heaps = (topk_heap *)malloc(sizeof(topk_heap) * n_queries);
+        for (uint32_t q = 0; q < n_queries; ++q) {
+            jobs[t].heaps[q].h = (cand *)malloc(sizeof(cand) * k); jobs[t].heaps[q].n = 0; jobs[t].heaps[q].cap = k;
+        }
+        if (threads == 1) multi_worker(&jobs[t]); else pthread_create(&tid[t], NULL, multi_worker, &jobs[t]);
+    }
+    if (threads > 1) for (int t = 0; t < threads; ++t) pthread_join(tid[t], NULL);
+
+    cand *all = (cand *)malloc(sizeof(cand) * (size_t)threads * k);
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        size_t total = 0;
+        for (int t = 0; t < threads; ++t) {
+            memcpy(all + total, jobs[t].heaps[q].h, sizeof(cand) * jobs[t].heaps[q].n);
+            total += jobs[t].heaps[q].n;
+        }
+        qsort(all, total, sizeof(cand), cand_cmp);
+        uint32_t n = (uint32_t)(total < k ? total : k);
+        for (uint32_t i = 0; i < n; ++i) {
+            if (out_rows) out_rows[(size_t)q * k + i] = all[i].row;
+            if (out_d) out_d[(size_t)q * k + i] = all[i].d;
+            if (out_s) out_s[(size_t)q * k + i] = wax_oracle_score_from_distance(metric, all[i].d);
+        }
+        out_n[q] = n;
+    }
+    for (int t = 0; t < threads; ++t) {
+        for (uint32_t q = 0; q < n_queries; ++q) free(jobs[t].heaps[q].h);
+        free(jobs[t].heaps);
+    }
+    free(all); free(jobs); free(tid); free(qcs);
+    return 0;
+}
+
+int wax_oracle_search_multi(int metric, int mode, const float *corpus, uint64_t n_rows, uint32_t dims,
+                            const float *queries, uint32_t n_queries, int64_t top_k, uint64_t row_base, int threads,
+                            uint64_t *out_rows, float *out_distances, float *out_scores, uint32_t *out_n) {
+    if (!corpus && n_rows) return -1;
+    return multi_common(metric, mode, corpus, 0, 0, n_rows, dims, queries, n_queries, top_k, row_base, threads,
+                        out_rows, out_distances, out_scores, out_n);
+}
+
+int wax_oracle_search_synth_multi(int metric, int mode, uint64_t seed, uint64_t first_row, uint64_t n_rows,
+                                  uint32_t dims, int normalize, const float *queries, uint32_t n_queries,
+                                  int64_t top_k, int threads, uint64_t *out_rows, float *out_distances,
+                                  float *out_scores, uint32_t *out_n) {
+    return multi_common(metric, mode, NULL, seed, normalize, n_rows, dims, queries, n_queries, top_k, first_row,
+                        threads, out_rows, out_distances, out_scores, out_n);
+}
+
 /* siftDown of MetalVectorEngine.swift:635-647 (distance-only max-heap). */
 static void metal_sift_down(cand *h, uint32_t start, uint32_t end) {
     uint32_t root = start;

@@ -106,6 +106,17 @@ int wax_oracle_search_synth(int metric, int mode, uint64_t seed, uint64_t first_
                             int threads, uint64_t *out_rows, float *out_distances,
                             float *out_scores, uint32_t *out_n);
 
+/* Multi-query forms: the same scan for n_queries queries (row-major [n_queries][dims]) in ONE pass over the rows
+   (a synthetic row is generated once for all queries).  Outputs are [n_queries][k] with
+   k = min(clamp(top_k), n_rows); out_n[q] = results of query q.  Identical arithmetic, identical total order. */
+int wax_oracle_search_multi(int metric, int mode, const float *corpus, uint64_t n_rows, uint32_t dims,
+                            const float *queries, uint32_t n_queries, int64_t top_k, uint64_t row_base, int threads,
+                            uint64_t *out_rows, float *out_distances, float *out_scores, uint32_t *out_n);
+int wax_oracle_search_synth_multi(int metric, int mode, uint64_t seed, uint64_t first_row, uint64_t n_rows,
+                                  uint32_t dims, int normalize, const float *queries, uint32_t n_queries,
+                                  int64_t top_k, int threads, uint64_t *out_rows, float *out_distances,
+                                  float *out_scores, uint32_t *out_n);
+
 /* MetalVectorEngine.topK CPU heap (MetalVectorEngine.swift:630-680): k smallest of `distances`,
    boundary ties keep the earlier row (value >= heap[0] -> skip); final order here is made total
    (distance, row) because Swift's sort is not stable.  Returns count written. */

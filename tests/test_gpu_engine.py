@@ -229,6 +229,66 @@ def test_concurrent_searches_are_reentrant(oracle):
     assert allocs <= 9 and reuses > 0
 
 
+def test_search_concurrent_with_add_never_reports_a_short_buffer(oracle):
+    """A search whose result buffers were sized while another thread grows the corpus must still succeed (the mirror
+    allocates clamp(topK) entries / re-sizes on ERR_BUFFER), and every answer must be a valid answer for SOME prefix of
+    the add sequence: best-first, no duplicate ids, scores of the returned ids exact."""
+    dims = 32
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    rows = oracle.synth_rows(21, 0, 600, dims)
+    eng.add_batch([0, 1, 2], rows[:3])
+    qs = oracle.synth_rows(22, 0, 4, dims)
+    errors, stop = [], threading.Event()
+
+    def searcher(t):
+        try:
+            while not stop.is_set():
+                got = eng.search(qs[t % 4], 50)              # k > count at first: the buffer-size race window
+                assert len({g[0] for g in got}) == len(got)
+                assert all(a[1] >= b[1] for a, b in zip(got, got[1:]))
+                batch = eng.search_batch(qs, 50)
+                assert all(len({g[0] for g in b}) == len(b) for b in batch)
+        except Exception as exc:  # noqa: BLE001
+            errors.append(exc)
+    threads = [threading.Thread(target=searcher, args=(t,)) for t in range(4)]
+    [t.start() for t in threads]
+    for i in range(3, 600):
+        eng.add(i, rows[i])
+    stop.set()
+    [t.join() for t in threads]
+    assert not errors, errors[:1]
+    r, _, s = oracle.search(oracle.COSINE, rows, qs[0], 50, mode=oracle.ACC_F32_TREE)
+    got = eng.search(qs[0], 50)
+    assert [g[0] for g in got] == r.tolist()
+
+
+def test_mutator_drains_in_flight_device_path_scans(oracle):
+    """wax_vs_search_device returns with its kernel still in flight on the caller's (non-blocking) stream; a mutator
+    that follows must wait for it before moving rows: the candidates written by the in-flight scan are the
+    pre-mutation answer, bit for bit."""
+    import ctypes as C
+    import torch
+    from wax_b200 import _lib as L, sharded
+    dims, n, k = 384, 2_000_000, 10
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.fill_synthetic(23, n)
+    q = oracle.synth_row(24, 0, dims, True)
+    expect = eng.search(q, k)
+    d_q = torch.from_numpy(q).cuda()
+    stream = torch.cuda.Stream()
+    buf = torch.zeros(k * 24, dtype=torch.uint8, device="cuda")
+    torch.cuda.synchronize()
+    rc = L.lib().wax_vs_search_device(eng.handle, C.c_void_p(d_q.data_ptr()), 1, k, 0, C.c_void_p(buf.data_ptr()),
+                                      C.c_void_p(stream.cuda_stream))
+    assert rc == 0, L.last_error()
+    eng.remove(expect[0][0])          # shifts ~all rows down by one: must not start under the scan
+    stream.synchronize()
+    cands = buf.cpu().numpy().view(sharded.CAND_DTYPE)
+    assert [int(c["frame_id"]) for c in cands] == [e[0] for e in expect]
+    after = eng.search(q, k)
+    assert after[0][0] != expect[0][0] and [a[0] for a in after[:k - 1]] == [e[0] for e in expect[1:]]
+
+
 def test_growth_from_initial_reserve(oracle):
     eng = CUDAVectorEngine(VectorMetric.l2, 3)           # initialReserve 64, doubling (:19, :857-871)
     rows = oracle.synth_rows(8, 0, 1000, 3, normalize=False)

@@ -35,15 +35,127 @@ def test_full_size_top10_bit_exact_against_streaming_oracle(oracle, full_engine)
     assert all(a > b for a, b in zip(exact, exact[1:]))
 
 
-def test_full_size_k72_and_k100(oracle, full_engine):
-    q = oracle.synth_row(1002, 1, DIMS, True)
-    top100 = full_engine.search(q, 100)
-    assert len(top100) == 100 and all(a[1] >= b[1] for a, b in zip(top100, top100[1:]))
-    assert full_engine.search(q, 72) == top100[:72]              # select path is prefix-consistent
-    assert full_engine.search(q, 10) == top100[:10]              # fused-list path agrees with the select path
-    for fid, score in top100[::9]:                                # re-score sampled hits from regenerated rows
-        row = oracle.synth_row(SEED, fid, DIMS, True)
-        assert np.float32(1.0) - np.float32(oracle.distance(oracle.COSINE, oracle.ACC_F32_TREE, q, row)) == np.float32(score)
+N_SAMPLED = 16          # queries of the full-size batch that are checked against the streaming oracle
+
+
+@pytest.fixture(scope="module")
+def c3_queries(oracle):
+    """BASELINE configs[2]: 1024 queries against the 10 M x 384 corpus."""
+    return oracle.synth_rows(1010, 0, 1024, DIMS, normalize=True)
+
+
+@pytest.fixture(scope="module")
+def c3_oracle_top100(oracle, c3_queries):
+    """ONE streaming oracle pass over the 10 M synthetic rows for the sampled queries (each row generated once for
+    all of them), kernel accumulation order, top-100: the top-72 / top-10 answers are its prefixes (total order)."""
+    sample = list(range(0, 1024, 1024 // N_SAMPLED))[:N_SAMPLED]
+    rows, d, s, n = oracle.search_synth_multi(oracle.COSINE, SEED, 0, N_FULL, DIMS, True, c3_queries[sample], 100,
+                                              mode=oracle.ACC_F32_TREE, threads=oracle.host_threads())
+    assert n.tolist() == [100] * N_SAMPLED
+    return sample, rows, s
+
+
+def _check_against_f64(oracle, metric, seed, n_rows, dims, normalize, queries, k, got_ids, got_scores):
+    """north_star's bar against the fp64 truth: scores within 1e-4, ids identical outside fp64 near-ties (< 2e-6).
+    One extra reference row (k + 1) exposes a near-tie at the k-th boundary."""
+    from helpers import assert_tie_aware_order
+    rows, d, s, n = oracle.search_synth_multi(metric, seed, 0, n_rows, dims, normalize, queries, k + 1,
+                                              mode=oracle.ACC_F64, threads=oracle.host_threads())
+    for i in range(len(queries)):
+        ref64 = [1.0 - float(x) if metric == oracle.COSINE else -float(x) for x in d[i].astype(np.float64)]
+        assert np.max(np.abs(np.float64(got_scores[i]) - np.float64(ref64[:k]))) <= 1e-4
+        boundary_tie = abs(ref64[k] - ref64[k - 1]) <= 2e-6
+        if not boundary_tie:
+            assert sorted(int(x) for x in got_ids[i]) == sorted(rows[i][:k].tolist())
+        assert_tie_aware_order(got_ids[i], rows[i][:k].tolist(), ref64[:k], 2e-6)
+
+
+def test_full_size_k72_and_k100_against_the_full_oracle_top100(oracle, full_engine, c3_queries, c3_oracle_top100):
+    """k = 100 (emit + radix-select path when fused_k_max < 100; fused lists otherwise), the production k = 72 and
+    k = 10 against the oracle's COMPLETE top-100 of the 10 M rows: every id and every score bit, so a missed
+    neighbour anywhere in the list fails."""
+    sample, rows, s = c3_oracle_top100
+    for j in (0, 7):
+        q = c3_queries[sample[j]]
+        for k in (100, 72, 10):
+            got = full_engine.search(q, k)
+            assert [g[0] for g in got] == rows[j][:k].tolist(), (j, k)
+            assert np.array_equal(np.float32([g[1] for g in got]).view(np.uint32), s[j][:k].view(np.uint32)), (j, k)
+    full_engine.set_option("fused_k_max", 32)                  # force the emit + radix-select path for k = 72 / 100
+    try:
+        q = c3_queries[sample[3]]
+        for k in (100, 72):
+            got = full_engine.search(q, k)
+            assert [g[0] for g in got] == rows[3][:k].tolist(), ("select", k)
+            assert np.array_equal(np.float32([g[1] for g in got]).view(np.uint32), s[3][:k].view(np.uint32))
+    finally:
+        full_engine.set_option("fused_k_max", 128)
+
+
+def test_config2_full_size_batch_1024_top10_cosine(oracle, full_engine, c3_queries, c3_oracle_top100):
+    """BASELINE configs[2] at its stated size: 10 M x 384, batch 1024, top-10 cosine through wax_vs_search_batch (the
+    tcgen05 nomination levels).  (1) the WHOLE batch equals the single-query fused scan on the GPU; (2) the sampled
+    queries equal the streaming oracle -- ids and score bits in the kernels' accumulation order; (3) within 1e-4 and
+    tie-aware order against the fp64 oracle."""
+    t0, f0 = full_engine.batch_stats()
+    b0 = full_engine.counter("batch_bf16_queries")
+    ids, scores, ns = full_engine.search_batch_arrays(c3_queries, 10)
+    t1, f1 = full_engine.batch_stats()
+    assert ns.tolist() == [10] * 1024
+    assert (t1 - t0) + (f1 - f0) == 1024, "the batch did not take the tensor path"
+    assert full_engine.counter("batch_bf16_queries") - b0 == 1024, "bf16 shadow nominations did not run"
+    assert f1 - f0 <= 10, f"{f1 - f0} of 1024 queries fell back to the exact scan on unstructured data"
+    full_engine.set_option("batch_tensor", 0)
+    try:
+        for i in range(1024):                                   # (1) 1024 fused single-query scans, ~2 ms each
+            one = full_engine.search(c3_queries[i], 10)
+            assert [g[0] for g in one] == ids[i].tolist(), i
+            assert np.array_equal(np.float32([g[1] for g in one]).view(np.uint32), scores[i].view(np.uint32)), i
+    finally:
+        full_engine.set_option("batch_tensor", 1)
+    sample, rows, s = c3_oracle_top100                          # (2)
+    for j, qi in enumerate(sample):
+        assert ids[qi].tolist() == rows[j][:10].tolist(), qi
+        assert np.array_equal(scores[qi].view(np.uint32), s[j][:10].view(np.uint32)), qi
+    four = sample[:4]                                           # (3) full fp64 scan for four of them
+    _check_against_f64(oracle, oracle.COSINE, SEED, N_FULL, DIMS, True, c3_queries[four], 10,
+                       [ids[i] for i in four], [scores[i] for i in four])
+
+
+def test_config4_full_size_10m_x_768_batch_256_top100_dot(oracle):
+    """BASELINE configs[4] at its stated size: 10 M x 768 fp32 rows that are NOT normalised, batch 256, top-100 under
+    the dot metric (USearch ip: d = 1 - q.v, score = q.v - 1, VectorMetric.swift:21-43).  Same three checks."""
+    n, dims, seed, b, k = 10_000_000, 768, 5, 256, 100
+    eng = CUDAVectorEngine(VectorMetric.dot, dims)
+    try:
+        eng.fill_synthetic(seed, n, normalize=False)
+        qs = oracle.synth_rows(1011, 0, b, dims, normalize=True)
+        t0, f0 = eng.batch_stats()
+        ids, scores, ns = eng.search_batch_arrays(qs, k)
+        t1, f1 = eng.batch_stats()
+        assert ns.tolist() == [k] * b
+        assert (t1 - t0) + (f1 - f0) == b, "the batch did not take the tensor path"
+        assert eng.counter("batch_bf16_queries") == b
+        assert f1 - f0 <= 4, f"{f1 - f0} of {b} queries fell back to the exact scan"
+        eng.set_option("batch_tensor", 0)
+        for i in range(b):                                      # whole batch == fused single-query scan (k = 100)
+            one = eng.search(qs[i], k)
+            assert [g[0] for g in one] == ids[i].tolist(), i
+            assert np.array_equal(np.float32([g[1] for g in one]).view(np.uint32), scores[i].view(np.uint32)), i
+        eng.set_option("batch_tensor", 1)
+        sample = list(range(0, b, b // 8))[:8]
+        rows, d, s, cnt = oracle.search_synth_multi(oracle.DOT, seed, 0, n, dims, False, qs[sample], k,
+                                                    mode=oracle.ACC_F32_TREE, threads=oracle.host_threads())
+        assert cnt.tolist() == [k] * 8
+        for j, qi in enumerate(sample):
+            assert ids[qi].tolist() == rows[j].tolist(), qi
+            assert np.array_equal(scores[qi].view(np.uint32), s[j].view(np.uint32)), qi
+            assert np.array_equal(scores[qi], -d[j])            # score = -(1 - q.v)
+        two = sample[:2]
+        _check_against_f64(oracle, oracle.DOT, seed, n, dims, False, qs[two], k, [ids[i] for i in two],
+                           [scores[i] for i in two])
+    finally:
+        eng.close()
 
 
 def test_full_size_planted_neighbours_are_found(oracle, full_engine):

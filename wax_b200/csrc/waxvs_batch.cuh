@@ -1084,13 +1084,19 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
             const float qn = s_sqrt_a2;
             const float scale = METRIC == kCosine ? qn : qn * __uint_as_float(*p.max_norm_bits);
             const float sk_exact = METRIC == kCosine ? (1.0f - dk) * qn : 1.0f - dk;
-            const float eps = p.eps_rel * scale * 1.01f + 1e-30f;
+            // Slack on top of the operand-rounding bound: (a) fp32 accumulation error of the tensor-core pass and of
+            // the exact re-score, at most ~dims * 2^-24 * |q||v| each; (b) sk_exact is rebuilt from the ROUNDED
+            // distance dk (two roundings near 1.0), so a row excluded by less than that could still tie the k-th
+            // result in distance and win on the row index -- a few ulps of max(1, |dk|) cover it.
+            const float acc_slack = static_cast<float>(p.dims) * 0x1p-23f * scale;
+            const float ulp_slack = 0x1p-21f * fmaxf(1.0f, fabsf(dk)) * (METRIC == kCosine ? qn : 1.0f);
+            const float eps = p.eps_rel * scale * 1.01f + acc_slack + ulp_slack + 1e-30f;
             if (excluded_any && (!(sk_exact > tau + eps) || !finite_f32(eps))) ok = 0;
             // Filter level: the true top-k rows all have exact score >= the true k-th score >= sk_exact (the nominees
             // are a subset of the corpus), hence score' >= sk_exact - eps_filter: a pass that collects EVERY row above
             // that fixed threshold misses none of them.  A relative 2^-20 margin absorbs the rounding of this
             // subtraction and of the fp32 products sk_exact was built from.
-            const float feps = p.filter_eps_rel * scale * 1.01f + 1e-30f;
+            const float feps = p.filter_eps_rel * scale * 1.01f + acc_slack + ulp_slack + 1e-30f;
             const float t = sk_exact - feps;
             tau_star = finite_f32(t) ? t - fabsf(t) * 0x1p-20f - 1e-30f : -INFINITY;
         } else if (excluded_any) {

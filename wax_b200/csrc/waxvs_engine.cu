@@ -13,6 +13,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -198,13 +199,23 @@ struct wax_vs_engine {
     __nv_bfloat16 *d_shadow = nullptr; size_t shadow_cap = 0;
     bool shadow_valid = false, shadow_unavailable = false;
     uint64_t batch_tensor_queries = 0, batch_fallback_queries = 0;   // instrumentation
-    uint64_t batch_bf16_queries = 0, batch_retry_queries = 0;
+    uint64_t batch_bf16_queries = 0, batch_retry_queries = 0, batch_tf32_queries = 0;
     // Adaptive level choice: when more than a quarter of a batch fails the coarse bf16 bound (tightly clustered
     // neighbours), the next 16 batches nominate in TF32 straight away, then bf16 is probed again.
     uint32_t bf16_skip_batches = 0;
     std::mutex attr_mu;            // cudaFuncSetAttribute bookkeeping (per engine = per device)
     bool sort_attr_set = false, gather_attr_set = false, batch_attr_set = false;
+    std::unordered_map<const void *, int> smem_granted;   // opt-in shared memory already granted, per kernel (attr_mu)
+    // Device-path searches (wax_vs_search_device & co.) return while their kernels are still in flight on the
+    // caller's stream.  Mutators must not touch the corpus under them: every mutator drains the device first when
+    // this flag says something was enqueued since the last drain.
+    std::atomic<bool> async_pending{false};
 };
+
+// Called by every mutator after it has taken the write lock (and selected the device).
+static void drain_device_path(wax_vs_engine *e) {
+    if (e->async_pending.exchange(false)) cudaDeviceSynchronize();
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // scratch contexts
@@ -278,6 +289,21 @@ static void ctx_release(wax_vs_engine *e, SearchCtx *c) {
     std::lock_guard<std::mutex> g(e->pool_mu);
     e->pool.push_back(c);
 }
+// The scratch context bound to a caller-owned stream (device-path entry points): find-or-create in ONE critical
+// section, so two threads that first use the same stream cannot both insert (and leak) a context.
+static int32_t ctx_for_stream(wax_vs_engine *e, void *cuda_stream, SearchCtx **out) {
+    std::lock_guard<std::mutex> pg(e->pool_mu);
+    auto it = e->stream_ctx.find(cuda_stream);
+    if (it != e->stream_ctx.end()) { *out = it->second; return WAX_VS_OK; }
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_new(e, &c, false);
+    if (rc) return rc;
+    c->stream = static_cast<cudaStream_t>(cuda_stream);
+    e->stream_ctx[cuda_stream] = c;
+    ++e->pool_allocs;
+    *out = c;
+    return WAX_VS_OK;
+}
 
 template <typename T>
 static int32_t ensure_dev(T **p, size_t *cap, size_t need, const char *what) {
@@ -340,41 +366,44 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     return true;
 }
 
+// The opt-in shared-memory limit is per function and per device: set it once per engine (= per device), and again
+// only if a larger ring is requested, instead of on every launch -- it costs more host time than a 10 K-row scan.
+template <typename K>
+static cudaError_t grant_smem(wax_vs_engine *e, K kernel, size_t bytes) {
+    std::lock_guard<std::mutex> g(e->attr_mu);
+    int &have = e->smem_granted[reinterpret_cast<const void *>(kernel)];
+    if (have >= static_cast<int>(bytes)) return cudaSuccess;
+    cudaError_t err = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes));
+    if (err == cudaSuccess) have = static_cast<int>(bytes);
+    return err;
+}
+
 template <int C, int R, int M, int E, bool EMIT>
-static cudaError_t launch_tma_inst(const ScanParams &p, int grid, const TmaConfig &cfg, cudaStream_t s) {
-    // The opt-in shared-memory limit is per function and per device: set it once (and again only if a larger
-    // ring is requested) instead of on every launch -- it costs more host time than a 10 K-row scan takes.
-    static int granted[64] = {0};
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (dev < 0 || dev >= 64 || granted[dev] < static_cast<int>(cfg.smem)) {
-        cudaError_t err = cudaFuncSetAttribute(scan_tma_kernel<C, R, M, E, EMIT>,
-                                               cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(cfg.smem));
-        if (err != cudaSuccess) return err;
-        if (dev >= 0 && dev < 64) granted[dev] = static_cast<int>(cfg.smem);
-    }
+static cudaError_t launch_tma_inst(wax_vs_engine *e, const ScanParams &p, int grid, const TmaConfig &cfg, cudaStream_t s) {
+    cudaError_t err = grant_smem(e, scan_tma_kernel<C, R, M, E, EMIT>, cfg.smem);
+    if (err != cudaSuccess) return err;
     scan_tma_kernel<C, R, M, E, EMIT><<<grid, cfg.warps * 32, cfg.smem, s>>>(p);
     return cudaGetLastError();
 }
 // mode: 0 = fused list k <= 32, 1 = fused list k <= 128, 2 = emit distance keys
 template <int C, int R>
-static cudaError_t launch_tma_cr(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, int mode,
+static cudaError_t launch_tma_cr(wax_vs_engine *e, const ScanParams &p, int grid, const TmaConfig &cfg, int metric, int mode,
                                  cudaStream_t s) {
     switch (metric * 3 + mode) {
-        case 0: return launch_tma_inst<C, R, kCosine, 1, false>(p, grid, cfg, s);
-        case 1: return launch_tma_inst<C, R, kCosine, 4, false>(p, grid, cfg, s);
-        case 2: return launch_tma_inst<C, R, kCosine, 1, true>(p, grid, cfg, s);
-        case 3: return launch_tma_inst<C, R, kDot, 1, false>(p, grid, cfg, s);
-        case 4: return launch_tma_inst<C, R, kDot, 4, false>(p, grid, cfg, s);
-        case 5: return launch_tma_inst<C, R, kDot, 1, true>(p, grid, cfg, s);
-        case 6: return launch_tma_inst<C, R, kL2, 1, false>(p, grid, cfg, s);
-        case 7: return launch_tma_inst<C, R, kL2, 4, false>(p, grid, cfg, s);
-        default: return launch_tma_inst<C, R, kL2, 1, true>(p, grid, cfg, s);
+        case 0: return launch_tma_inst<C, R, kCosine, 1, false>(e, p, grid, cfg, s);
+        case 1: return launch_tma_inst<C, R, kCosine, 4, false>(e, p, grid, cfg, s);
+        case 2: return launch_tma_inst<C, R, kCosine, 1, true>(e, p, grid, cfg, s);
+        case 3: return launch_tma_inst<C, R, kDot, 1, false>(e, p, grid, cfg, s);
+        case 4: return launch_tma_inst<C, R, kDot, 4, false>(e, p, grid, cfg, s);
+        case 5: return launch_tma_inst<C, R, kDot, 1, true>(e, p, grid, cfg, s);
+        case 6: return launch_tma_inst<C, R, kL2, 1, false>(e, p, grid, cfg, s);
+        case 7: return launch_tma_inst<C, R, kL2, 4, false>(e, p, grid, cfg, s);
+        default: return launch_tma_inst<C, R, kL2, 1, true>(e, p, grid, cfg, s);
     }
 }
-static cudaError_t launch_tma(const ScanParams &p, int grid, const TmaConfig &cfg, int metric, int mode,
+static cudaError_t launch_tma(wax_vs_engine *e, const ScanParams &p, int grid, const TmaConfig &cfg, int metric, int mode,
                               cudaStream_t s) {
-#define WAXVS_CASE(Cv, Rv) if (cfg.C == Cv && cfg.R == Rv) return launch_tma_cr<Cv, Rv>(p, grid, cfg, metric, mode, s)
+#define WAXVS_CASE(Cv, Rv) if (cfg.C == Cv && cfg.R == Rv) return launch_tma_cr<Cv, Rv>(e, p, grid, cfg, metric, mode, s)
     WAXVS_CASE(1, 4); WAXVS_CASE(1, 8); WAXVS_CASE(2, 4); WAXVS_CASE(2, 8);
     WAXVS_CASE(3, 4); WAXVS_CASE(3, 8); WAXVS_CASE(4, 4); WAXVS_CASE(4, 8);
     WAXVS_CASE(6, 2); WAXVS_CASE(6, 4); WAXVS_CASE(8, 2); WAXVS_CASE(8, 4);
@@ -437,7 +466,7 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count;
         grid = static_cast<int>(std::min<uint64_t>(max_grid, (steps + cfg.warps - 1) / cfg.warps));
         grid = std::max(std::min(grid, grid_cap), 1);
-        CUDA_TRY(launch_tma(p, grid, cfg, e->similarity, mode, stream));
+        CUDA_TRY(launch_tma(e, p, grid, cfg, e->similarity, mode, stream));
     } else {
         const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count * e->tune.ldg_ctas_per_sm;
         grid = static_cast<int>(std::min<uint64_t>(max_grid, (e->n_rows + 7) / 8));
@@ -509,6 +538,7 @@ static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, ui
     const uint32_t min_batch = (e->tune.single_shadow && batch_bf16_wanted(e)) ? 1u : static_cast<uint32_t>(std::max(e->tune.batch_min, 1));
     return e->tune.batch_tensor && n_queries >= min_batch &&
            (e->similarity == WAX_VS_COSINE || e->similarity == WAX_VS_DOT) && e->dims % kBatchKBlock == 0 &&
+           e->dims <= 8192 &&        // the proof's accumulation slack (dims * 2^-23) stays far below the operand bound
            k_eff >= 1 && k_eff <= 128 && e->n_rows >= 1;
 }
 
@@ -938,6 +968,7 @@ int32_t wax_vs_reserve(wax_vs_engine *e, uint64_t rows) {
                     static_cast<unsigned long long>(rows));
     std::unique_lock<std::shared_mutex> w(e->rw);
     DeviceGuard g(e->device);
+    drain_device_path(e);
     return set_capacity(e, rows);
 }
 
@@ -950,6 +981,7 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
         return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, vector_len);
     std::unique_lock<std::shared_mutex> w(e->rw);
     DeviceGuard g(e->device);
+    drain_device_path(e);
     int32_t rc = grow_for(e, e->n_rows + n);  // maxNewCount (:379-380)
     if (rc) return rc;
     materialize_ids(e);
@@ -1021,6 +1053,7 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
         index = r;
     }
     DeviceGuard g(e->device);
+    drain_device_path(e);
     const uint64_t after = e->n_rows - 1 - index;  // countAfter (:431)
     if (after > 0) {
         // memmove of the tail (:433-437) through a bounce buffer, ascending chunks (dst < src).
@@ -1180,6 +1213,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
             e->batch_tensor_queries += n_queries - unproven.size();
             e->batch_fallback_queries += unproven.size();
             if (used_bf16) e->batch_bf16_queries += n_queries;
+            else e->batch_tf32_queries += n_queries;
             e->batch_retry_queries += retried;
         }
     } else {
@@ -1267,22 +1301,11 @@ int32_t wax_vs_search_device(wax_vs_engine *e, const float *d_queries, uint32_t 
     if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
     const uint32_t k_eff = clamp_topk(top_k);
     SearchCtx *c = nullptr;
-    {
-        std::lock_guard<std::mutex> pg(e->pool_mu);
-        auto it = e->stream_ctx.find(cuda_stream);
-        if (it != e->stream_ctx.end()) c = it->second;
-    }
-    if (!c) {
-        int32_t rc = ctx_new(e, &c, false);
-        if (rc) return rc;
-        c->stream = static_cast<cudaStream_t>(cuda_stream);
-        std::lock_guard<std::mutex> pg(e->pool_mu);
-        e->stream_ctx[cuda_stream] = c;
-        ++e->pool_allocs;
-    }
-    const uint64_t *d_ids = nullptr;
-    int32_t rc = sync_device_ids(e, &d_ids);
+    int32_t rc = ctx_for_stream(e, cuda_stream, &c);
     if (rc) return rc;
+    e->async_pending.store(true);
+    const uint64_t *d_ids = nullptr;
+    if ((rc = sync_device_ids(e, &d_ids))) return rc;
     uint64_t launches = 0;
     for (uint32_t qi = 0; qi < n_queries; ++qi) {
         rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
@@ -1305,22 +1328,11 @@ int32_t wax_vs_search_batch_device(wax_vs_engine *e, const float *d_queries, uin
     if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
     const uint32_t k_eff = clamp_topk(top_k);
     SearchCtx *c = nullptr;
-    {
-        std::lock_guard<std::mutex> pg(e->pool_mu);
-        auto it = e->stream_ctx.find(cuda_stream);
-        if (it != e->stream_ctx.end()) c = it->second;
-    }
-    if (!c) {
-        int32_t rc = ctx_new(e, &c, false);
-        if (rc) return rc;
-        c->stream = static_cast<cudaStream_t>(cuda_stream);
-        std::lock_guard<std::mutex> pg(e->pool_mu);
-        e->stream_ctx[cuda_stream] = c;
-        ++e->pool_allocs;
-    }
-    const uint64_t *d_ids = nullptr;
-    int32_t rc = sync_device_ids(e, &d_ids);
+    int32_t rc = ctx_for_stream(e, cuda_stream, &c);
     if (rc) return rc;
+    e->async_pending.store(true);
+    const uint64_t *d_ids = nullptr;
+    if ((rc = sync_device_ids(e, &d_ids))) return rc;
     uint64_t launches = 0;
     if (k_eff > e->n_rows) {   // a shard smaller than k: the scan pads with invalid candidates, the tensor path does not
         for (uint32_t qi = 0; qi < n_queries; ++qi) {
@@ -1510,6 +1522,7 @@ int32_t wax_vs_deserialize(wax_vs_engine *e, const uint8_t *src, uint64_t len) {
         return fail(WAX_VS_ERR_FORMAT, "vec segment length mismatch: expected %llu, got %llu",
                     static_cast<unsigned long long>(36 + vbytes + 8 + ibytes), static_cast<unsigned long long>(len));
     DeviceGuard g(e->device);
+    drain_device_path(e);
     int32_t rc = set_capacity(e, std::max<uint64_t>(count, 64));  // reservedCapacity = max(...) (:791-792)
     if (rc) return rc;
     if (vbytes) CUDA_TRY(cudaMemcpy(e->d_corpus, src + 36, vbytes, cudaMemcpyHostToDevice));  // :794-799
@@ -1538,6 +1551,7 @@ int32_t wax_vs_debug_fill_synthetic(wax_vs_engine *e, uint64_t seed, uint64_t fi
     if (rows > 0xFFFFFFFFull) return fail(WAX_VS_ERR_CAPACITY, "capacity exceeded: limit %llu, requested %llu", 0xFFFFFFFFull, static_cast<unsigned long long>(rows));
     std::unique_lock<std::shared_mutex> w(e->rw);
     DeviceGuard g(e->device);
+    drain_device_path(e);
     e->n_rows = 0;
     int32_t rc = set_capacity(e, std::max<uint64_t>(rows, 64));
     if (rc) return rc;
@@ -1659,6 +1673,8 @@ int32_t wax_vs_debug_counter(wax_vs_engine *e, const char *name, uint64_t *out) 
     else if (!strcmp(name, "batch_bf16_queries")) *out = e->batch_bf16_queries;
     else if (!strcmp(name, "batch_retry_queries")) *out = e->batch_retry_queries;
     else if (!strcmp(name, "shadow_bytes")) *out = e->shadow_valid ? e->shadow_cap * sizeof(__nv_bfloat16) : 0;
+    else if (!strcmp(name, "shadow_unavailable")) *out = e->shadow_unavailable ? 1 : 0;   // bf16 shadow did not fit: TF32 level runs
+    else if (!strcmp(name, "batch_tf32_queries")) *out = e->batch_tf32_queries;
     else if (!strcmp(name, "pool_allocs")) *out = e->pool_allocs;
     else if (!strcmp(name, "pool_reuses")) *out = e->pool_reuses;
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown counter '%s'", name);

@@ -104,6 +104,11 @@ def is_normalized_l2(vector: Sequence[float], tolerance: float = 1e-3) -> bool:
     return bool(abs(np.float32(np.sqrt(s)) - np.float32(1)) <= np.float32(tolerance))
 
 
+def _clamp_topk(top_k: int) -> int:
+    """clampTopK (MetalVectorEngine.swift:842-846)."""
+    return max(1, min(int(top_k), L.MAX_RESULTS))
+
+
 def _as_rows(vectors, dims: int) -> np.ndarray:
     rows = [np.asarray(v, dtype=np.float32).reshape(-1) for v in vectors] if not isinstance(vectors, np.ndarray) \
         else None
@@ -202,10 +207,11 @@ class CUDAVectorEngine:
     def search(self, vector: Sequence[float], top_k: int) -> List[Tuple[int, float]]:
         """search(vector:topK:) -> [(frameId, score)] best first."""
         q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
-        n_rows = self.count
-        cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(n_rows, 1)))
-        ids = np.zeros(cap, np.uint64)
-        scores = np.zeros(cap, np.float32)
+        # clamp(topK) entries, as the Swift mirror allocates: sizing from a separate count() call would race with a
+        # concurrent add (the library would then need more room than `cap` and report ERR_BUFFER on a valid search)
+        cap = _clamp_topk(top_k)
+        ids = np.empty(cap, np.uint64)
+        scores = np.empty(cap, np.float32)
         n = C.c_uint32(0)
         _check(L.lib().wax_vs_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k),
                                      ids.ctypes.data_as(C.POINTER(C.c_uint64)),
@@ -221,9 +227,9 @@ class CUDAVectorEngine:
             raise ValueError("pass exactly one of allow= / deny=")
         ids = np.ascontiguousarray(allow if allow is not None else deny, dtype=np.uint64).reshape(-1)
         q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
-        cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(self.count, 1)))
-        out_ids = np.zeros(cap, np.uint64)
-        scores = np.zeros(cap, np.float32)
+        cap = _clamp_topk(top_k)
+        out_ids = np.empty(cap, np.uint64)
+        scores = np.empty(cap, np.float32)
         n = C.c_uint32(0)
         idp = ids.ctypes.data_as(C.POINTER(C.c_uint64)) if ids.size else None
         _check(L.lib().wax_vs_search_filtered(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k), idp,
@@ -243,15 +249,21 @@ class CUDAVectorEngine:
         b = qs.shape[0]
         if b == 0:
             return np.zeros((0, 0), np.uint64), np.zeros((0, 0), np.float32), np.zeros(0, np.uint32)
-        n_rows = self.count
-        cap = max(1, min(max(1, min(int(top_k), L.MAX_RESULTS)), max(n_rows, 1)))
-        ids = np.zeros((b, cap), np.uint64)
-        scores = np.zeros((b, cap), np.float32)
-        ns = np.zeros(b, np.uint32)
-        _check(L.lib().wax_vs_search_batch(self._h, qs.ctypes.data_as(C.POINTER(C.c_float)), b, qs.shape[1],
-                                           int(top_k), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
-                                           scores.ctypes.data_as(C.POINTER(C.c_float)), cap,
-                                           ns.ctypes.data_as(C.POINTER(C.c_uint32))))
+        # b x min(clamp(topK), count) entries; a concurrent add can grow the count between the two calls, in which
+        # case the library answers ERR_BUFFER and the buffers are re-sized (clamp(topK) always suffices)
+        cap = max(1, min(_clamp_topk(top_k), max(self.count, 1)))
+        for attempt in range(3):
+            ids = np.zeros((b, cap), np.uint64)
+            scores = np.zeros((b, cap), np.float32)
+            ns = np.zeros(b, np.uint32)
+            rc = L.lib().wax_vs_search_batch(self._h, qs.ctypes.data_as(C.POINTER(C.c_float)), b, qs.shape[1],
+                                             int(top_k), ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                             scores.ctypes.data_as(C.POINTER(C.c_float)), cap,
+                                             ns.ctypes.data_as(C.POINTER(C.c_uint32)))
+            if rc != L.ERR_BUFFER:
+                break
+            cap = _clamp_topk(top_k) if attempt else max(1, min(_clamp_topk(top_k), max(self.count, 1)))
+        _check(rc)
         return ids, scores, ns
 
     def add(self, frame_id: int, vector: Sequence[float]) -> None:

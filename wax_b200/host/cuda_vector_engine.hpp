@@ -95,13 +95,23 @@ public:
             flat.insert(flat.end(), v.begin(), v.end());
         }
         const int64_t lim = topK < 1 ? 1 : (topK > WAX_VS_MAX_RESULTS ? WAX_VS_MAX_RESULTS : topK);
+        // stride = min(clamp(topK), count); a concurrent add may grow the count between count() and the search, the
+        // library then answers WAX_VS_ERR_BUFFER and the buffers are re-sized (clamp(topK) always suffices)
         const uint64_t rows = count();
-        const uint32_t stride = static_cast<uint32_t>(rows < static_cast<uint64_t>(lim) ? (rows ? rows : 1) : lim);
-        std::vector<uint64_t> ids(vectors.size() * stride);
-        std::vector<float> scores(vectors.size() * stride);
+        uint32_t stride = static_cast<uint32_t>(rows < static_cast<uint64_t>(lim) ? (rows ? rows : 1) : lim);
+        std::vector<uint64_t> ids;
+        std::vector<float> scores;
         std::vector<uint32_t> ns(vectors.size());
-        check(wax_vs_search_batch(h_, flat.data(), static_cast<uint32_t>(vectors.size()), dimensions_, topK, ids.data(),
-                                  scores.data(), stride, ns.data()));
+        int32_t rc = WAX_VS_OK;
+        for (int attempt = 0; attempt < 2; ++attempt) {
+            ids.assign(vectors.size() * stride, 0);
+            scores.assign(vectors.size() * stride, 0.0f);
+            rc = wax_vs_search_batch(h_, flat.data(), static_cast<uint32_t>(vectors.size()), dimensions_, topK, ids.data(),
+                                     scores.data(), stride, ns.data());
+            if (rc != WAX_VS_ERR_BUFFER) break;
+            stride = static_cast<uint32_t>(lim);
+        }
+        check(rc);
         for (size_t q = 0; q < vectors.size(); ++q) {
             out[q].resize(ns[q]);
             for (uint32_t i = 0; i < ns[q]; ++i) out[q][i] = {ids[q * stride + i], scores[q * stride + i]};
