@@ -9,8 +9,8 @@ A "step" is one pass of the hot path over the corpus for one query (BASELINE con
     python bench.py --impl reference ...      (the CPU restatement of the reference path on the host cores)
 
 N > 1 is STRONG scaling: the same 10 M-row corpus row-sharded N ways (contiguous ranges), the query
-replicated, one all-gather (NCCL) of the per-shard top-k per step and a host-side merge -- the only exchange
-the path has.
+replicated, the per-shard top-k lists exchanged over NVLink peer memory and merged inside the scan launch -- the only
+exchange the path has.  Same measurement mode at every N: one query in flight.
 
 Prints ONE JSON line (rank 0).  Keys follow the driver's contract; see DESIGN.md section "Measurement".
 """
@@ -186,6 +186,31 @@ def cpu_reference_arm(rows: int, steps: int, warmup: int, budget_s: float = 25.0
     }
 
 
+def cpu_c1_single_thread(samples: int = 15, warmup: int = 2):
+    """BASELINE configs[0]: 10 K x 384 fp32, 1 query, top-10 cosine on ONE host thread -- the reference's own
+    CPU-runnable case, timed the way the reference times things (warm-up, then per-iteration samples:
+    Tests/WaxIntegrationTests/RAGBenchmarkSupport.swift:285-308).  Both accumulation orders of the restatement:
+    the scalar sequential loop (USearch's metric_cos / the in-test loop, the literal "reference order") and the
+    SIMD-friendly tree order the kernels mirror."""
+    from oracle import oracle as o
+    o.build()
+    corpus = o.synth_rows(1, 0, 10_000, DIMS, normalize=True, threads=1)
+    q = o.synth_rows(QUERY_SEED, 0, 1, DIMS, normalize=True, threads=1)[0]
+    out = {"workload": "10000 x 384 fp32 corpus (BASELINE configs[0]), 1 query, top-10 cosine, single host thread",
+           "cores": 1, "kind": "port", "samples": samples, "warmup": warmup}
+    for name, mode in (("f32_seq", o.ACC_F32_SEQ), ("f32_tree", o.ACC_F32_TREE)):
+        for _ in range(warmup):
+            o.search(o.COSINE, corpus, q, TOP_K, mode=mode, threads=1)
+        ts = []
+        for _ in range(samples):
+            t = time.perf_counter()
+            o.search(o.COSINE, corpus, q, TOP_K, mode=mode, threads=1)
+            ts.append(time.perf_counter() - t)
+        out[name] = {"ms_mean": float(np.mean(ts)) * 1e3, "ms_min": float(np.min(ts)) * 1e3,
+                     "ms_median": float(np.median(ts)) * 1e3, "queries_per_s": 1.0 / float(np.mean(ts))}
+    return out
+
+
 def run_reference(args, rank: int):
     if rank != 0:
         return
@@ -197,6 +222,7 @@ def run_reference(args, rank: int):
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, max(args.gpus, 1)),
         "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+        "cpu_c1_single_thread": cpu_c1_single_thread(),
         "e2e": {"value": base["value"], "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "note": "CPU restatement of the reference path (exact scan, USearch metric formulas); the shipped reference "
                 "CPU engine is USearch HNSW (approximate) and cannot be built here (no Swift toolchain).",
@@ -301,39 +327,93 @@ def run_single(args):
             line["batched"] = batched_arm(eng, args)
         except Exception as ex:     # noqa: BLE001
             line["batched"] = {"error": repr(ex)}
+    if not args.no_shadow and not small:
+        eng.close()                 # free the 23 GB of configs[1]/[2] before the 46 GB of configs[4]
+        try:
+            line["batched_c5"] = batched_c5_arm()
+        except Exception as ex:     # noqa: BLE001
+            line["batched_c5"] = {"error": repr(ex)}
     if not args.no_cpu_baseline:
         base = cpu_reference_arm(args.rows, steps=5, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        try:
+            line["cpu_c1_single_thread"] = cpu_c1_single_thread()
+            # the GPU side of configs[0] for context (launch-latency-bound: 15 MB is 2 us of HBM time)
+        except Exception as ex:     # noqa: BLE001
+            line["cpu_c1_single_thread"] = {"error": repr(ex)}
     print(json.dumps(line), flush=True)
 
 
-def batched_arm(eng, args, batch: int = 1024, steps: int = 10):
-    """NOT the headline: BASELINE configs[2] (batch of 1024 queries, top-10 cosine) on the corpus already resident for
-    the headline -- tcgen05 nominations over the bf16 shadow + exact fp32 re-score + completeness proof (DESIGN 4.5.1),
-    results identical to 1024 single-query scans.  Device-only, CUDA events inside the library; the full companion
-    (end to end, configs[4], TF32) is scripts/bench_batch.py."""
-    peaks = {}
+def _tensor_peaks():
     try:
-        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+        return json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
     except Exception:  # noqa: BLE001
-        pass
-    ms, launches, unproven = eng.time_search_batch(batch, TOP_K, steps, warmup=2, seed=QUERY_SEED)
+        return {}
+
+
+def _batched_line(eng, rows, dims, batch, top_k, metric_name, workload, steps):
+    """Device-only time (CUDA events inside the library) + the same batch END TO END through wax_vs_search_batch with
+    HOST buffers (queries H2D, ids/scores D2H inside the timed region) + which level answered."""
+    import torch
+    peaks = _tensor_peaks()
+    ms, launches, unproven = eng.time_search_batch(batch, top_k, steps, warmup=2, seed=QUERY_SEED)
     per = ms / steps
-    flops = 2.0 * batch * args.rows * DIMS
+    flops = 2.0 * batch * rows * dims
     tf = flops / (per * 1e-3) / 1e12
     bf16 = eng.counter("shadow_bytes") > 0
     peak = float(peaks.get("bf16_tflops", 2250.0)) if bf16 else 1100.0
+    rng = np.random.default_rng(QUERY_SEED + batch)
+    qs = rng.uniform(-1.0, 1.0, size=(batch, dims)).astype(np.float32)
+    qs /= np.linalg.norm(qs, axis=1, keepdims=True)
+    for _ in range(2):
+        eng.search_batch_arrays(qs, top_k)
+    t0q, f0q = eng.batch_stats()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        ids, scores, ns = eng.search_batch_arrays(qs, top_k)
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t0) / steps
+    t1q, f1q = eng.batch_stats()
     return {
-        "workload": f"{args.rows} x {DIMS} fp32 corpus (BASELINE configs[2]), batch {batch}, top-{TOP_K} cosine",
-        "value": batch / per * 1e3, "unit": "queries/s", "ms_per_step": per, "steps": steps,
+        "workload": workload, "value": batch / per * 1e3, "unit": "queries/s", "ms_per_step": per, "steps": steps,
         "dtype": ("bf16" if bf16 else "tf32") + " nominations + f32 exact re-score",
         "roofline": {"bound": "tensor", "achieved": tf, "peak": peak, "unit": "TFLOP/s", "frac": tf / peak,
                      "peak_source": "measured cuBLAS bf16 burst (MEASURED_PEAKS.json bf16_tflops)" if bf16 and "bf16_tflops" in peaks
                      else ("nominal dense bf16" if bf16 else "nominal dense TF32"),
                      "frac_of_sustained": tf / float(peaks["bf16_tflops_sustained"]) if bf16 and "bf16_tflops_sustained" in peaks else None,
-                     "useful_flops_per_launch": flops},
+                     "useful_flops_per_launch": flops,
+                     "hbm_floor_ms": rows * dims * (2 if bf16 else 4) / (float(peaks.get("hbm_gbs", FALLBACK_HBM_GBS)) * 1e9) * 1e3},
+        "e2e": {"value": batch / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s * 1e3,
+                "h2d_bytes_per_step": batch * dims * 4, "d2h_bytes_per_step": batch * top_k * 24,
+                "api": "wax_vs_search_batch (host queries -> host ids/scores, synchronous)"},
         "gpu_launches_per_step": launches / steps, "unproven_queries_last_step": unproven,
+        "levels": {"tensor_proven_queries": t1q - t0q, "exact_scan_fallback_queries": f1q - f0q,
+                   "shadow_unavailable_tf32_level": bool(eng.counter("shadow_unavailable")),
+                   "shadow_gb": eng.counter("shadow_bytes") / 1e9},
+        "metric": metric_name,
     }
+
+
+def batched_arm(eng, args, batch: int = 1024, steps: int = 10):
+    """NOT the headline: BASELINE configs[2] (batch of 1024 queries, top-10 cosine) on the corpus already resident for
+    the headline -- tcgen05 nominations over the bf16 shadow + exact fp32 re-score + completeness proof (DESIGN 4.5.1),
+    results identical to 1024 single-query scans (tests/test_gpu_fullsize.py checks that at this size)."""
+    return _batched_line(eng, args.rows, DIMS, batch, TOP_K, "queries/sec cosine top-10, batch 1024 @ 10Mx384 fp32",
+                         f"{args.rows} x {DIMS} fp32 corpus (BASELINE configs[2]), batch {batch}, top-{TOP_K} cosine", steps)
+
+
+def batched_c5_arm(rows: int = 10_000_000, dims: int = 768, batch: int = 256, top_k: int = 100, steps: int = 10):
+    """NOT the headline: BASELINE configs[4] -- 10 M x 768 fp32 rows that are NOT normalised, batch 256, top-100 under
+    the dot metric (score = q.v - 1).  Its own engine (30.7 GB corpus + 15.4 GB bf16 shadow)."""
+    from wax_b200 import CUDAVectorEngine, VectorMetric
+    eng = CUDAVectorEngine(VectorMetric.dot, dims, device=0)
+    try:
+        eng.fill_synthetic(5, rows, normalize=False)
+        return _batched_line(eng, rows, dims, batch, top_k, "queries/sec dot top-100, batch 256 @ 10Mx768 fp32",
+                             f"{rows} x {dims} fp32 un-normalised corpus (BASELINE configs[4]), batch {batch}, top-{top_k} dot", steps)
+    finally:
+        eng.close()
 
 
 def shadow_filtered_arm(eng, args, qs, n_distinct):
@@ -370,6 +450,11 @@ def shadow_filtered_arm(eng, args, qs, n_distinct):
 
 
 def run_sharded(args, rank: int, world: int, local_rank: int):
+    """N > 1: the same 10 M-row corpus row-sharded N ways (STRONG scaling), measured in the SAME mode as N = 1:
+    `value` = K collective searches strictly one at a time on one stream, CUDA events on that stream, max over ranks
+    (N = 1 times K fused scans back to back on one stream the same way); `e2e` = K synchronous calls of the public
+    sharded search with a HOST query and HOST results on every rank.  One kernel launch per query per rank: the
+    exchange of the per-shard top-k lists and the merge run inside the scan launch over NVLink peer memory."""
     import torch
     import torch.distributed as dist
     from wax_b200 import VectorMetric, sharded
@@ -381,74 +466,65 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
         eng.engine.set_option(key, int(val))
     n_distinct = min(64, args.steps + args.warmup)
     qs_host = host_queries(n_distinct)
-    qs_dev = torch.from_numpy(qs_host).cuda()
-    qs_pinned = torch.from_numpy(qs_host).pin_memory()
     warm = max(args.warmup, 3)
     shard_bytes = (eng.row_hi - eng.row_lo) * DIMS * 4
-    small = shard_bytes <= 4 * 126e6
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda") if small else None
+    fused = eng.transport == "p2p-fused"
 
-    depth = max(1, args.pipeline)      # independent queries in flight (throughput metric): host merge of
-                                       # query i overlaps the scan + all-gather of query i+1
+    def max_over_ranks(x: float) -> float:
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
 
-    micro = max(1, args.micro)         # queries per exchange: one all-gather carries `micro` queries' candidates
-
-    def run_steps(n, queries_of):
-        """n single-query steps, issued in micro-batches; queries_of(i0, g) -> [g, DIMS] device tensor."""
-        from collections import deque
-        pending, last, i, b = deque(), None, 0, 0
-        while i < n:
-            g = min(micro, n - i)
-            if small:
-                flush.fill_(i & 0xFF)
-            pending.append(eng.search_many_async(queries_of(i, g), TOP_K, slot=b % depth))
-            i += g; b += 1
-            if len(pending) == depth:
-                last = eng.finish_many(pending.popleft())[-1]
-        while pending:
-            last = eng.finish_many(pending.popleft())[-1]
-        return last
-
-    def resident(i0, g):
-        j0 = i0 % n_distinct
-        if j0 + g <= n_distinct:
-            return qs_dev[j0:j0 + g]                       # a view: no kernel, queries already resident in HBM
-        return torch.cat([qs_dev[j0:], qs_dev[: g - (n_distinct - j0)]])
-
-    # ---- value: inputs resident in HBM; per step = local fused kernel + all-gather + D2H + host merge
-    run_steps(warm, resident)
-    dist.barrier(); torch.cuda.synchronize()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        ev0.record()
-        last = run_steps(args.steps, resident)
-        ev1.record()
+    def timed_value(e, steps):
+        """K searches, one in flight, device-timed; returns (ms_total max over ranks, launches on this rank)."""
+        dist.barrier(); torch.cuda.synchronize()
+        if e.transport == "p2p-fused":
+            ms, launches = e.time_search(TOP_K, steps, warmup=warm, n_queries=n_distinct, seed=QUERY_SEED)
+        else:   # no peer mapping between the ranks: NCCL all-gather + host merge, still strictly one query at a time
+            qs_dev = torch.from_numpy(qs_host).cuda()
+            for i in range(warm):
+                e.finish(e.search_async(qs_dev[i % n_distinct], TOP_K))
+            torch.cuda.synchronize(); dist.barrier()
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            for i in range(steps):
+                e.finish(e.search_async(qs_dev[i % n_distinct], TOP_K))
+            ev1.record(); torch.cuda.synchronize()
+            ms, launches = ev0.elapsed_time(ev1), steps
         torch.cuda.synchronize(); dist.barrier()
-        ms = torch.tensor([ev0.elapsed_time(ev1)], device="cuda")
-        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-        ms_total = float(ms.item())
+        return max_over_ranks(ms), launches
 
-        # ---- e2e: host query -> H2D -> scan -> all-gather -> D2H -> host merge, every step
-        d_qs = [torch.empty((micro, DIMS), dtype=torch.float32, device="cuda") for _ in range(depth)]
-        pin_stage = [torch.empty((micro, DIMS), dtype=torch.float32).pin_memory() for _ in range(depth)]
-        counter = [0]
-
-        def host_query(i0, g):
-            slot = counter[0] % depth
-            counter[0] += 1
-            for j in range(g):                                    # host queries arrive one by one
-                pin_stage[slot][j].copy_(qs_pinned[(i0 + j) % n_distinct])
-            d_qs[slot][:g].copy_(pin_stage[slot][:g], non_blocking=True)
-            return d_qs[slot][:g]
-        run_steps(warm, host_query)
+    def timed_e2e(e, steps):
+        for i in range(warm):
+            e.search(qs_host[i % n_distinct], TOP_K)
         dist.barrier(); torch.cuda.synchronize()
         t0 = time.perf_counter()
-        last = run_steps(args.steps, host_query)
-        torch.cuda.synchronize(); dist.barrier()
-        e2e = torch.tensor([time.perf_counter() - t0], device="cuda")
-        dist.all_reduce(e2e, op=dist.ReduceOp.MAX)
-        e2e_s = float(e2e.item())
+        last = None
+        for i in range(steps):
+            last = e.search(qs_host[i % n_distinct], TOP_K)      # host query in, merged host result out, synchronous
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        dist.barrier()
+        return max_over_ranks(dt), last
+
+    with ClockSampler(local_rank) as clk:
+        ms_total, launches = timed_value(eng, args.steps)
+        e2e_s, last = timed_e2e(eng, args.steps)
     clocks = clk.summary()
+    # every rank must hold the same merged answer
+    same = torch.tensor([last[0][0], int(np.float32(last[0][1]).view(np.uint32))], dtype=torch.int64, device="cuda")
+    lo, hi = same.clone(), same.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    ranks_agree = bool(torch.equal(lo, hi))
+
+    transport, transport_note = eng.transport, eng.transport_note
+    weak = None
+    if not args.no_weak:
+        try:
+            weak = weak_arm(args, eng, world, timed_value, timed_e2e)
+        except Exception as ex:     # noqa: BLE001
+            weak = {"error": repr(ex)}
+    eng.close()     # no-op for the engine the weak arm already closed
     if rank == 0:
         peak, peak_src = measured_peak()
         ms_per_step = ms_total / args.steps
@@ -458,20 +534,58 @@ def run_sharded(args, rank: int, world: int, local_rank: int):
             "steps": args.steps, "warmup": warm, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": workload_config(args, world),
+            "mode": "latency: strictly one query in flight, K launches back to back on one stream per rank (as N=1)",
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": None, "peak_source": peak_src,
-                         "note": "per-GPU: shard bytes / whole step time (scan + all-gather + D2H + host merge)",
+                         "note": "per GPU: shard bytes / the step's single kernel launch (scan + NVLink exchange + merge "
+                                 "in one launch; its duration includes waiting for the slowest rank)",
                          "algorithmic_bytes_per_launch": shard_bytes},
             "e2e": {"value": args.steps / e2e_s, "unit": "queries/s", "h2d_bytes_per_step": DIMS * 4,
-                    "d2h_bytes_per_step": world * TOP_K * 24, "ms_per_step": e2e_s / args.steps * 1e3,
-                    "api": "ShardedVectorEngine.search_async/finish (host query -> host ids/scores on every rank)"},
-            "gpu_launches": args.steps, "queries_in_flight": depth * micro,
-            "collective": f"1 all_gather_into_tensor of {micro} x {TOP_K * 24} B per rank per {micro} steps (nccl)",
+                    "d2h_bytes_per_step": TOP_K * 24, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "ShardedVectorEngine.search -> wax_vs_shard_search (host query -> merged host ids/scores on "
+                           "every rank, synchronous)" if fused else "ShardedVectorEngine.search (all-gather transport)"},
+            "gpu_launches": int(launches), "queries_in_flight": 1,
+            "collective": ("none per query: the scan's last CTA writes its top-k (240 B) into every rank's mailbox over "
+                           "NVLink peer memory and merges in-kernel; torch.distributed only passed the mailbox handles "
+                           "at start-up") if fused else
+                          f"1 all_gather_into_tensor of {TOP_K * 24} B per rank per step (nccl) + host merge",
+            "transport": transport, "transport_note": transport_note,
             "clocks": clocks,
-            "check": {"top1_frame_id": last[0][0], "top1_score": last[0][1]},
+            "check": {"top1_frame_id": last[0][0], "top1_score": last[0][1], "ranks_agree": ranks_agree},
         }
+        if weak is not None:
+            line["weak"] = weak
         print(json.dumps(line), flush=True)
     dist.destroy_process_group()
+
+
+def weak_arm(args, strong_eng, world, timed_value, timed_e2e, rows_per_gpu: int = 12_500_000, steps: int = 10):
+    """NOT the headline: WEAK scaling -- 12.5 M rows x 384 per GPU, generated on device (at 8 GPUs this is BASELINE
+    configs[3]: 100 M x 384 row-sharded over 8 B200s, 19.2 GB per GPU, 1 query, top-10 cosine).  Same latency mode."""
+    import torch
+    import torch.distributed as dist
+    from wax_b200 import VectorMetric, sharded
+    strong_eng.close()
+    total = rows_per_gpu * world
+    eng = sharded.ShardedVectorEngine(VectorMetric.cosine, DIMS, total_rows=total)
+    eng.fill_synthetic(4)
+    ms_total, launches = timed_value(eng, steps)
+    e2e_s, last = timed_e2e(eng, steps)
+    per = ms_total / steps
+    peak, _ = measured_peak()
+    gbs = rows_per_gpu * DIMS * 4 / (per / 1e3) / 1e9
+    out = {
+        "workload": f"{total} x {DIMS} fp32 corpus row-sharded over {world} GPUs ({rows_per_gpu} rows = "
+                    f"{rows_per_gpu * DIMS * 4 / 1e9:.1f} GB per GPU), 1 query per step, top-{TOP_K} cosine"
+                    + (" (BASELINE configs[3])" if world == 8 else ""),
+        "value": steps / (ms_total / 1e3), "unit": "queries/s", "ms_per_step": per, "steps": steps,
+        "per_gpu_gbs": gbs, "per_gpu_frac_of_measured_peak": gbs / peak, "aggregate_gbs": gbs * world,
+        "e2e": {"value": steps / e2e_s, "unit": "queries/s", "ms_per_step": e2e_s / steps * 1e3},
+        "gpu_launches_per_step": launches / steps, "transport": eng.transport,
+        "check": {"top1_frame_id": last[0][0], "top1_score": last[0][1]},
+    }
+    eng.close()
+    return out
 
 
 def main():
@@ -484,8 +598,7 @@ def main():
     ap.add_argument("--opt", action="append", default=[], help="engine tuning option key=value (experiments)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-shadow", action="store_true", help="skip the extra `shadow_filtered` (opt-in mode) measurement")
-    ap.add_argument("--pipeline", type=int, default=2, help="N>1: micro-batches in flight per rank")
-    ap.add_argument("--micro", type=int, default=4, help="N>1: queries per exchange (one all-gather carries them all)")
+    ap.add_argument("--no-weak", action="store_true", help="N>1: skip the extra weak-scaling (12.5 M rows per GPU) measurement")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -157,6 +157,41 @@ int32_t wax_vs_search_batch_device(wax_vs_engine *engine, const float *d_queries
                                    int64_t top_k, uint64_t row_offset, wax_vs_candidate *d_candidates,
                                    void *cuda_stream);
 
+/* ---- row-sharded search across the GPUs of one node (no reference counterpart) -------------
+   One engine per GPU holds a contiguous row range of the corpus; the query is replicated; every rank scans its shard
+   and the per-shard top-k lists are exchanged and merged under the total order (distance, GLOBAL row).  The exchange is
+   fused into the scan launch: the kernel's last CTA writes its k candidates straight into every rank's mailbox over
+   NVLink / NVSwitch peer memory, raises a flag, waits for the others' flags and merges world x k candidates -- no
+   collective launch, no D2H copy, no host merge (wax_b200/csrc/waxvs_shard.cuh).  Every rank gets the same result.
+
+   Setup: each rank calls wax_vs_shard_open (allocates its mailbox, returns a WAX_VS_SHARD_HANDLE_BYTES blob), the
+   blobs are exchanged by any out-of-band means (the Python mirror uses one torch.distributed all-gather; a single
+   process driving several GPUs just passes them along), then every rank calls wax_vs_shard_connect with all `world`
+   blobs in rank order (CUDA IPC between processes, peer access inside one process).
+   Searches are COLLECTIVE: every rank must issue the same searches in the same order (same query, same top_k).
+   top_k is clamped to [1, 10000] as usual but must not exceed WAX_VS_SHARD_MAX_K (the fused top-k range);
+   larger k -> WAX_VS_ERR_UNSUPPORTED (gather wax_vs_search_device candidates instead).  A rank whose peers never
+   arrive gets WAX_VS_ERR_CUDA after the exchange timeout (20 s; option "shard_timeout_ms") instead of hanging. */
+#define WAX_VS_SHARD_HANDLE_BYTES 128
+#define WAX_VS_SHARD_MAX_RANKS 16
+#define WAX_VS_SHARD_MAX_K 128
+int32_t wax_vs_shard_open(wax_vs_engine *engine, int32_t rank, int32_t world, uint64_t row_offset,
+                          uint8_t *out_handle /* WAX_VS_SHARD_HANDLE_BYTES */);
+int32_t wax_vs_shard_connect(wax_vs_engine *engine, const uint8_t *handles /* n_handles x HANDLE_BYTES, rank order */,
+                             int32_t n_handles);
+/* Leave the group: unmaps the peers' mailboxes.  This rank's own mailbox stays allocated until wax_vs_destroy or the
+   next wax_vs_shard_open, because other processes may still have it mapped -- close on every rank, synchronise the
+   ranks (a barrier), then destroy. */
+int32_t wax_vs_shard_close(wax_vs_engine *engine);
+/* search(vector:topK:) over the whole sharded corpus; host query in, host ids / scores out (best first, as
+   wax_vs_search); blocks until the merged result is in the caller's buffers.  out_cap >= clamp(top_k). */
+int32_t wax_vs_shard_search(wax_vs_engine *engine, const float *query, uint32_t query_len, int64_t top_k,
+                            uint64_t *out_ids, float *out_scores, uint32_t out_cap, uint32_t *out_n);
+/* Device-resident form: d_query (dims floats) and d_candidates (clamp(top_k) merged entries, padding valid = 0) are
+   device pointers; enqueued on `cuda_stream`, returns without synchronising. */
+int32_t wax_vs_shard_search_device(wax_vs_engine *engine, const float *d_query, int64_t top_k,
+                                   wax_vs_candidate *d_candidates, void *cuda_stream);
+
 /* ---- persistence: "MV2V" v1 encoding = 2, byte-identical to MetalVectorEngine.serialize ---------- */
 
 /* serialize() (MetalVectorEngine.swift:682-714). */
@@ -192,6 +227,12 @@ int32_t wax_vs_debug_read_rows(wax_vs_engine *engine, uint64_t first, uint64_t n
 int32_t wax_vs_debug_time_search(wax_vs_engine *engine, uint32_t n_queries, int64_t top_k, uint64_t seed,
                                  uint32_t warmup, uint32_t iters, float *out_ms_total,
                                  uint64_t *out_launches);
+
+/* wax_vs_debug_time_search for the sharded path: warmup + iters collective searches strictly one at a time on one
+   stream, CUDA events around the `iters` (every rank makes the same call; queries are generated on device from
+   `seed`, identical on every rank). */
+int32_t wax_vs_debug_time_shard_search(wax_vs_engine *engine, uint32_t n_queries, int64_t top_k, uint64_t seed,
+                                       uint32_t warmup, uint32_t iters, float *out_ms_total, uint64_t *out_launches);
 
 /* Batched-path instrumentation: how many queries were answered by the tensor-core nomination path with a
    completed exactness proof, and how many had to be re-run on the exact single-query path. */

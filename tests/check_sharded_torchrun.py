@@ -1,6 +1,11 @@
 """Multi-GPU parity check (run under torchrun, one rank per GPU, NCCL; lives under tests/ because it uses the oracle
 as the checker -- not collected by pytest): the row-sharded search must return exactly
-what a single exact scan of the whole corpus returns (bit-exact against the streaming oracle)."""
+what a single exact scan of the whole corpus returns (bit-exact against the streaming oracle).
+
+    torchrun --nproc-per-node N tests/check_sharded_torchrun.py [total_rows] [light]
+
+`total_rows` defaults to 2 000 003; 100000000 is BASELINE configs[3] at 8 GPUs (12.5 M rows = 19.2 GB per GPU).
+`light` skips the batched / micro-batched forms (they are size-independent and covered at the default size)."""
 import os
 import sys
 from pathlib import Path
@@ -17,38 +22,77 @@ from wax_b200 import VectorMetric, sharded  # noqa: E402
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)
 dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-total, dims, seed = 2_000_003, 384, 31
+total = int(sys.argv[1]) if len(sys.argv) > 1 else 2_000_003
+light = len(sys.argv) > 2 and sys.argv[2] == "light"
+dims, seed = 384, (4 if total >= 100_000_000 else 31)
 eng = sharded.ShardedVectorEngine(VectorMetric.cosine, dims, total_rows=total)
 eng.fill_synthetic(seed)
+if rank == 0:
+    print(f"world={world} total_rows={total} rows/GPU={eng.row_hi - eng.row_lo} transport={eng.transport} {eng.transport_note}", flush=True)
 ok = True
-for qi, k in ((0, 10), (1, 32), (2, 72), (3, 1)):
-    q = o.synth_row(777, qi, dims, True)
-    got = eng.search(q, k)
-    rows, d, s = o.search_synth(o.COSINE, seed, 0, total, dims, True, q, k, mode=o.ACC_F32_TREE, threads=16)
-    same = [g[0] for g in got] == rows.tolist() and np.array_equal(np.float32([g[1] for g in got]).view(np.uint32), s.view(np.uint32))
+
+
+def same_bits(got, rows, s):
+    return [g[0] for g in got] == rows.tolist() and \
+        np.array_equal(np.float32([g[1] for g in got]).view(np.uint32), s.view(np.uint32))
+
+
+# ONE streaming oracle pass on rank 0 for all checked queries (top-128: every smaller k is a prefix), shared by broadcast
+cases = ((0, 10), (1, 32), (2, 72), (3, 1), (4, 128))
+qs = np.stack([o.synth_row(777, qi, dims, True) for qi, _ in cases])
+exp = torch.zeros((len(cases), 128, 2), dtype=torch.int64, device="cuda")
+if rank == 0:
+    rows, d, s, n = o.search_synth_multi(o.COSINE, seed, 0, total, dims, True, qs, 128, mode=o.ACC_F32_TREE,
+                                         threads=o.host_threads())
+    exp[:, :, 0] = torch.from_numpy(rows.astype(np.int64)).cuda()
+    exp[:, :, 1] = torch.from_numpy(s.view(np.uint32).astype(np.int64)).cuda()
+dist.broadcast(exp, src=0)
+exp = exp.cpu().numpy()
+for ci, (qi, k) in enumerate(cases):
+    got = eng.search(qs[ci], k)                                  # p2p-fused transport when the ranks can map each other
+    same = [g[0] for g in got] == exp[ci, :k, 0].tolist() and \
+        [int(np.float32(g[1]).view(np.uint32)) for g in got] == exp[ci, :k, 1].tolist()
     ok = ok and same
     if rank == 0:
         print(f"k={k}: {'OK' if same else 'MISMATCH'} top1={got[0]}", flush=True)
-qs = o.synth_rows(778, 0, 4, dims, normalize=True)
-many = eng.finish_many(eng.search_many_async(torch.from_numpy(qs).cuda(), 10, slot=0))
-same = many == [eng.search(q, 10) for q in qs]
+# the all-gather transport (what k > 128 and the batched forms use) must agree with the fused one
+d_q = torch.from_numpy(qs[0]).cuda()
+via_allgather = eng.finish(eng.search_async(d_q, 10))
+same = via_allgather == eng.search(qs[0], 10)
+big = eng.search(qs[0], 200)
+same = same and len(big) == 200 and [b[0] for b in big[:128]] == exp[0, :128, 0].tolist()
 ok = ok and same
 if rank == 0:
-    print(f"micro-batched exchange (4 queries, one all-gather): {'OK' if same else 'MISMATCH'}", flush=True)
-# batched form: tensor-core levels per shard, one all-gather for the whole batch, vectorised merge
-qb = o.synth_rows(779, 0, 300, dims, normalize=True)
-batch = eng.search_batch(qb, 10)
-same = all(batch[i] == eng.search(qb[i], 10) for i in (0, 1, 127, 128, 299))
-rows, d, s = o.search_synth(o.COSINE, seed, 0, total, dims, True, qb[5], 10, mode=o.ACC_F32_TREE, threads=16)
-same = same and [g[0] for g in batch[5]] == rows.tolist() and \
-    np.array_equal(np.float32([g[1] for g in batch[5]]).view(np.uint32), s.view(np.uint32))
+    print(f"all-gather transport (k=10 and k=200) agrees with the fused exchange: {'OK' if same else 'MISMATCH'}", flush=True)
+# many collective searches back to back on one stream (mailbox slot reuse under real NVLink latency)
+ms, launches = eng.time_search(10, 40, warmup=5, n_queries=8, seed=778)
+after = eng.search(qs[0], 10)
+same = [g[0] for g in after] == exp[0, :10, 0].tolist() and launches == 40
 ok = ok and same
 if rank == 0:
-    print(f"sharded search_batch (300 queries, bf16 queries {eng.engine.counter('batch_bf16_queries')}): "
+    print(f"40 back-to-back collective searches: {ms / 40:.3f} ms each, {launches} launches; result afterwards "
           f"{'OK' if same else 'MISMATCH'}", flush=True)
+if not light:
+    qm = o.synth_rows(778, 0, 4, dims, normalize=True)
+    many = eng.finish_many(eng.search_many_async(torch.from_numpy(qm).cuda(), 10, slot=0))
+    same = many == [eng.search(q, 10) for q in qm]
+    ok = ok and same
+    if rank == 0:
+        print(f"micro-batched exchange (4 queries, one all-gather): {'OK' if same else 'MISMATCH'}", flush=True)
+    # batched form: tensor-core levels per shard, one all-gather for the whole batch, vectorised merge
+    qb = o.synth_rows(779, 0, 300, dims, normalize=True)
+    batch = eng.search_batch(qb, 10)
+    same = all(batch[i] == eng.search(qb[i], 10) for i in (0, 1, 127, 128, 299))
+    rows, d, s = o.search_synth(o.COSINE, seed, 0, total, dims, True, qb[5], 10, mode=o.ACC_F32_TREE, threads=16)
+    same = same and same_bits(batch[5], rows, s)
+    ok = ok and same
+    if rank == 0:
+        print(f"sharded search_batch (300 queries, bf16 queries {eng.engine.counter('batch_bf16_queries')}): "
+              f"{'OK' if same else 'MISMATCH'}", flush=True)
 flag = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:
-    print("SHARDED PARITY", "PASS" if flag.item() == 1 else "FAIL", f"world={world}", flush=True)
+    print("SHARDED PARITY", "PASS" if flag.item() == 1 else "FAIL", f"world={world} rows={total} transport={eng.transport}", flush=True)
+eng.close()
 dist.destroy_process_group()
 sys.exit(0 if flag.item() == 1 else 1)

@@ -18,6 +18,7 @@ OK, ERR_NULL, ERR_DIMENSION, ERR_CAPACITY, ERR_CUDA, ERR_FORMAT, ERR_ARGUMENT, E
     0, -1, -2, -3, -4, -5, -6, -7, -8)
 MAX_RESULTS = 10_000
 MAX_DIMENSIONS = 1_000_000
+SHARD_HANDLE_BYTES, SHARD_MAX_RANKS, SHARD_MAX_K = 128, 16, 128
 
 
 class Candidate(C.Structure):
@@ -49,6 +50,11 @@ SIGNATURES = {
                                          C.c_void_p]),
     "wax_vs_search_batch_device": (C.c_int32, [_eng, C.c_void_p, C.c_uint32, C.c_int64, C.c_uint64, C.c_void_p,
                                                C.c_void_p]),
+    "wax_vs_shard_open": (C.c_int32, [_eng, C.c_int32, C.c_int32, C.c_uint64, _u8p]),
+    "wax_vs_shard_connect": (C.c_int32, [_eng, _u8p, C.c_int32]),
+    "wax_vs_shard_close": (C.c_int32, [_eng]),
+    "wax_vs_shard_search": (C.c_int32, [_eng, _f32p, C.c_uint32, C.c_int64, _u64p, _f32p, C.c_uint32, _u32p]),
+    "wax_vs_shard_search_device": (C.c_int32, [_eng, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p]),
     "wax_vs_serialized_length": (C.c_int32, [_eng, _u64p]),
     "wax_vs_serialize": (C.c_int32, [_eng, _u8p, C.c_uint64, _u64p]),
     "wax_vs_deserialize": (C.c_int32, [_eng, _u8p, C.c_uint64]),
@@ -58,6 +64,8 @@ SIGNATURES = {
     "wax_vs_debug_read_rows": (C.c_int32, [_eng, C.c_uint64, C.c_uint64, _f32p]),
     "wax_vs_debug_time_search": (C.c_int32, [_eng, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,
                                              _f32p, _u64p]),
+    "wax_vs_debug_time_shard_search": (C.c_int32, [_eng, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                                   _f32p, _u64p]),
     "wax_vs_debug_batch_stats": (C.c_int32, [_eng, _u64p, _u64p]),
     "wax_vs_debug_counter": (C.c_int32, [_eng, C.c_char_p, _u64p]),
     "wax_vs_debug_time_search_batch": (C.c_int32, [_eng, C.c_uint32, C.c_int64, C.c_uint64, C.c_uint32, C.c_uint32,

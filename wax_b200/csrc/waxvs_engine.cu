@@ -22,6 +22,10 @@
 #include <shared_mutex>
 #include <string>
 #include <unordered_map>
+#include <chrono>
+#include <random>
+#include <thread>
+#include <unistd.h>
 #include <cmath>
 #include <vector>
 
@@ -127,6 +131,7 @@ struct Tuning {
     int batch_rescore = 0;  // 0 auto; else nominees re-scored exactly per query (256, 512 or 1024)
     int batch_retry = 1;    // queries level 1 cannot prove go through the filter level (TF32, complete by construction) before an exact scan
     int filter_cap = 8192;  // candidates per query the filter level may collect (power of two <= 16384); overflow -> exact scan
+    int shard_fused = 1;    // sharded search: exchange + merge inside the scan launch (0: separate 1-CTA launch)
     int single_shadow = 0;  // 1: single queries / batches below batch_min also take the bf16-shadow nominations
                             // (half the HBM bytes per query: 1.19 vs 2.04 ms at 10 M x 384, same results); off by
                             // default: the plain single-query path is the fused fp32 scan BASELINE's north_star names
@@ -162,6 +167,7 @@ struct SearchCtx {
     uint64_t *d_cand_keys = nullptr; size_t cand_keys_cap = 0;
     uint32_t *d_mask = nullptr; size_t mask_cap = 0;              // filtered search: row bitset / listed rows
     uint64_t *d_gather_keys = nullptr; size_t gather_cap = 0;     // filtered search: keys of the listed rows
+    wax_vs_candidate *d_shard_local = nullptr;                    // sharded search: this rank's list before the exchange [kShardKCap]
 };
 
 struct wax_vs_engine {
@@ -210,7 +216,25 @@ struct wax_vs_engine {
     // caller's stream.  Mutators must not touch the corpus under them: every mutator drains the device first when
     // this flag says something was enqueued since the last drain.
     std::atomic<bool> async_pending{false};
+
+    // Row-sharded search (wax_vs_shard_*): this engine is rank `rank` of `world`; box[r] = rank r's mailbox.
+    struct Shard {
+        bool open = false, connected = false;
+        int rank = 0, world = 0;
+        uint64_t row_offset = 0;
+        ShardMailbox *box[kShardMaxRanks] = {};
+        bool ipc[kShardMaxRanks] = {};            // mapped with cudaIpcOpenMemHandle (closed in shard_close)
+        unsigned long long seq = 0;               // collective calls issued so far (same on every rank)
+        unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+        std::mutex mu;                            // one collective call at a time per rank: seq order = issue order
+        SearchCtx *ctx = nullptr;                 // host entry point: stream + scratch
+        wax_vs_candidate *d_final = nullptr;      // [kShardKCap]
+        wax_vs_candidate *h_final = nullptr;      // mapped pinned [kShardKCap]: the kernel writes the merged result here
+        unsigned long long *h_flag = nullptr;     // mapped pinned: seq when h_final is complete
+    } shard;
 };
+
+extern "C" { static void shard_teardown(wax_vs_engine *e, bool free_own); }
 
 // Called by every mutator after it has taken the write lock (and selected the device).
 static void drain_device_path(wax_vs_engine *e) {
@@ -245,6 +269,7 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_cand_keys) cudaFree(c->d_cand_keys);
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_gather_keys) cudaFree(c->d_gather_keys);
+    if (c->d_shard_local) cudaFree(c->d_shard_local);
     if (c->h_ok) cudaFreeHost(c->h_ok);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -427,12 +452,31 @@ static cudaError_t launch_ldg(const ScanParams &p, int grid, int metric, int mod
 }
 
 // Enqueue one query's scan + top-k on `stream`.  k_eff <= 10000.  Adds the number of kernels launched.
+// `shard` (optional): the row-sharded form -- d_out receives the result MERGED over all ranks; the exchange runs inside
+// the scan launch when the kernel's shared-memory lists can hold the merge keys, else as one extra 1-CTA launch.
 static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_query, uint32_t k_eff,
                               uint64_t row_offset, wax_vs_candidate *d_out, const uint64_t *d_ids,
-                              cudaStream_t stream, uint64_t *launches, const uint32_t *d_mask = nullptr) {
+                              cudaStream_t stream, uint64_t *launches, const uint32_t *d_mask = nullptr,
+                              const ShardParams *shard = nullptr) {
+    wax_vs_candidate *d_merged = nullptr;
+    if (shard) {
+        if (k_eff > static_cast<uint32_t>(kShardKCap))
+            return fail(WAX_VS_ERR_UNSUPPORTED, "sharded search supports top_k <= %d (got %u)", kShardKCap, k_eff);
+        if (!c->d_shard_local) CUDA_TRY(cudaMalloc(&c->d_shard_local, kShardKCap * sizeof(wax_vs_candidate)));
+        d_merged = d_out;
+        d_out = c->d_shard_local;           // the scan produces the LOCAL list; the exchange writes d_merged
+    }
+    auto exchange_standalone = [&]() -> int32_t {
+        ShardParams sp = *shard;
+        sp.final_out = d_merged;
+        shard_exchange_kernel<<<1, 256, 0, stream>>>(sp, d_out, k_eff);
+        CUDA_TRY(cudaGetLastError());
+        ++*launches;
+        return WAX_VS_OK;
+    };
     if (e->n_rows == 0) {
         CUDA_TRY(cudaMemsetAsync(d_out, 0, static_cast<size_t>(k_eff) * sizeof(wax_vs_candidate), stream));
-        return WAX_VS_OK;
+        return shard ? exchange_standalone() : WAX_VS_OK;
     }
     ScanParams p{};
     p.corpus = e->d_corpus; p.query = d_query;
@@ -458,6 +502,12 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     bool use_tma = (e->tune.variant != 2) && pick_tma_config(e, &cfg);
     if (e->tune.variant == 1 && !use_tma)
         return fail(WAX_VS_ERR_UNSUPPORTED, "TMA-staged kernel does not support dims=%u", e->dims);
+    bool fused_exchange = false;
+    if (shard && !emit) {     // the merge keys (world * k uint32) live in the kernel's block-list shared memory
+        const size_t list_bytes = static_cast<size_t>(use_tma ? cfg.warps : 8) * 32 * (mode == 0 ? 1 : 4) * sizeof(uint64_t);
+        fused_exchange = e->tune.shard_fused != 0 && static_cast<size_t>(shard->world) * k_eff * sizeof(uint32_t) <= list_bytes;
+        if (fused_exchange) { p.shard = *shard; p.shard.final_out = d_merged; }
+    }
     int grid;
     const int grid_cap = static_cast<int>(c->block_keys_cap / 128);
     if (use_tma) {
@@ -497,6 +547,7 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         CUDA_TRY(cudaGetLastError());
         *launches += 3 + 2 * kSelectPasses;
     }
+    if (shard && !fused_exchange) return exchange_standalone();
     return WAX_VS_OK;
 }
 
@@ -933,6 +984,7 @@ void wax_vs_destroy(wax_vs_engine *e) {
         std::unique_lock<std::shared_mutex> w(e->rw);
         DeviceGuard g(e->device);
         cudaDeviceSynchronize();
+        shard_teardown(e, true);
         for (SearchCtx *c : e->pool) ctx_free(c);
         for (auto &kv : e->stream_ctx) ctx_free(kv.second);
         if (e->d_corpus) cudaFree(e->d_corpus);
@@ -1345,6 +1397,282 @@ int32_t wax_vs_search_batch_device(wax_vs_engine *e, const float *d_queries, uin
     return run_queries_on_device(e, c, d_queries, n_queries, k_eff, row_offset, d_candidates, d_ids, &launches);
 }
 
+// ---- row-sharded search: fused scan + NVLink exchange + merge (waxvs_shard.cuh) ---------------
+// Handle blob exchanged between the ranks (WAX_VS_SHARD_HANDLE_BYTES): how a peer reaches this rank's mailbox.
+struct ShardHandle {
+    uint32_t magic, version;
+    int32_t pid, device;
+    uint64_t nonce;                  // per-process random: same (pid, nonce) = same process -> plain peer access
+    uint64_t ptr;                    // mailbox device pointer (valid in the owning process)
+    int32_t rank, world;
+    cudaIpcMemHandle_t ipc;          // 64 bytes: for other processes on the node
+    uint8_t pad[WAX_VS_SHARD_HANDLE_BYTES - 40 - sizeof(cudaIpcMemHandle_t)];
+};
+static_assert(sizeof(ShardHandle) == WAX_VS_SHARD_HANDLE_BYTES, "handle blob size");
+static uint64_t process_nonce() {
+    static const uint64_t n = [] { std::random_device rd; return (static_cast<uint64_t>(rd()) << 32) ^ rd() ^ 0x9E3779B97F4A7C15ull; }();
+    return n;
+}
+
+// Caller holds the write lock, device selected.  Two steps because other PROCESSES may still have this rank's mailbox
+// mapped: wax_vs_shard_close only unmaps the peers' mailboxes (free_own = false); the own mailbox is released when the
+// engine is destroyed or re-opened, i.e. after the group has agreed (a barrier on the caller's side) that everyone
+// has closed.
+static void shard_teardown(wax_vs_engine *e, bool free_own) {
+    auto &sh = e->shard;
+    if (!sh.open) return;
+    cudaDeviceSynchronize();
+    for (int r = 0; r < sh.world; ++r) {
+        if (r != sh.rank && sh.ipc[r] && sh.box[r]) cudaIpcCloseMemHandle(sh.box[r]);
+        sh.ipc[r] = false;
+        if (r != sh.rank) sh.box[r] = nullptr;
+    }
+    sh.connected = false;
+    cudaGetLastError();
+    if (!free_own) return;
+    if (sh.box[sh.rank]) cudaFree(sh.box[sh.rank]);
+    sh.box[sh.rank] = nullptr;
+    if (sh.ctx) { ctx_free(sh.ctx); sh.ctx = nullptr; }
+    if (sh.d_final) { cudaFree(sh.d_final); sh.d_final = nullptr; }
+    if (sh.h_final) { cudaFreeHost(sh.h_final); sh.h_final = nullptr; }
+    if (sh.h_flag) { cudaFreeHost(sh.h_flag); sh.h_flag = nullptr; }
+    cudaGetLastError();
+    sh.open = false;
+    sh.seq = 0;
+}
+
+int32_t wax_vs_shard_open(wax_vs_engine *e, int32_t rank, int32_t world, uint64_t row_offset, uint8_t *out_handle) {
+    if (!e || !out_handle) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (world < 1 || world > kShardMaxRanks || rank < 0 || rank >= world)
+        return fail(WAX_VS_ERR_ARGUMENT, "rank %d of %d: world must be 1..%d", rank, world, kShardMaxRanks);
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    drain_device_path(e);
+    shard_teardown(e, true);
+    auto &sh = e->shard;
+    ShardMailbox *box = nullptr;
+    CUDA_TRY(cudaMalloc(&box, sizeof(ShardMailbox)));
+    cudaError_t err = cudaMemset(box, 0, sizeof(ShardMailbox));
+    if (err == cudaSuccess) err = cudaMalloc(&sh.d_final, kShardKCap * sizeof(wax_vs_candidate));
+    if (err == cudaSuccess) err = cudaHostAlloc(&sh.h_final, kShardKCap * sizeof(wax_vs_candidate), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) err = cudaHostAlloc(&sh.h_flag, sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable);
+    if (err == cudaSuccess) err = cudaDeviceSynchronize();
+    ShardHandle h{};
+    if (err == cudaSuccess) err = cudaIpcGetMemHandle(&h.ipc, box);
+    if (err != cudaSuccess) {
+        cudaFree(box);
+        if (sh.d_final) { cudaFree(sh.d_final); sh.d_final = nullptr; }
+        if (sh.h_final) { cudaFreeHost(sh.h_final); sh.h_final = nullptr; }
+        if (sh.h_flag) { cudaFreeHost(sh.h_flag); sh.h_flag = nullptr; }
+        return fail(WAX_VS_ERR_CUDA, "failed to create the shard mailbox: %s", cudaGetErrorString(err));
+    }
+    *sh.h_flag = 0;
+    int32_t rc = ctx_new(e, &sh.ctx, true);
+    if (rc) { cudaFree(box); return rc; }
+    sh.rank = rank; sh.world = world; sh.row_offset = row_offset;
+    sh.box[rank] = box;
+    sh.open = true; sh.connected = (world == 1);
+    sh.seq = 0;
+    h.magic = 0x48535857u; h.version = 1; h.pid = static_cast<int32_t>(getpid()); h.device = e->device;
+    h.nonce = process_nonce(); h.ptr = reinterpret_cast<uint64_t>(box); h.rank = rank; h.world = world;
+    memcpy(out_handle, &h, sizeof h);
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_shard_connect(wax_vs_engine *e, const uint8_t *handles, int32_t n_handles) {
+    if (!e || !handles) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    auto &sh = e->shard;
+    if (!sh.open) return fail(WAX_VS_ERR_ARGUMENT, "wax_vs_shard_open has not been called");
+    if (n_handles != sh.world) return fail(WAX_VS_ERR_ARGUMENT, "expected %d handles, got %d", sh.world, n_handles);
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    for (int r = 0; r < sh.world; ++r) {
+        ShardHandle h;
+        memcpy(&h, handles + static_cast<size_t>(r) * sizeof h, sizeof h);
+        if (h.magic != 0x48535857u || h.version != 1 || h.rank != r || h.world != sh.world)
+            return fail(WAX_VS_ERR_ARGUMENT, "handle %d is not rank %d of %d", r, r, sh.world);
+        if (r == sh.rank) continue;
+        if (h.pid == static_cast<int32_t>(getpid()) && h.nonce == process_nonce()) {
+            // same process (several engines in one host process): plain peer access to the other device
+            if (h.device != e->device) {
+                int can = 0;
+                CUDA_TRY(cudaDeviceCanAccessPeer(&can, e->device, h.device));
+                if (!can) return fail(WAX_VS_ERR_UNSUPPORTED, "device %d cannot access device %d (no P2P path)", e->device, h.device);
+                cudaError_t pe = cudaDeviceEnablePeerAccess(h.device, 0);
+                if (pe != cudaSuccess && pe != cudaErrorPeerAccessAlreadyEnabled)
+                    return fail(WAX_VS_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d) failed: %s", h.device, cudaGetErrorString(pe));
+                cudaGetLastError();
+            }
+            sh.box[r] = reinterpret_cast<ShardMailbox *>(h.ptr);
+            sh.ipc[r] = false;
+        } else {
+            void *ptr = nullptr;
+            cudaError_t ie = cudaIpcOpenMemHandle(&ptr, h.ipc, cudaIpcMemLazyEnablePeerAccess);
+            if (ie != cudaSuccess) {
+                cudaGetLastError();
+                return fail(WAX_VS_ERR_UNSUPPORTED, "cudaIpcOpenMemHandle for rank %d failed: %s (no P2P/IPC path between the ranks)",
+                            r, cudaGetErrorString(ie));
+            }
+            sh.box[r] = static_cast<ShardMailbox *>(ptr);
+            sh.ipc[r] = true;
+        }
+    }
+    sh.connected = true;
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_shard_close(wax_vs_engine *e) {
+    if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    shard_teardown(e, false);
+    return WAX_VS_OK;
+}
+
+// caller holds e->shard.mu: the next collective sequence number and the parameter block that goes with it
+static ShardParams shard_params_next(wax_vs_engine *e) {
+    auto &sh = e->shard;
+    ShardParams sp{};
+    for (int r = 0; r < sh.world; ++r) sp.box[r] = sh.box[r];
+    sp.rank = static_cast<uint32_t>(sh.rank); sp.world = static_cast<uint32_t>(sh.world);
+    sp.seq = ++sh.seq;
+    sp.timeout_ns = sh.timeout_ns;
+    return sp;
+}
+
+int32_t wax_vs_shard_search_device(wax_vs_engine *e, const float *d_query, int64_t top_k, wax_vs_candidate *d_candidates,
+                                   void *cuda_stream) {
+    if (!e || !d_query || !d_candidates) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    if (!e->shard.connected) return fail(WAX_VS_ERR_ARGUMENT, "the shard group is not connected (wax_vs_shard_open / _connect)");
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    const uint32_t k_eff = clamp_topk(top_k);
+    if (k_eff > static_cast<uint32_t>(kShardKCap))
+        return fail(WAX_VS_ERR_UNSUPPORTED, "sharded search supports top_k <= %d (got %u)", kShardKCap, k_eff);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_for_stream(e, cuda_stream, &c);
+    if (rc) return rc;
+    e->async_pending.store(true);
+    const uint64_t *d_ids = nullptr;
+    if ((rc = sync_device_ids(e, &d_ids))) return rc;
+    std::lock_guard<std::mutex> sg(e->shard.mu);
+    ShardParams sp = shard_params_next(e);
+    uint64_t launches = 0;
+    return enqueue_search(e, c, d_query, k_eff, e->shard.row_offset, d_candidates, d_ids,
+                          static_cast<cudaStream_t>(cuda_stream), &launches, nullptr, &sp);
+}
+
+// Wait for the kernel's host-visible completion flag (mapped pinned memory): a few microseconds after the merge,
+// instead of an event/stream synchronisation.  The stream is polled now and then so that a launch failure surfaces.
+static int32_t shard_wait_host(wax_vs_engine *e, unsigned long long seq) {
+    auto &sh = e->shard;
+    volatile unsigned long long *flag = sh.h_flag;
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    for (;;) {
+        const unsigned long long v = *flag;
+        if ((v & ~kShardErrorBit) == seq) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            if (v & kShardErrorBit)
+                return fail(WAX_VS_ERR_CUDA, "shard exchange timed out: a peer rank did not deliver its candidates for query #%llu", seq);
+            return WAX_VS_OK;
+        }
+        if ((++spins & 0x3FFu) == 0) {
+            const cudaError_t q = cudaStreamQuery(sh.ctx->stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+                return fail(WAX_VS_ERR_CUDA, "sharded search failed on the device: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && ((*flag) & ~kShardErrorBit) != seq)
+                return fail(WAX_VS_ERR_CUDA, "sharded search finished without publishing its result");
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(sh.timeout_ns) + std::chrono::seconds(5))
+                return fail(WAX_VS_ERR_CUDA, "sharded search did not complete");
+        }
+    }
+}
+
+int32_t wax_vs_shard_search(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k, uint64_t *out_ids,
+                            float *out_scores, uint32_t out_cap, uint32_t *out_n) {
+    if (!e || !out_n) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    *out_n = 0;
+    if (!e->shard.connected) return fail(WAX_VS_ERR_ARGUMENT, "the shard group is not connected (wax_vs_shard_open / _connect)");
+    if (!query) return fail(WAX_VS_ERR_NULL, "query is NULL");
+    if (query_len != e->dims)
+        return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, query_len);
+    const uint32_t k_eff = clamp_topk(top_k);
+    if (k_eff > static_cast<uint32_t>(kShardKCap))
+        return fail(WAX_VS_ERR_UNSUPPORTED, "sharded search supports top_k <= %d (got %u)", kShardKCap, k_eff);
+    if (!out_ids || !out_scores) return fail(WAX_VS_ERR_NULL, "output buffer is NULL");
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    auto &sh = e->shard;
+    std::lock_guard<std::mutex> sg(sh.mu);      // one host-path collective at a time: it owns sh.ctx and h_final
+    SearchCtx *c = sh.ctx;
+    int32_t rc;
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(e->dims), "query buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, static_cast<size_t>(e->dims), "query staging"))) return rc;
+    const uint64_t *d_ids = nullptr;
+    if ((rc = sync_device_ids(e, &d_ids))) return rc;
+    memcpy(c->h_queries, query, e->dims * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, e->dims * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    ShardParams sp = shard_params_next(e);
+    sp.host_out = sh.h_final; sp.host_flag = sh.h_flag;      // mapped pinned: the kernel delivers the result itself
+    uint64_t launches = 0;
+    if ((rc = enqueue_search(e, c, c->d_queries, k_eff, sh.row_offset, sh.d_final, d_ids, c->stream, &launches, nullptr, &sp))) {
+        cudaStreamSynchronize(c->stream);
+        return rc;
+    }
+    if ((rc = shard_wait_host(e, sp.seq))) { cudaStreamSynchronize(c->stream); return rc; }
+    uint32_t m = 0;
+    for (uint32_t i = 0; i < k_eff; ++i) {
+        const wax_vs_candidate &cd = sh.h_final[i];
+        if (cd.valid != 1u) continue;
+        if (m >= out_cap) return fail(WAX_VS_ERR_BUFFER, "output buffers hold %u entries, need more", out_cap);
+        out_ids[m] = cd.frame_id;
+        out_scores[m] = score_from_distance(e->similarity, cd.distance);
+        ++m;
+    }
+    *out_n = m;
+    return WAX_VS_OK;
+}
+
+// Device-timed sharded searches, strictly one query at a time on one stream (the same mode as wax_vs_debug_time_search):
+// `n_queries` unit queries generated on device from generator stream `seed` (identical on every rank), warmup + iters
+// collective searches back to back, CUDA events around the `iters`.  Every rank must make the same call.
+int32_t wax_vs_debug_time_shard_search(wax_vs_engine *e, uint32_t n_queries, int64_t top_k, uint64_t seed, uint32_t warmup,
+                                       uint32_t iters, float *out_ms_total, uint64_t *out_launches) {
+    if (!e || !out_ms_total) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (n_queries == 0) n_queries = 1;
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    if (!e->shard.connected) return fail(WAX_VS_ERR_ARGUMENT, "the shard group is not connected (wax_vs_shard_open / _connect)");
+    DeviceGuard g(e->device);
+    auto &sh = e->shard;
+    std::lock_guard<std::mutex> sg(sh.mu);
+    SearchCtx *c = sh.ctx;
+    const uint32_t k_eff = clamp_topk(top_k);
+    int32_t rc;
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(n_queries) * e->dims, "query buffer"))) return rc;
+    synth_fill_kernel<<<(n_queries + 255) / 256, 256, 0, c->stream>>>(c->d_queries, n_queries, e->dims, seed, 0, 1);
+    CUDA_TRY(cudaGetLastError());
+    const uint64_t *d_ids = nullptr;
+    if ((rc = sync_device_ids(e, &d_ids))) return rc;
+    uint64_t launches = 0;
+    for (uint32_t it = 0; it < warmup + iters; ++it) {
+        if (it == warmup) { launches = 0; CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); }
+        ShardParams sp = shard_params_next(e);
+        rc = enqueue_search(e, c, c->d_queries + static_cast<size_t>(it % n_queries) * e->dims, k_eff, sh.row_offset,
+                            sh.d_final, d_ids, c->stream, &launches, nullptr, &sp);
+        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+    }
+    CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
+    CUDA_TRY(cudaStreamSynchronize(c->stream));
+    CUDA_TRY(cudaEventElapsedTime(out_ms_total, c->ev0, c->ev1));
+    if (out_launches) *out_launches = launches;
+    return WAX_VS_OK;
+}
+
 // ---- filtered search -------------------------------------------------------------------
 // The reference filters AFTER the engine call and over-fetches 3 x topK to compensate (UnifiedSearch.swift:58,
 // 371-442, 1195-1200, 1241-1258).  Here the filter is pushed below the top-k: a row bitset consulted only for rows
@@ -1747,6 +2075,8 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_retry")) e->tune.batch_retry = v;
     else if (!strcmp(key, "filter_cap")) e->tune.filter_cap = v;
     else if (!strcmp(key, "single_shadow")) e->tune.single_shadow = v;
+    else if (!strcmp(key, "shard_fused")) e->tune.shard_fused = v;
+    else if (!strcmp(key, "shard_timeout_ms")) e->shard.timeout_ns = static_cast<unsigned long long>(std::max<int64_t>(value, 1)) * 1000000ull;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown option '%s'", key);

@@ -24,6 +24,7 @@
 //     same launch.
 #pragma once
 #include "waxvs_common.cuh"
+#include "waxvs_shard.cuh"
 #include "../../include/wax_vs_cuda.h"
 
 namespace waxvs {
@@ -46,6 +47,8 @@ struct ScanParams {
     uint32_t chunk_steps;       // > 0: dynamic scheduling, warps claim chunks of this many steps from work_counter
     uint32_t *work_counter;     // zero on entry, zero again on exit (reset by the last CTA)
     const uint32_t *mask;       // optional row filter: bit r of mask[r / 32] set = row r may be returned (nullptr = all)
+    ShardParams shard;          // shard.world > 0: `out` is this rank's local list and the last CTA goes on to exchange it
+                                // with the other ranks over NVLink and to merge (waxvs_shard.cuh): still the same launch
 };
 
 __device__ __forceinline__ bool row_allowed(const ScanParams &p, uint32_t row) {
@@ -132,6 +135,9 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
             if (j * 32 + lane < k) write_candidate(p, j * 32 + lane, tk.key[j]);
         if (lane == 0) { *p.ticket = 0u; if (p.work_counter) *p.work_counter = 0u; }
     }
+    // Row-sharded search: push the local list to every rank, wait for theirs, merge -- the block lists are done with,
+    // their shared memory holds the distance keys of the merge (the host checks that world * k * 4 bytes fit).
+    if (p.shard.world) shard_exchange_cta(p.shard, p.out, p.k, reinterpret_cast<uint32_t *>(lists));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -143,7 +149,7 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
 //          candidateLimit of 72, UnifiedSearch.swift:1195-1200, stays in the single launch)
 //   EMIT   false: fused top-k;  true: write orderable distance keys for the large-k select path
 template <int C, int R, int METRIC, int E, bool EMIT>
-__global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant__ ScanParams p) {
     const int D4 = C > 0 ? 32 * C : static_cast<int>(p.dims / 4u);          // float4 per row
     const int CN = C > 0 ? C : (D4 + 31) / 32;                               // chunks per lane
     const uint32_t ROW_BYTES = C > 0 ? 512u * C : p.dims * 4u;
@@ -333,7 +339,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const ScanParams p) {
 // Generic kernel: any dims (including dims % 4 != 0 and rows too large for a shared-memory tile).
 // One warp per row, coalesced direct global loads (LDG.128 when dims % 4 == 0), same accumulation order.
 template <int METRIC, int E, bool EMIT>
-__global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const ScanParams p) {
+__global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const __grid_constant__ ScanParams p) {
     __shared__ uint64_t lists[8 * 32 * E];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, warps = blockDim.x >> 5;
     const uint32_t dims = p.dims;

@@ -302,6 +302,43 @@ class CUDAVectorEngine:
     def reserve(self, rows: int) -> None:
         _check(L.lib().wax_vs_reserve(self._h, int(rows)))
 
+    # -- row-sharded search (wax_vs_shard_*; no reference counterpart) ------------------------------
+    def shard_open(self, rank: int, world: int, row_offset: int) -> bytes:
+        """Become rank `rank` of `world`: allocates this engine's mailbox and returns the handle blob the other ranks
+        need to reach it."""
+        blob = (C.c_uint8 * L.SHARD_HANDLE_BYTES)()
+        _check(L.lib().wax_vs_shard_open(self._h, int(rank), int(world), int(row_offset), blob))
+        return bytes(blob)
+
+    def shard_connect(self, blobs: Sequence[bytes]) -> None:
+        """Map every rank's mailbox (`blobs` in rank order, this rank's own included)."""
+        flat = b"".join(blobs)
+        buf = (C.c_uint8 * len(flat)).from_buffer_copy(flat)
+        _check(L.lib().wax_vs_shard_connect(self._h, buf, len(blobs)))
+
+    def shard_close(self) -> None:
+        _check(L.lib().wax_vs_shard_close(self._h))
+
+    def shard_search(self, vector: Sequence[float], top_k: int) -> List[Tuple[int, float]]:
+        """COLLECTIVE search over the whole sharded corpus (every rank calls it with the same query): scan + NVLink
+        exchange + merge in one kernel launch, merged result delivered into host memory."""
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        cap = _clamp_topk(top_k)
+        ids = np.empty(cap, np.uint64)
+        scores = np.empty(cap, np.float32)
+        n = C.c_uint32(0)
+        _check(L.lib().wax_vs_shard_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k),
+                                           ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                           scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
+        return [(int(ids[i]), float(scores[i])) for i in range(n.value)]
+
+    def time_shard_search(self, top_k: int, iters: int, warmup: int = 3, n_queries: int = 1, seed: int = 7):
+        """Device-timed collective searches, strictly one at a time on one stream. Returns (ms_total, launches)."""
+        ms, launches = C.c_float(0), C.c_uint64(0)
+        _check(L.lib().wax_vs_debug_time_shard_search(self._h, n_queries, int(top_k), seed, warmup, iters,
+                                                      C.byref(ms), C.byref(launches)))
+        return ms.value, launches.value
+
     # -- persistence (MV2V encoding = 2)
     def serialize(self) -> bytes:
         n = C.c_uint64(0)

@@ -1,10 +1,18 @@
 """Row-sharded vector search across GPUs: one process (rank) per GPU, one CUDA engine per rank.
 
 Design (BASELINE.json north_star): contiguous row ranges per rank, the query
-replicated, the identical fused kernel on every shard, ONE all-gather of the per-shard top-k candidates
-(k x 24 B per rank -- NCCL over NVLink when the group's backend is nccl) and a final host-side merge under
-the same total order (distance ascending, GLOBAL row ascending), so results do not depend on the shard
-count.  Nothing else is exchanged.
+replicated, the identical fused kernel on every shard, ONE exchange of the per-shard top-k candidates
+(k x 24 B per rank) and a merge under the same total order (distance ascending, GLOBAL row ascending), so
+results do not depend on the shard count.  Nothing else is exchanged.
+
+Two transports for that exchange:
+  * "p2p-fused" (default whenever the ranks can map each other's memory): the exchange is part of the scan launch --
+    the kernel's last CTA writes its candidates into every rank's mailbox over NVLink/NVSwitch peer memory, waits for
+    the others' flags and merges on the device, delivering the result into mapped host memory (wax_vs_shard_search,
+    wax_b200/csrc/waxvs_shard.cuh).  torch.distributed is used ONCE, at construction, to pass the 128-byte mailbox
+    handles around.  No collective launch, no D2H copy, no host merge per query.
+  * "allgather": torch.distributed all_gather_into_tensor (NCCL) + host merge -- k > 128, the micro-batched /
+    batched forms, and the CPU (gloo) tests of the host logic.
 
 The reference has no distributed code at all ("none exist"); this is the only
 parallelism the build adds.
@@ -99,8 +107,58 @@ class ShardedVectorEngine:
             # +15 % at 1.9 GB) and costs ~3 % when it is large (19 GB: twice the bytes in flight per SM), measured
             # in profiles/bench_r01_n*_m*.json -- so alternate streams only below 12 GB per shard.
             self._overlap_scans = (self.row_hi - self.row_lo) * self.dimensions * 4 < 12e9
+            self.transport = "allgather"
+            self.transport_note = ""
+            self._connect_peers()
         else:
             self.device = torch.device("cpu")
+            self.transport = "allgather"
+
+    def _connect_peers(self) -> None:
+        """Create this rank's mailbox, exchange the handles (one all-gather of 128 bytes per rank, the only use of
+        torch.distributed on this path) and map the peers' mailboxes.  All ranks agree on the outcome: if any rank
+        cannot map a peer (no P2P / IPC path) every rank stays on the all-gather transport."""
+        torch, dist = self._torch, self._dist
+        from . import _lib as L
+        from .engine import WaxError
+        blob, ok = bytes(L.SHARD_HANDLE_BYTES), self.world_size <= L.SHARD_MAX_RANKS
+        if ok:
+            try:
+                blob = self.engine.shard_open(self.rank, self.world_size, self.row_lo)
+            except WaxError as exc:
+                ok, self.transport_note = False, str(exc)
+        if self.world_size > 1:
+            dev = self.device if dist.get_backend(self.group) == "nccl" else torch.device("cpu")
+            mine = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(dev)
+            every = torch.empty(self.world_size * L.SHARD_HANDLE_BYTES, dtype=torch.uint8, device=dev)
+            dist.all_gather_into_tensor(every, mine, group=self.group)
+            flat = every.cpu().numpy().tobytes()
+            if ok:
+                try:
+                    self.engine.shard_connect([flat[i * L.SHARD_HANDLE_BYTES:(i + 1) * L.SHARD_HANDLE_BYTES]
+                                               for i in range(self.world_size)])
+                except WaxError as exc:
+                    ok, self.transport_note = False, str(exc)
+            flag = torch.tensor([1 if ok else 0], dtype=torch.int32, device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+            if ok and flag.item() != 1:
+                ok, self.transport_note = False, "another rank could not map its peers"
+        if ok:
+            self.transport = "p2p-fused"
+        else:
+            self.engine.shard_close()
+
+    def close(self) -> None:
+        """Collective: unmap the peers' mailboxes, agree that everyone has (barrier), then release the engine."""
+        if self.engine is None or getattr(self, "_closed", False):
+            return
+        self._closed = True
+        if self.transport == "p2p-fused":
+            self.engine.shard_close()
+            self.transport = "allgather"
+        if self.world_size > 1 and self._dist.is_initialized():
+            self._dist.barrier(group=self.group)
+        self.engine.close()
 
     # -- corpus
     def fill_synthetic(self, seed: int, normalize: bool = True) -> None:
@@ -357,5 +415,16 @@ class ShardedVectorEngine:
             return []
         if self._local_search is not None:
             return self.finish(self.search_async(q, top_k))
+        if self.transport == "p2p-fused" and clamp_topk(top_k) <= 128:
+            return self._search_fused(q, top_k)
         d_q = torch.from_numpy(q).to(self.device, non_blocking=False)
         return self.finish(self.search_async(d_q, top_k))
+
+    def _search_fused(self, q: np.ndarray, top_k: int) -> List[Tuple[int, float]]:
+        """wax_vs_shard_search: host query in, merged host result out; scan + NVLink exchange + merge in one launch."""
+        return self.engine.shard_search(q, top_k)
+
+    def time_search(self, top_k: int, iters: int, warmup: int = 3, n_queries: int = 1, seed: int = 7):
+        """Device-timed collective searches, strictly one at a time on one stream (the sharded twin of
+        CUDAVectorEngine.time_search).  Returns (ms_total, kernel launches)."""
+        return self.engine.time_shard_search(top_k, iters, warmup=warmup, n_queries=n_queries, seed=seed)
