@@ -93,6 +93,9 @@ int32_t wax_vs_reserve(wax_vs_engine *engine, uint64_t rows);
    dimensions (validate, :830-833). */
 int32_t wax_vs_add(wax_vs_engine *engine, uint64_t frame_id, const float *vector, uint32_t vector_len);
 
+/* Bulk transfers (add_batch, deserialize, serialize) move caller memory through two pinned staging buffers with the
+   host-side copy of one chunk overlapping the DMA of the other, so PAGEABLE caller buffers still reach PCIe speed;
+   caller memory that is already pinned is handed to the DMA engine directly. */
 /* addBatch(frameIds:vectors:) (MetalVectorEngine.swift:359-402): upsert n rows, `rows` is n x dims
    row-major (the Swift side flattens [[Float]]).  An id already present is overwritten in place
    (:385-389), a new id is appended at row N (:390-397); later duplicates inside one batch overwrite
@@ -103,6 +106,12 @@ int32_t wax_vs_add_batch(wax_vs_engine *engine, const uint64_t *frame_ids, const
 /* remove(frameId:) (MetalVectorEngine.swift:423-444): unknown id / empty engine = no-op rc 0 (:425-426);
    known id: row deleted, later rows keep their relative order (:431-441). */
 int32_t wax_vs_remove(wax_vs_engine *engine, uint64_t frame_id);
+
+/* remove(frameId:) for n frames in ONE pass (the reference memmoves the whole tail once per id,
+   MetalVectorEngine.swift:431-441): same result as n calls of wax_vs_remove in any order -- unknown / repeated ids
+   are ignored, surviving rows keep their relative order -- with one compaction of the matrix in HBM, one compaction
+   of the id array and one id->row hash rebuild.  *out_removed (optional) = rows actually deleted. */
+int32_t wax_vs_remove_batch(wax_vs_engine *engine, const uint64_t *frame_ids, uint64_t n, uint64_t *out_removed);
 
 /* ---- search ------------------------------------------------------------------------------------- */
 

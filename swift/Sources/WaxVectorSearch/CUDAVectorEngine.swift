@@ -150,6 +150,22 @@ public actor CUDAVectorEngine {
         dirty = true
     }
 
+    /// Many frames in one pass: one order-preserving compaction in HBM and one id-map rebuild instead of one
+    /// tail `memmove` per id (`MetalVectorEngine.swift:431-441`).  Unknown ids are ignored.
+    @discardableResult
+    public func removeBatch(frameIds: [UInt64]) async throws -> Int {
+        guard !frameIds.isEmpty else { return 0 }
+        let handle = self.handle
+        let removed: UInt64 = try await io.run {
+            var gone: UInt64 = 0
+            let rc = frameIds.withUnsafeBufferPointer { wax_vs_remove_batch(handle, $0.baseAddress, UInt64($0.count), &gone) }
+            guard rc == WAX_VS_OK else { throw Self.error(rc) }
+            return gone
+        }
+        if removed > 0 { dirty = true }
+        return Int(removed)
+    }
+
     public func serialize() async throws -> Data {
         let handle = self.handle
         return try await io.run {

@@ -41,6 +41,7 @@ SIGNATURES = {
     "wax_vs_add": (C.c_int32, [_eng, C.c_uint64, _f32p, C.c_uint32]),
     "wax_vs_add_batch": (C.c_int32, [_eng, _u64p, _f32p, C.c_uint64, C.c_uint32]),
     "wax_vs_remove": (C.c_int32, [_eng, C.c_uint64]),
+    "wax_vs_remove_batch": (C.c_int32, [_eng, _u64p, C.c_uint64, _u64p]),
     "wax_vs_search": (C.c_int32, [_eng, _f32p, C.c_uint32, C.c_int64, _u64p, _f32p, C.c_uint32, _u32p]),
     "wax_vs_search_filtered": (C.c_int32, [_eng, _f32p, C.c_uint32, C.c_int64, _u64p, C.c_uint64, C.c_int32, _u64p, _f32p,
                                            C.c_uint32, _u32p]),

@@ -199,16 +199,30 @@ struct wax_vs_engine {
     // cached per corpus version for the batched path: 1/|v| per row and max |v|
     float *d_inv_norm = nullptr; size_t inv_norm_cap = 0;
     uint32_t *d_max_norm = nullptr;
-    bool norms_valid = false;
+    uint64_t norms_rows = 0;       // rows [0, norms_rows) of d_inv_norm are valid (appends extend it, other mutations reset it)
     std::mutex norms_mu;
     // bf16 shadow of the corpus for the batched bf16 nominations (cached per corpus version, guarded by norms_mu)
     __nv_bfloat16 *d_shadow = nullptr; size_t shadow_cap = 0;
+    uint64_t shadow_rows = 0;      // rows [0, shadow_rows) of d_shadow are valid; shadow_valid = covers every live row
     bool shadow_valid = false, shadow_unavailable = false;
     uint64_t batch_tensor_queries = 0, batch_fallback_queries = 0;   // instrumentation
     uint64_t batch_bf16_queries = 0, batch_retry_queries = 0, batch_tf32_queries = 0;
     // Adaptive level choice: when more than a quarter of a batch fails the coarse bf16 bound (tightly clustered
     // neighbours), the next 16 batches nominate in TF32 straight away, then bf16 is probed again.
     uint32_t bf16_skip_batches = 0;
+    // Bulk ingest / export staging: two pinned buffers so that the host-side copy of chunk i+1 overlaps
+    // the DMA of chunk i, one copy stream, a device staging area for upserts and for the compaction of removes.
+    struct Ingest {
+        cudaStream_t stream = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        uint8_t *pin[2] = {nullptr, nullptr};
+        size_t pin_bytes = 0;
+        float *d_stage = nullptr; size_t d_stage_cap = 0;        // floats
+        uint32_t *d_index = nullptr; size_t d_index_cap = 0;     // u32
+        int threads = 1;
+    } ing;
+    uint64_t ingest_h2d_bytes = 0, ingest_d2h_bytes = 0;         // instrumentation
+    std::mutex ingest_mu;                                        // readers that use the staging (serialize)
     std::mutex attr_mu;            // cudaFuncSetAttribute bookkeeping (per engine = per device)
     bool sort_attr_set = false, gather_attr_set = false, batch_attr_set = false;
     std::unordered_map<const void *, int> smem_granted;   // opt-in shared memory already granted, per kernel (attr_mu)
@@ -234,11 +248,18 @@ struct wax_vs_engine {
     } shard;
 };
 
-extern "C" { static void shard_teardown(wax_vs_engine *e, bool free_own); }
+extern "C" { static void shard_teardown(wax_vs_engine *e, bool free_own); static void ingest_free(wax_vs_engine *e); }
 
 // Called by every mutator after it has taken the write lock (and selected the device).
 static void drain_device_path(wax_vs_engine *e) {
     if (e->async_pending.exchange(false)) cudaDeviceSynchronize();
+}
+// Derived per-row caches (1/|v|, bf16 shadow) after a mutation.  keep_prefix: rows [0, keep_prefix) are untouched (a pure
+// append keeps everything it had); 0 = rebuild from scratch on the next batched search.
+static void invalidate_row_caches(wax_vs_engine *e, uint64_t keep_prefix) {
+    e->norms_rows = std::min(e->norms_rows, keep_prefix);
+    e->shadow_rows = std::min(e->shadow_rows, keep_prefix);
+    if (e->shadow_rows == 0) e->shadow_valid = false;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -593,18 +614,28 @@ static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, ui
            k_eff >= 1 && k_eff <= 128 && e->n_rows >= 1;
 }
 
-// 1/|v| per row + max |v|, cached until the corpus changes.
+// 1/|v| per row + max |v|, cached per corpus version.  Appends only extend the cache (rows [norms_rows, n_rows) are
+// computed, the running max only grows); anything that moves or overwrites rows resets norms_rows to 0.
 static int32_t ensure_norms_locked(wax_vs_engine *e, cudaStream_t stream) {
-    if (e->norms_valid) return WAX_VS_OK;
-    int32_t rc = ensure_dev(&e->d_inv_norm, &e->inv_norm_cap, static_cast<size_t>(std::max<uint64_t>(e->n_rows, 1)), "row norms");
-    if (rc) return rc;
-    if (!e->d_max_norm) CUDA_TRY(cudaMalloc(&e->d_max_norm, sizeof(uint32_t)));
-    CUDA_TRY(cudaMemsetAsync(e->d_max_norm, 0, sizeof(uint32_t), stream));
-    row_norms_kernel<<<e->sm_count * 8, 256, 0, stream>>>(e->d_corpus, static_cast<uint32_t>(e->n_rows), e->dims,
-                                                           e->d_inv_norm, e->d_max_norm);
-    CUDA_TRY(cudaGetLastError());
+    if (e->norms_rows == e->n_rows && e->d_inv_norm) return WAX_VS_OK;
+    if (static_cast<size_t>(e->n_rows) > e->inv_norm_cap || !e->d_inv_norm) {
+        e->norms_rows = 0;                                       // ensure_dev re-allocates: the cached prefix is gone
+        const size_t want = static_cast<size_t>(std::max<uint64_t>(e->cap_rows, std::max<uint64_t>(e->n_rows, 1)));
+        int32_t rc = ensure_dev(&e->d_inv_norm, &e->inv_norm_cap, want, "row norms");
+        if (rc) return rc;
+    }
+    if (!e->d_max_norm) { CUDA_TRY(cudaMalloc(&e->d_max_norm, sizeof(uint32_t))); e->norms_rows = 0; }
+    if (e->norms_rows > e->n_rows) e->norms_rows = 0;
+    if (e->norms_rows == 0) CUDA_TRY(cudaMemsetAsync(e->d_max_norm, 0, sizeof(uint32_t), stream));
+    const uint64_t first = e->norms_rows, count = e->n_rows - first;
+    if (count) {
+        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * 8, (count + 7) / 8));
+        row_norms_kernel<<<std::max(grid, 1), 256, 0, stream>>>(e->d_corpus + first * e->dims, static_cast<uint32_t>(count), e->dims,
+                                                                e->d_inv_norm + first, e->d_max_norm);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
-    e->norms_valid = true;
+    e->norms_rows = e->n_rows;
     return WAX_VS_OK;
 }
 static int32_t ensure_norms(wax_vs_engine *e, cudaStream_t stream) {
@@ -617,33 +648,45 @@ static bool batch_bf16_wanted(const wax_vs_engine *e) {
     return e->tune.batch_bf16 != 0 && e->dims % kBatchKBlockBf16 == 0 && !e->shadow_unavailable;
 }
 
-// bf16 shadow of the corpus (cosine: rows pre-scaled by 1/|v|), cached until the corpus changes.  Returns
-// WAX_VS_OK with e->shadow_valid == false when the extra dims*2 bytes per row do not fit in HBM (the caller then
-// nominates in TF32 from the fp32 corpus).
+// bf16 shadow of the corpus (cosine: rows pre-scaled by 1/|v|), cached per corpus version and extended incrementally
+// by appends like the norms.  Returns WAX_VS_OK with e->shadow_valid == false when the extra dims*2 bytes per row do
+// not fit in HBM (the caller then nominates in TF32 from the fp32 corpus; counter "shadow_unavailable").
 static int32_t ensure_shadow(wax_vs_engine *e, cudaStream_t stream) {
     std::lock_guard<std::mutex> g(e->norms_mu);
-    if (e->shadow_valid || e->shadow_unavailable) return WAX_VS_OK;
+    if ((e->shadow_valid && e->shadow_rows == e->n_rows) || e->shadow_unavailable) return WAX_VS_OK;
     int32_t rc = ensure_norms_locked(e, stream);
     if (rc) return rc;
-    const size_t need = static_cast<size_t>(e->n_rows) * e->dims;
+    const size_t need = static_cast<size_t>(e->n_rows) * e->dims;                                  // must hold
+    const size_t pref = static_cast<size_t>(std::max<uint64_t>(e->cap_rows, e->n_rows)) * e->dims;   // would like
     if (e->shadow_cap < need) {
         if (e->d_shadow) { cudaFree(e->d_shadow); e->d_shadow = nullptr; e->shadow_cap = 0; }
+        e->shadow_rows = 0; e->shadow_valid = false;
         size_t free_b = 0, total_b = 0;
-        const size_t bytes = need * sizeof(__nv_bfloat16);
-        // keep headroom for scratch and growth: the shadow must leave max(2 GiB, 10 % of the device) free
-        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess ||
-            free_b < bytes + std::max<size_t>(size_t(2) << 30, total_b / 10) ||
-            cudaMalloc(&e->d_shadow, bytes) != cudaSuccess) {
+        size_t want = pref;
+        size_t bytes = want * sizeof(__nv_bfloat16);
+        // keep headroom for scratch and growth: the shadow must leave max(2 GiB, 10 % of the device) free.  Sized for
+        // the corpus CAPACITY so that appends extend it in place; if only the live rows fit, take that.
+        const bool info = cudaMemGetInfo(&free_b, &total_b) == cudaSuccess;
+        const size_t headroom = std::max<size_t>(size_t(2) << 30, total_b / 10);
+        if (info && free_b < bytes + headroom) { want = need; bytes = want * sizeof(__nv_bfloat16); }
+        if (!info || free_b < bytes + headroom || cudaMalloc(&e->d_shadow, bytes) != cudaSuccess) {
             cudaGetLastError();
             e->shadow_unavailable = true;      // stays off for this engine: TF32 nominations need no extra memory
             return WAX_VS_OK;
         }
-        e->shadow_cap = need;
+        e->shadow_cap = want;
     }
-    shadow_bf16_kernel<<<e->sm_count * 16, 256, 0, stream>>>(e->d_corpus, e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr,
-                                                             e->n_rows, e->dims, e->d_shadow);
-    CUDA_TRY(cudaGetLastError());
+    if (e->shadow_rows > e->n_rows) e->shadow_rows = 0;
+    const uint64_t first = e->shadow_rows, count = e->n_rows - first;
+    if (count) {
+        const int grid = static_cast<int>(std::min<uint64_t>(static_cast<uint64_t>(e->sm_count) * 16, (count * (e->dims / 4) + 255) / 256));
+        shadow_bf16_kernel<<<std::max(grid, 1), 256, 0, stream>>>(e->d_corpus + first * e->dims,
+                                                                  e->similarity == WAX_VS_COSINE ? e->d_inv_norm + first : nullptr,
+                                                                  count, e->dims, e->d_shadow + first * e->dims);
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaStreamSynchronize(stream));
+    e->shadow_rows = e->n_rows;
     e->shadow_valid = true;
     return WAX_VS_OK;
 }
@@ -868,7 +911,7 @@ static int32_t set_capacity(wax_vs_engine *e, uint64_t rows) {
         // the bf16 shadow is derived data: give its HBM back before giving up (mutators hold the write lock)
         cudaGetLastError();
         if (e->d_shadow) {
-            cudaFree(e->d_shadow); e->d_shadow = nullptr; e->shadow_cap = 0; e->shadow_valid = false;
+            cudaFree(e->d_shadow); e->d_shadow = nullptr; e->shadow_cap = 0; e->shadow_valid = false; e->shadow_rows = 0;
             e->shadow_unavailable = true;
         }
         if (cudaMalloc(&n, bytes) != cudaSuccess)
@@ -985,6 +1028,7 @@ void wax_vs_destroy(wax_vs_engine *e) {
         DeviceGuard g(e->device);
         cudaDeviceSynchronize();
         shard_teardown(e, true);
+        ingest_free(e);
         for (SearchCtx *c : e->pool) ctx_free(c);
         for (auto &kv : e->stream_ctx) ctx_free(kv.second);
         if (e->d_corpus) cudaFree(e->d_corpus);
@@ -1024,6 +1068,131 @@ int32_t wax_vs_reserve(wax_vs_engine *e, uint64_t rows) {
     return set_capacity(e, rows);
 }
 
+// ---- bulk ingest / export plumbing ---------------------------------------------------------------
+// Host <-> HBM at device speed from PAGEABLE caller memory: the bytes go through two pinned staging buffers; worker
+// threads fill (or drain) one buffer while the DMA engine moves the other.  Caller memory that is already pinned
+// (cudaHostAlloc / cudaHostRegister) is handed to the DMA engine directly.
+static int32_t ingest_init(wax_vs_engine *e) {
+    auto &g = e->ing;
+    if (g.stream) return WAX_VS_OK;
+    CUDA_TRY(cudaStreamCreateWithFlags(&g.stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) CUDA_TRY(cudaEventCreateWithFlags(&g.ev[i], cudaEventDisableTiming));
+    unsigned hw = std::thread::hardware_concurrency();
+    long quota = 0, period = 0;                       // cgroup v2 CPU quota, when there is one
+    if (FILE *f = fopen("/sys/fs/cgroup/cpu.max", "r")) {
+        char q[32] = "";
+        if (fscanf(f, "%31s %ld", q, &period) == 2 && strcmp(q, "max") != 0) quota = atol(q);
+        fclose(f);
+    }
+    if (quota > 0 && period > 0) hw = static_cast<unsigned>(std::max<long>(1, std::min<long>(hw ? hw : 1, (quota + period / 2) / period)));
+    g.threads = static_cast<int>(std::max(1u, std::min(8u, hw ? hw : 1u)));
+    return WAX_VS_OK;
+}
+static int32_t ingest_staging(wax_vs_engine *e, size_t want_bytes) {
+    auto &g = e->ing;
+    int32_t rc = ingest_init(e);
+    if (rc) return rc;
+    const size_t chunk = std::min<size_t>(size_t(64) << 20, std::max<size_t>(size_t(1) << 20, want_bytes));
+    if (g.pin_bytes >= chunk) return WAX_VS_OK;
+    for (int i = 0; i < 2; ++i) {
+        if (g.pin[i]) { cudaFreeHost(g.pin[i]); g.pin[i] = nullptr; }
+        g.pin_bytes = 0;
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g.pin[i]), chunk, cudaHostAllocDefault) != cudaSuccess)
+            return fail(WAX_VS_ERR_CUDA, "failed to allocate pinned ingest staging (%zu bytes): %s", chunk, cudaGetErrorString(cudaGetLastError()));
+    }
+    g.pin_bytes = chunk;
+    return WAX_VS_OK;
+}
+static void ingest_free(wax_vs_engine *e) {
+    auto &g = e->ing;
+    for (int i = 0; i < 2; ++i) {
+        if (g.pin[i]) cudaFreeHost(g.pin[i]);
+        if (g.ev[i]) cudaEventDestroy(g.ev[i]);
+        g.pin[i] = nullptr; g.ev[i] = nullptr;
+    }
+    if (g.d_stage) cudaFree(g.d_stage);
+    if (g.d_index) cudaFree(g.d_index);
+    if (g.stream) cudaStreamDestroy(g.stream);
+    g = wax_vs_engine::Ingest();
+}
+
+static void parallel_memcpy(void *dst, const void *src, size_t bytes, int threads) {
+    const size_t min_slice = size_t(2) << 20;
+    int t = static_cast<int>(std::min<size_t>(static_cast<size_t>(std::max(threads, 1)), std::max<size_t>(1, bytes / min_slice)));
+    if (t <= 1) { memcpy(dst, src, bytes); return; }
+    std::vector<std::thread> pool;
+    pool.reserve(static_cast<size_t>(t - 1));
+    const size_t per = ((bytes + t - 1) / t + 63) & ~size_t(63);
+    for (int i = 1; i < t; ++i) {
+        const size_t off = std::min(bytes, per * i), len = std::min(bytes - off, per);
+        if (len) pool.emplace_back([=] { memcpy(static_cast<char *>(dst) + off, static_cast<const char *>(src) + off, len); });
+    }
+    memcpy(dst, src, std::min(bytes, per));
+    for (auto &th : pool) th.join();
+}
+
+static bool host_pointer_is_pinned(const void *p) {
+    cudaPointerAttributes at{};
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return at.type == cudaMemoryTypeHost;
+}
+
+// host (pageable or pinned) -> device, synchronous on return
+static int32_t upload_bytes(wax_vs_engine *e, void *d_dst, const void *h_src, size_t bytes) {
+    if (bytes == 0) return WAX_VS_OK;
+    int32_t rc = ingest_staging(e, bytes);
+    if (rc) return rc;
+    auto &g = e->ing;
+    e->ingest_h2d_bytes += bytes;
+    if (host_pointer_is_pinned(h_src)) {
+        CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        return WAX_VS_OK;
+    }
+    size_t off = 0;
+    for (int i = 0; off < bytes; ++i) {
+        const int b = i & 1;
+        const size_t len = std::min(g.pin_bytes, bytes - off);
+        CUDA_TRY(cudaEventSynchronize(g.ev[b]));                 // the DMA that last read this buffer is done
+        parallel_memcpy(g.pin[b], static_cast<const char *>(h_src) + off, len, g.threads);
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, g.pin[b], len, cudaMemcpyHostToDevice, g.stream));
+        CUDA_TRY(cudaEventRecord(g.ev[b], g.stream));
+        off += len;
+    }
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return WAX_VS_OK;
+}
+
+// device -> host (pageable or pinned), synchronous on return
+static int32_t download_bytes(wax_vs_engine *e, void *h_dst, const void *d_src, size_t bytes) {
+    if (bytes == 0) return WAX_VS_OK;
+    int32_t rc = ingest_staging(e, bytes);
+    if (rc) return rc;
+    auto &g = e->ing;
+    e->ingest_d2h_bytes += bytes;
+    if (host_pointer_is_pinned(h_dst)) {
+        CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, g.stream));
+        CUDA_TRY(cudaStreamSynchronize(g.stream));
+        return WAX_VS_OK;
+    }
+    const size_t n_chunks = (bytes + g.pin_bytes - 1) / g.pin_bytes;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * g.pin_bytes, len = std::min(g.pin_bytes, bytes - off);
+        cudaError_t err = cudaMemcpyAsync(g.pin[i & 1], static_cast<const char *>(d_src) + off, len, cudaMemcpyDeviceToHost, g.stream);
+        if (err == cudaSuccess) err = cudaEventRecord(g.ev[i & 1], g.stream);
+        return err;
+    };
+    CUDA_TRY(issue(0));
+    for (size_t i = 0; i < n_chunks; ++i) {
+        if (i + 1 < n_chunks) CUDA_TRY(issue(i + 1));            // its buffer was drained in iteration i-1
+        CUDA_TRY(cudaEventSynchronize(g.ev[i & 1]));
+        const size_t off = i * g.pin_bytes, len = std::min(g.pin_bytes, bytes - off);
+        parallel_memcpy(static_cast<char *>(h_dst) + off, g.pin[i & 1], len, g.threads);
+    }
+    CUDA_TRY(cudaStreamSynchronize(g.stream));
+    return WAX_VS_OK;
+}
+
 int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const float *rows, uint64_t n,
                          uint32_t vector_len) {
     if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
@@ -1055,12 +1224,12 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
         if (row != n0 + i) pure_append = false;
     }
     e->d_ids_dirty = true;
-    e->norms_valid = false; e->shadow_valid = false;
     const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
     if (pure_append) {
-        CUDA_TRY(cudaMemcpy(e->d_corpus + n0 * e->dims, rows, n * row_bytes, cudaMemcpyHostToDevice));
-        return WAX_VS_OK;
+        invalidate_row_caches(e, n0);          // the cached norms / shadow of rows [0, n0) stay valid
+        return upload_bytes(e, e->d_corpus + n0 * e->dims, rows, n * row_bytes);
     }
+    invalidate_row_caches(e, 0);
     // Overwrites present: a later item for the same row wins; earlier ones are dropped.
     {
         std::unordered_map<uint32_t, uint64_t> last;
@@ -1068,20 +1237,20 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
         for (uint64_t i = 0; i < n; ++i) last[target[i]] = i;
         for (uint64_t i = 0; i < n; ++i) if (last[target[i]] != i) target[i] = 0xFFFFFFFFu;
     }
-    float *d_stage = nullptr; uint32_t *d_target = nullptr;
-    if (cudaMalloc(&d_stage, n * row_bytes) != cudaSuccess || cudaMalloc(&d_target, n * sizeof(uint32_t)) != cudaSuccess) {
-        if (d_stage) cudaFree(d_stage);
-        return fail(WAX_VS_ERR_CUDA, "failed to allocate upsert staging: %s", cudaGetErrorString(cudaGetLastError()));
+    // Staged in HBM (persistent staging area, grown on demand) and scattered by one kernel: no per-call allocation.
+    auto &ig = e->ing;
+    if ((rc = ingest_init(e))) return rc;
+    const uint64_t slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(n, (size_t(256) << 20) / row_bytes));
+    if ((rc = ensure_dev(&ig.d_stage, &ig.d_stage_cap, static_cast<size_t>(slab_rows) * e->dims, "upsert staging"))) return rc;
+    if ((rc = ensure_dev(&ig.d_index, &ig.d_index_cap, static_cast<size_t>(slab_rows), "upsert targets"))) return rc;
+    for (uint64_t done = 0; done < n; done += slab_rows) {
+        const uint64_t m = std::min(slab_rows, n - done);
+        if ((rc = upload_bytes(e, ig.d_stage, rows + done * e->dims, m * row_bytes))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(ig.d_index, target.data() + done, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ig.stream));
+        scatter_rows_kernel<<<static_cast<unsigned>(m), 128, 0, ig.stream>>>(e->d_corpus, ig.d_stage, ig.d_index, m, e->dims);
+        CUDA_TRY(cudaGetLastError());
+        CUDA_TRY(cudaStreamSynchronize(ig.stream));
     }
-    cudaError_t err = cudaMemcpy(d_stage, rows, n * row_bytes, cudaMemcpyHostToDevice);
-    if (err == cudaSuccess) err = cudaMemcpy(d_target, target.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice);
-    if (err == cudaSuccess) {
-        scatter_rows_kernel<<<static_cast<unsigned>(n), 256>>>(e->d_corpus, d_stage, d_target, n, e->dims);
-        err = cudaGetLastError();
-        if (err == cudaSuccess) err = cudaDeviceSynchronize();
-    }
-    cudaFree(d_stage); cudaFree(d_target);
-    if (err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "upsert failed: %s", cudaGetErrorString(err));
     return WAX_VS_OK;
 }
 
@@ -1089,46 +1258,89 @@ int32_t wax_vs_add(wax_vs_engine *e, uint64_t frame_id, const float *vector, uin
     return wax_vs_add_batch(e, &frame_id, vector, 1, vector_len);
 }
 
-int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
+// remove(frameId:) for a whole set of frames (MetalVectorEngine.swift:423-444 applied n times, as ONE pass): unknown ids
+// are ignored (:426), the surviving rows keep their relative order (:431-441).  The reference memmoves the tail once
+// per id; here the survivors' source rows are computed once on the host, the matrix is compacted slab by slab through
+// an HBM bounce buffer (gather kernel + copy back: destinations never overtake unread sources because rows only move
+// down and slabs go in ascending order), the id array is compacted once and the id->row hash rebuilt once.
+int32_t wax_vs_remove_batch(wax_vs_engine *e, const uint64_t *frame_ids, uint64_t n, uint64_t *out_removed) {
     if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
+    if (out_removed) *out_removed = 0;
+    if (n == 0) return WAX_VS_OK;
+    if (!frame_ids) return fail(WAX_VS_ERR_NULL, "frame_ids is NULL");
     std::unique_lock<std::shared_mutex> w(e->rw);
     if (e->n_rows == 0) return WAX_VS_OK;  // :425
-    uint64_t index;
+    // which rows go
+    std::vector<uint32_t> gone;
+    gone.reserve(n);
     if (e->ids_identity) {
-        if (frame_id < e->id_base || frame_id - e->id_base >= e->n_rows) return WAX_VS_OK;
-        index = frame_id - e->id_base;
-        materialize_ids(e);
+        for (uint64_t i = 0; i < n; ++i)
+            if (frame_ids[i] >= e->id_base && frame_ids[i] - e->id_base < e->n_rows) gone.push_back(static_cast<uint32_t>(frame_ids[i] - e->id_base));
     } else {
         ensure_map(e);
-        const uint32_t r = e->map.find(frame_id);
-        if (r == 0xFFFFFFFFu) return WAX_VS_OK;  // :426
-        index = r;
+        for (uint64_t i = 0; i < n; ++i) {
+            const uint32_t r = e->map.find(frame_ids[i]);
+            if (r != 0xFFFFFFFFu) gone.push_back(r);                // :426 unknown id = no-op
+        }
     }
+    if (gone.empty()) return WAX_VS_OK;
+    std::sort(gone.begin(), gone.end());
+    gone.erase(std::unique(gone.begin(), gone.end()), gone.end());
     DeviceGuard g(e->device);
     drain_device_path(e);
-    const uint64_t after = e->n_rows - 1 - index;  // countAfter (:431)
-    if (after > 0) {
-        // memmove of the tail (:433-437) through a bounce buffer, ascending chunks (dst < src).
-        const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
-        const uint64_t chunk_rows = std::max<uint64_t>(1, std::min<uint64_t>(after, (256ull << 20) / row_bytes));
-        float *bounce = nullptr;
-        CUDA_TRY(cudaMalloc(&bounce, chunk_rows * row_bytes));
-        cudaError_t err = cudaSuccess;
-        for (uint64_t done = 0; done < after && err == cudaSuccess; done += chunk_rows) {
-            const uint64_t m = std::min(chunk_rows, after - done);
-            err = cudaMemcpy(bounce, e->d_corpus + (index + 1 + done) * e->dims, m * row_bytes, cudaMemcpyDeviceToDevice);
-            if (err == cudaSuccess)
-                err = cudaMemcpy(e->d_corpus + (index + done) * e->dims, bounce, m * row_bytes, cudaMemcpyDeviceToDevice);
+    materialize_ids(e);
+    const uint64_t old_n = e->n_rows, first = gone.front(), new_n = old_n - gone.size();
+    // source row of every destination row >= first (rows below the first removed row do not move)
+    std::vector<uint32_t> src;
+    src.reserve(static_cast<size_t>(new_n - first));
+    {
+        size_t gi = 0;
+        for (uint64_t r = first; r < old_n; ++r) {
+            if (gi < gone.size() && gone[gi] == r) { ++gi; continue; }
+            src.push_back(static_cast<uint32_t>(r));
         }
-        cudaFree(bounce);
-        if (err != cudaSuccess) return fail(WAX_VS_ERR_CUDA, "remove failed: %s", cudaGetErrorString(err));
     }
-    e->ids.erase(e->ids.begin() + static_cast<std::ptrdiff_t>(index));  // :440
-    --e->n_rows;
+    int32_t rc = ingest_init(e);
+    if (rc) return rc;
+    auto &ig = e->ing;
+    const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
+    const uint64_t moving = src.size();
+    if (moving) {
+        const uint64_t slab_rows = std::max<uint64_t>(1, std::min<uint64_t>(moving, (size_t(256) << 20) / row_bytes));
+        if ((rc = ensure_dev(&ig.d_stage, &ig.d_stage_cap, static_cast<size_t>(slab_rows) * e->dims, "compaction bounce buffer"))) return rc;
+        if ((rc = ensure_dev(&ig.d_index, &ig.d_index_cap, static_cast<size_t>(slab_rows), "compaction sources"))) return rc;
+        if ((rc = ingest_staging(e, slab_rows * sizeof(uint32_t)))) return rc;
+        for (uint64_t done = 0; done < moving; done += slab_rows) {
+            const uint64_t m = std::min(slab_rows, moving - done);
+            // contiguous runs (nothing removed inside the slab) are a plain device copy; otherwise gather by index
+            const bool contiguous = src[done + m - 1] - src[done] == m - 1;
+            float *dst = e->d_corpus + (first + done) * e->dims;
+            if (contiguous) {
+                CUDA_TRY(cudaMemcpyAsync(ig.d_stage, e->d_corpus + static_cast<uint64_t>(src[done]) * e->dims, m * row_bytes,
+                                         cudaMemcpyDeviceToDevice, ig.stream));
+            } else {
+                CUDA_TRY(cudaMemcpyAsync(ig.d_index, src.data() + done, m * sizeof(uint32_t), cudaMemcpyHostToDevice, ig.stream));
+                const unsigned grid = static_cast<unsigned>(std::min<uint64_t>(m, static_cast<uint64_t>(e->sm_count) * 32));
+                gather_rows_kernel<<<grid, 128, 0, ig.stream>>>(ig.d_stage, e->d_corpus, ig.d_index, m, e->dims);
+                CUDA_TRY(cudaGetLastError());
+            }
+            CUDA_TRY(cudaMemcpyAsync(dst, ig.d_stage, m * row_bytes, cudaMemcpyDeviceToDevice, ig.stream));
+            CUDA_TRY(cudaStreamSynchronize(ig.stream));          // src / d_index are reused by the next slab
+        }
+    }
+    // ids: one compaction, one hash rebuild (lazily, on the next lookup)
+    for (uint64_t j = 0; j < moving; ++j) e->ids[first + j] = e->ids[src[j]];
+    e->ids.resize(new_n);
+    e->n_rows = new_n;
     e->map_valid = false;
     e->d_ids_dirty = true;
-    e->norms_valid = false; e->shadow_valid = false;
+    invalidate_row_caches(e, first);           // rows below the first removed row did not move
+    if (out_removed) *out_removed = gone.size();
     return WAX_VS_OK;
+}
+
+int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
+    return wax_vs_remove_batch(e, &frame_id, 1, nullptr);
 }
 
 // Filter level (level 2 of the batched path): for queries level 1 could not prove.  One TF32 tensor-core pass in
@@ -1812,7 +2024,11 @@ int32_t wax_vs_serialize(wax_vs_engine *e, uint8_t *dst, uint64_t cap, uint64_t 
     const uint64_t vbytes = e->n_rows * e->dims * 4ull;
     memcpy(p, &vbytes, 8); p += 8;                                // :697-699
     memset(p, 0, 8); p += 8;                                      // reserved (:700)
-    if (vbytes) CUDA_TRY(cudaMemcpy(p, e->d_corpus, vbytes, cudaMemcpyDeviceToHost));  // :703-705
+    if (vbytes) {                                                 // :703-705, through the pinned double-buffered D2H pipeline
+        std::lock_guard<std::mutex> ig(e->ingest_mu);             // serialize holds only the READ lock: one exporter at a time
+        int32_t rc = download_bytes(e, p, e->d_corpus, vbytes);
+        if (rc) return rc;
+    }
     p += vbytes;
     const uint64_t ibytes = e->n_rows * 8ull;
     memcpy(p, &ibytes, 8); p += 8;                                // :707-709
@@ -1853,14 +2069,14 @@ int32_t wax_vs_deserialize(wax_vs_engine *e, const uint8_t *src, uint64_t len) {
     drain_device_path(e);
     int32_t rc = set_capacity(e, std::max<uint64_t>(count, 64));  // reservedCapacity = max(...) (:791-792)
     if (rc) return rc;
-    if (vbytes) CUDA_TRY(cudaMemcpy(e->d_corpus, src + 36, vbytes, cudaMemcpyHostToDevice));  // :794-799
+    if (vbytes && (rc = upload_bytes(e, e->d_corpus, src + 36, vbytes))) return rc;  // :794-799, pinned double-buffered H2D
     e->n_rows = count;
     e->ids.resize(count);
     if (count) memcpy(e->ids.data(), src + 36 + vbytes + 8, ibytes);  // :809-811
     e->ids_identity = false;
     e->map_valid = false;
     e->d_ids_dirty = true;
-    e->norms_valid = false; e->shadow_valid = false;
+    invalidate_row_caches(e, 0);
     return WAX_VS_OK;
 }
 
@@ -1894,7 +2110,7 @@ int32_t wax_vs_debug_fill_synthetic(wax_vs_engine *e, uint64_t seed, uint64_t fi
     e->ids_identity = true; e->id_base = id_base;
     e->map = IdMap(); e->map_valid = true;
     e->d_ids_dirty = true;
-    e->norms_valid = false; e->shadow_valid = false;
+    invalidate_row_caches(e, 0);
     return WAX_VS_OK;
 }
 
@@ -2003,6 +2219,10 @@ int32_t wax_vs_debug_counter(wax_vs_engine *e, const char *name, uint64_t *out) 
     else if (!strcmp(name, "shadow_bytes")) *out = e->shadow_valid ? e->shadow_cap * sizeof(__nv_bfloat16) : 0;
     else if (!strcmp(name, "shadow_unavailable")) *out = e->shadow_unavailable ? 1 : 0;   // bf16 shadow did not fit: TF32 level runs
     else if (!strcmp(name, "batch_tf32_queries")) *out = e->batch_tf32_queries;
+    else if (!strcmp(name, "ingest_h2d_bytes")) *out = e->ingest_h2d_bytes;
+    else if (!strcmp(name, "ingest_d2h_bytes")) *out = e->ingest_d2h_bytes;
+    else if (!strcmp(name, "norms_rows")) *out = e->norms_rows;       // rows whose cached 1/|v| is valid
+    else if (!strcmp(name, "shadow_rows")) *out = e->shadow_rows;     // rows whose bf16 shadow is valid
     else if (!strcmp(name, "pool_allocs")) *out = e->pool_allocs;
     else if (!strcmp(name, "pool_reuses")) *out = e->pool_reuses;
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown counter '%s'", name);

@@ -57,6 +57,22 @@ __global__ void __launch_bounds__(256) scatter_rows_kernel(float *corpus, const 
     for (uint32_t i = threadIdx.x; i < dims; i += blockDim.x) dst[i] = src[i];
 }
 
+// Order-preserving compaction (wax_vs_remove_batch): bounce row i <- corpus row src[i].  float4 when the rows allow it.
+__global__ void __launch_bounds__(128) gather_rows_kernel(float *__restrict__ bounce, const float *__restrict__ corpus,
+                                                          const uint32_t *__restrict__ src, uint64_t n, uint32_t dims) {
+    for (uint64_t row = blockIdx.x; row < n; row += gridDim.x) {
+        const float *s = corpus + static_cast<uint64_t>(src[row]) * dims;
+        float *d = bounce + row * dims;
+        if ((dims & 3u) == 0u) {
+            const float4 *s4 = reinterpret_cast<const float4 *>(s);
+            float4 *d4 = reinterpret_cast<float4 *>(d);
+            for (uint32_t i = threadIdx.x; i < dims / 4u; i += blockDim.x) d4[i] = __ldcs(s4 + i);
+        } else {
+            for (uint32_t i = threadIdx.x; i < dims; i += blockDim.x) d[i] = s[i];
+        }
+    }
+}
+
 // Read-only streaming ceiling: every thread LDG.128s a grid-stride slice and folds it into one word.  Used by
 // bench.py to report what a plain coalesced read of the same bytes achieves on the same box.
 __global__ void __launch_bounds__(512) stream_read_kernel(const uint4 *__restrict__ src, uint64_t n_vec,

@@ -299,6 +299,18 @@ class CUDAVectorEngine:
         if self.count != before:
             self._dirty = True
 
+    def remove_batch(self, frame_ids: Sequence[int]) -> int:
+        """remove(frameId:) for many frames in one pass (one compaction, one hash rebuild); returns how many rows went.
+        Same result as calling remove() for each id."""
+        ids = np.ascontiguousarray(frame_ids, dtype=np.uint64).reshape(-1)
+        if ids.size == 0:
+            return 0
+        gone = C.c_uint64(0)
+        _check(L.lib().wax_vs_remove_batch(self._h, ids.ctypes.data_as(C.POINTER(C.c_uint64)), ids.size, C.byref(gone)))
+        if gone.value:
+            self._dirty = True
+        return gone.value
+
     def reserve(self, rows: int) -> None:
         _check(L.lib().wax_vs_reserve(self._h, int(rows)))
 
@@ -343,13 +355,17 @@ class CUDAVectorEngine:
     def serialize(self) -> bytes:
         n = C.c_uint64(0)
         _check(L.lib().wax_vs_serialized_length(self._h, C.byref(n)))
-        buf = np.zeros(n.value, np.uint8)
+        buf = bytearray(n.value)          # calloc'ed, written once by the library: no zero-fill pass, no trailing copy
         out = C.c_uint64(0)
-        _check(L.lib().wax_vs_serialize(self._h, buf.ctypes.data_as(C.POINTER(C.c_uint8)), buf.size, C.byref(out)))
-        return buf[: out.value].tobytes()
+        ptr = (C.c_uint8 * len(buf)).from_buffer(buf) if buf else (C.c_uint8 * 1)()
+        _check(L.lib().wax_vs_serialize(self._h, ptr, len(buf), C.byref(out)))
+        del ptr
+        if out.value != len(buf):
+            del buf[out.value:]
+        return buf                          # bytes-like (compares equal to bytes; pass to deserialize() as is)
 
     def deserialize(self, data: bytes) -> None:
-        buf = np.frombuffer(bytes(data), np.uint8)
+        buf = np.frombuffer(data, np.uint8)     # zero-copy view of bytes / bytearray / memoryview
         ptr = buf.ctypes.data_as(C.POINTER(C.c_uint8)) if buf.size else C.cast(C.c_char_p(b""), C.POINTER(C.c_uint8))
         _check(L.lib().wax_vs_deserialize(self._h, ptr, buf.size))
         self._dirty = False

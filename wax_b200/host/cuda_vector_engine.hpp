@@ -80,6 +80,12 @@ public:
     }
     void reserve(uint64_t rows) { check(wax_vs_reserve(h_, rows)); }   // reserveIfNeeded (:857-871)
     void remove(uint64_t frameId) { check(wax_vs_remove(h_, frameId)); }
+    // Many frames in one pass (one compaction in HBM, one hash rebuild); returns how many rows were deleted.
+    uint64_t removeBatch(const std::vector<uint64_t> &frameIds) {
+        uint64_t gone = 0;
+        check(wax_vs_remove_batch(h_, frameIds.data(), frameIds.size(), &gone));
+        return gone;
+    }
 
     // A batch of independent queries (no reference counterpart: VectorSearchEngine.swift:13 takes one vector).  Eligible
     // batches take the tensor-core levels; the results are identical to one search() per query.
