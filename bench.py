@@ -291,14 +291,14 @@ def run_single(args):
     alg_bytes = args.rows * DIMS * 4                     # N*D*4 algorithmic bytes per launch
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
     traffic = None
-    tp = ROOT / "profiles" / "traffic_r01.json"
-    if tp.exists():
-        try:
-            t = json.loads(tp.read_text())
-            if t.get("rows") == args.rows:
-                traffic = t.get("dram_bytes_per_launch")
-        except Exception:
-            pass
+    for tp in (ROOT / "profiles" / "traffic_r02.json", ROOT / "profiles" / "r01" / "traffic_r01.json"):
+        if traffic is None and tp.exists():     # dram bytes per launch from the committed `ncu --set full` capture
+            try:
+                t = json.loads(tp.read_text())
+                if t.get("rows") == args.rows:
+                    traffic = t.get("dram_bytes_per_launch")
+            except Exception:
+                pass
     line = {
         "metric": METRIC_NAME, "value": value, "unit": "queries/s", "n_gpus": 1, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",

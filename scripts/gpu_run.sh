@@ -1,0 +1,46 @@
+#!/bin/bash
+# One parameterised runner for everything that goes to the GPU box (replaces the per-call scripts of round 1).
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash scripts/gpu_run.sh <tag> <step> [<step> ...]'
+# Outputs land in gpurun_out/<name>_<tag>.*; copy what should be judged into profiles/.
+# Steps:
+#   box        host/GPU facts                      smoke      __graft_entry__.smoke()
+#   tests      pytest -m gpu (whole suite)         bench      bench.py (N=1) + --impl reference
+#   batch      scripts/bench_batch.py (configs[2],[4]; bf16 then tf32)
+#   ingest     scripts/ingest_bench.py             latency    scripts/latency.py
+#   launches   ncu launch list of bench.py         ncu-scan   ncu --set full of the fused scan kernel
+#   ncu-batch  ncu --set full of the batched nominate + finish kernels (configs[2] and [4] shapes)
+#   sharded:N  torchrun -N tests/check_sharded_torchrun.py + bench.py --gpus N      (needs gpurun --gpus N)
+#   c4         torchrun -8 tests/check_sharded_torchrun.py 100000000 light          (needs gpurun --gpus 8)
+#   sass       cuobjdump opcode histogram of libwaxvs_cuda.so -> profiles-style text
+set -u
+TAG=${1:?tag}; shift
+mkdir -p gpurun_out; OUT=gpurun_out
+TR="python -m torch.distributed.run --nnodes=1 --master-addr 127.0.0.1 --master-port 29533"
+for step in "$@"; do
+  echo "=== $step"
+  case "$step" in
+    box) { cat /sys/fs/cgroup/cpu.max 2>/dev/null; nproc; free -g | sed -n 2p; nvidia-smi --query-gpu=index,name,memory.total,clocks.max.sm,power.limit --format=csv,noheader; nvidia-smi topo -m 2>/dev/null | head -12; } > $OUT/box_$TAG.txt 2>&1; cat $OUT/box_$TAG.txt ;;
+    smoke) timeout 300 python __graft_entry__.py --smoke 2>&1 | tail -2 ;;
+    tests) timeout 1500 python -m pytest tests -q -m gpu --durations=8 > $OUT/pytest_gpu_$TAG.txt 2>&1; tail -14 $OUT/pytest_gpu_$TAG.txt ;;
+    bench) timeout 900 python bench.py 2> $OUT/bench_$TAG.err | tail -1 > $OUT/bench_$TAG.json; cut -c1-600 $OUT/bench_$TAG.json; tail -3 $OUT/bench_$TAG.err
+           timeout 600 python bench.py --impl reference 2>/dev/null | tail -1 > $OUT/bench_reference_$TAG.json; cut -c1-300 $OUT/bench_reference_$TAG.json ;;
+    batch) timeout 600 python scripts/bench_batch.py 20 2>&1 | tee $OUT/bench_batch_$TAG.jsonl | cut -c1-300
+           timeout 600 python scripts/bench_batch.py 20 tf32 2>&1 | tee $OUT/bench_batch_tf32_$TAG.jsonl | cut -c1-300 ;;
+    ingest) timeout 900 python scripts/ingest_bench.py 2>&1 | tail -1 | tee $OUT/ingest_$TAG.json ;;
+    latency) timeout 600 python scripts/latency.py 2>&1 | tail -1 | tee $OUT/latency_$TAG.json ;;
+    launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/ncu_launches_$TAG.csv \
+                python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_$TAG.log 2>&1; grep -c scan_tma $OUT/ncu_launches_$TAG.csv ;;
+    ncu-scan) timeout 900 ncu --set full --clock-control none --import-source on -k regex:scan_tma -s 4 -c 1 -o $OUT/ncu_scan_$TAG -f \
+                python bench.py --steps 3 --warmup 3 --no-cpu-baseline --no-shadow > $OUT/ncu_scan_$TAG.log 2>&1
+              ncu -i $OUT/ncu_scan_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_scan_${TAG}_summary.csv; cat $OUT/ncu_scan_${TAG}_summary.csv | cut -c1-400 ;;
+    ncu-batch) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'batch_nominate|batch_finish' -s 6 -c 2 -o $OUT/ncu_batch_$TAG -f \
+                python scripts/bench_batch.py 2 > $OUT/ncu_batch_$TAG.log 2>&1
+              ncu -i $OUT/ncu_batch_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_batch_${TAG}_summary.csv; cut -c1-400 $OUT/ncu_batch_${TAG}_summary.csv ;;
+    sharded:*) N=${step#sharded:}
+           timeout 900 $TR --nproc-per-node $N tests/check_sharded_torchrun.py > $OUT/sharded_parity_${TAG}_n$N.txt 2>&1; tail -12 $OUT/sharded_parity_${TAG}_n$N.txt
+           timeout 900 $TR --nproc-per-node $N bench.py --gpus $N 2> $OUT/bench_${TAG}_n$N.err | tail -1 > $OUT/bench_${TAG}_n$N.json; cut -c1-700 $OUT/bench_${TAG}_n$N.json; tail -3 $OUT/bench_${TAG}_n$N.err ;;
+    c4) timeout 1200 $TR --nproc-per-node 8 tests/check_sharded_torchrun.py 100000000 light > $OUT/sharded_parity_${TAG}_c4_100m_n8.txt 2>&1; tail -12 $OUT/sharded_parity_${TAG}_c4_100m_n8.txt ;;
+    sass) cuobjdump -sass wax_b200/libwaxvs_cuda.so | python scripts/sass_histogram.py > $OUT/sass_opcodes_$TAG.txt; head -40 $OUT/sass_opcodes_$TAG.txt ;;
+    *) echo "unknown step $step" ;;
+  esac
+done
