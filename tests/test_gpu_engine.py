@@ -289,6 +289,25 @@ def test_mutator_drains_in_flight_device_path_scans(oracle):
     assert after[0][0] != expect[0][0] and [a[0] for a in after[:k - 1]] == [e[0] for e in expect[1:]]
 
 
+@pytest.mark.parametrize("dims", [384, 640, 100, 1000, 2048])
+def test_host_delivery_and_inline_query_do_not_change_results(oracle, dims):
+    """The synchronous single-query entry point normally sends the query in the kernel parameters (<= 512 floats, TMA
+    kernels) and lets the kernel store the result in mapped host memory + raise a flag.  Every combination of those two
+    switches -- and the shapes that cannot use them (long rows, the direct-load kernel) -- returns the same bits."""
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.fill_synthetic(31, 30_000)
+    qs = oracle.synth_rows(32, 0, 6, dims) * np.float32(1.7)
+    r, _, s = oracle.search_synth(oracle.COSINE, 31, 0, 30_000, dims, True, qs[0], 10, mode=oracle.ACC_F32_TREE, threads=8)
+    results = []
+    for delivery in (1, 0):
+        for inline in (1, 0):
+            eng.set_option("host_delivery", delivery); eng.set_option("inline_query", inline)
+            results.append([eng.search(q, k) for q in qs for k in (10, 72, 1)])
+    assert all(x == results[0] for x in results[1:])
+    assert [g[0] for g in results[0][0]] == r.tolist()
+    assert np.array_equal(np.float32([g[1] for g in results[0][0]]).view(np.uint32), s.view(np.uint32))
+
+
 def test_growth_from_initial_reserve(oracle):
     eng = CUDAVectorEngine(VectorMetric.l2, 3)           # initialReserve 64, doubling (:19, :857-871)
     rows = oracle.synth_rows(8, 0, 1000, 3, normalize=False)

@@ -131,6 +131,8 @@ struct Tuning {
     int batch_rescore = 0;  // 0 auto; else nominees re-scored exactly per query (256, 512 or 1024)
     int batch_retry = 1;    // queries level 1 cannot prove go through the filter level (TF32, complete by construction) before an exact scan
     int filter_cap = 8192;  // candidates per query the filter level may collect (power of two <= 16384); overflow -> exact scan
+    int inline_query = 1;   // host entry points: a query of <= 512 floats travels in the kernel parameters (no H2D copy)
+    int host_delivery = 1;  // host entry points: the kernel stores the result in mapped host memory + flag (no D2H copy / sync)
     int shard_fused = 1;    // sharded search: exchange + merge inside the scan launch (0: separate 1-CTA launch)
     int single_shadow = 0;  // 1: single queries / batches below batch_min also take the bf16-shadow nominations
                             // (half the HBM bytes per query: 1.19 vs 2.04 ms at 10 M x 384, same results); off by
@@ -168,6 +170,8 @@ struct SearchCtx {
     uint32_t *d_mask = nullptr; size_t mask_cap = 0;              // filtered search: row bitset / listed rows
     uint64_t *d_gather_keys = nullptr; size_t gather_cap = 0;     // filtered search: keys of the listed rows
     wax_vs_candidate *d_shard_local = nullptr;                    // sharded search: this rank's list before the exchange [kShardKCap]
+    unsigned long long *h_flag = nullptr;                         // mapped pinned: host-delivery completion flag
+    unsigned long long host_seq = 0;                              // last value the flag was asked to take
 };
 
 struct wax_vs_engine {
@@ -291,6 +295,7 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_mask) cudaFree(c->d_mask);
     if (c->d_gather_keys) cudaFree(c->d_gather_keys);
     if (c->d_shard_local) cudaFree(c->d_shard_local);
+    if (c->h_flag) cudaFreeHost(c->h_flag);
     if (c->h_ok) cudaFreeHost(c->h_ok);
     if (c->ev0) cudaEventDestroy(c->ev0);
     if (c->ev1) cudaEventDestroy(c->ev1);
@@ -365,7 +370,8 @@ template <typename T>
 static int32_t ensure_pinned(T **p, size_t *cap, size_t need, const char *what) {
     if (need <= *cap) return WAX_VS_OK;
     if (*p) { cudaFreeHost(*p); *p = nullptr; *cap = 0; }
-    if (cudaMallocHost(p, need * sizeof(T)) != cudaSuccess)
+    // mapped + portable: kernels may write results straight into it (host delivery), any device may use it
+    if (cudaHostAlloc(reinterpret_cast<void **>(p), need * sizeof(T), cudaHostAllocMapped | cudaHostAllocPortable) != cudaSuccess)
         return fail(WAX_VS_ERR_CUDA, "failed to allocate pinned %s (%zu bytes): %s", what, need * sizeof(T),
                     cudaGetErrorString(cudaGetLastError()));
     *cap = need;
@@ -473,12 +479,48 @@ static cudaError_t launch_ldg(const ScanParams &p, int grid, int metric, int mod
 }
 
 // Enqueue one query's scan + top-k on `stream`.  k_eff <= 10000.  Adds the number of kernels launched.
+// Wait for a kernel's host-visible completion flag (mapped pinned memory): the result is usable a few microseconds
+// after the kernel stored it, without an event / stream synchronisation.  The stream is polled now and then so that a
+// launch failure surfaces.  Returns WAX_VS_OK, 1 when the flag carries the error bit, or a negative code.
+static int32_t wait_host_flag(cudaStream_t stream, unsigned long long *flag_ptr, unsigned long long seq,
+                              unsigned long long timeout_ns) {
+    volatile unsigned long long *flag = flag_ptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    uint32_t spins = 0;
+    for (;;) {
+        const unsigned long long v = *flag;
+        if ((v & ~kShardErrorBit) == seq) {
+            std::atomic_thread_fence(std::memory_order_acquire);
+            return (v & kShardErrorBit) ? 1 : WAX_VS_OK;
+        }
+        if ((++spins & 0x3FFu) == 0) {
+            const cudaError_t q = cudaStreamQuery(stream);
+            if (q != cudaSuccess && q != cudaErrorNotReady)
+                return fail(WAX_VS_ERR_CUDA, "search failed on the device: %s", cudaGetErrorString(q));
+            if (q == cudaSuccess && ((*flag) & ~kShardErrorBit) != seq)
+                return fail(WAX_VS_ERR_CUDA, "search finished without publishing its result");
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(timeout_ns) + std::chrono::seconds(5))
+                return fail(WAX_VS_ERR_CUDA, "search did not complete");
+        }
+    }
+}
+
+// Host delivery (the synchronous host entry points, fused top-k only): h_query travels in the kernel parameters when the
+// kernel can take it (else it is copied H2D here), and the kernel stores the result into host_out + raises host_flag.
+struct HostDelivery {
+    const float *h_query;               // host query (dims floats); d_query is ignored when set
+    wax_vs_candidate *host_out;         // mapped pinned [k], or nullptr
+    unsigned long long *host_flag;      // mapped pinned
+    unsigned long long seq;
+    bool delivered = false;             // out: the launched kernel will raise host_flag (else: copy d_out back yourself)
+};
+
 // `shard` (optional): the row-sharded form -- d_out receives the result MERGED over all ranks; the exchange runs inside
 // the scan launch when the kernel's shared-memory lists can hold the merge keys, else as one extra 1-CTA launch.
 static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_query, uint32_t k_eff,
                               uint64_t row_offset, wax_vs_candidate *d_out, const uint64_t *d_ids,
                               cudaStream_t stream, uint64_t *launches, const uint32_t *d_mask = nullptr,
-                              const ShardParams *shard = nullptr) {
+                              const ShardParams *shard = nullptr, const HostDelivery *host = nullptr) {
     wax_vs_candidate *d_merged = nullptr;
     if (shard) {
         if (k_eff > static_cast<uint32_t>(kShardKCap))
@@ -493,6 +535,15 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         shard_exchange_kernel<<<1, 256, 0, stream>>>(sp, d_out, k_eff);
         CUDA_TRY(cudaGetLastError());
         ++*launches;
+        return WAX_VS_OK;
+    };
+    auto stage_query = [&]() -> int32_t {            // host query -> pinned staging -> device, on `stream`
+        int32_t rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(e->dims), "query buffer");
+        if (!rc) rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, static_cast<size_t>(e->dims), "query staging");
+        if (rc) return rc;
+        memcpy(c->h_queries, host->h_query, e->dims * sizeof(float));
+        CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, e->dims * sizeof(float), cudaMemcpyHostToDevice, stream));
+        d_query = c->d_queries;
         return WAX_VS_OK;
     };
     if (e->n_rows == 0) {
@@ -523,6 +574,21 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     bool use_tma = (e->tune.variant != 2) && pick_tma_config(e, &cfg);
     if (e->tune.variant == 1 && !use_tma)
         return fail(WAX_VS_ERR_UNSUPPORTED, "TMA-staged kernel does not support dims=%u", e->dims);
+    if (host && host->h_query) {
+        const bool inline_ok = use_tma && !emit && e->tune.inline_query != 0 && e->dims <= static_cast<uint32_t>(kInlineQueryFloats);
+        if (inline_ok) {
+            memcpy(p.query_inline, host->h_query, e->dims * sizeof(float));
+            p.query = nullptr;
+        } else {
+            int32_t rc = stage_query();
+            if (rc) return rc;
+            p.query = d_query;
+        }
+    }
+    if (host && host->host_out && !emit && !shard) {
+        p.host_out = host->host_out; p.host_flag = host->host_flag; p.host_seq = host->seq;
+        const_cast<HostDelivery *>(host)->delivered = true;
+    }
     bool fused_exchange = false;
     if (shard && !emit) {     // the merge keys (world * k uint32) live in the kernel's block-list shared memory
         const size_t list_bytes = static_cast<size_t>(use_tma ? cfg.warps : 8) * 32 * (mode == 0 ? 1 : 4) * sizeof(uint64_t);
@@ -1518,6 +1584,42 @@ static int32_t search_host(wax_vs_engine *e, const float *queries, uint32_t n_qu
 
     const size_t qfloats = static_cast<size_t>(n_queries) * e->dims;
     const size_t ncand = static_cast<size_t>(n_queries) * k_eff;
+    // One query on the fused scan: the query rides in the kernel parameters and the kernel itself stores the result in
+    // mapped host memory and raises a flag -- no H2D copy, no D2H copy, no stream synchronisation on the way.
+    if (n_queries == 1 && e->tune.host_delivery && k_eff <= static_cast<uint32_t>(e->tune.fused_k_max) &&
+        !batch_tensor_eligible(e, 1, k_eff)) {
+        if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, ncand, "result buffer"))) return rc;
+        if ((rc = ensure_pinned(&c->h_out, &c->h_out_cap, ncand, "result staging"))) return rc;
+        if (!c->h_flag) {
+            CUDA_TRY(cudaHostAlloc(reinterpret_cast<void **>(&c->h_flag), sizeof(unsigned long long), cudaHostAllocMapped | cudaHostAllocPortable));
+            *c->h_flag = 0; c->host_seq = 0;
+        }
+        HostDelivery hd{queries, c->h_out, c->h_flag, ++c->host_seq};
+        uint64_t launches = 0;
+        if ((rc = enqueue_search(e, c, nullptr, k_eff, 0, c->d_out, nullptr, c->stream, &launches, nullptr, nullptr, &hd))) {
+            cudaStreamSynchronize(c->stream);
+            return rc;
+        }
+        if (hd.delivered) {
+            if ((rc = wait_host_flag(c->stream, c->h_flag, hd.seq, 30ull * 1000 * 1000 * 1000)) != WAX_VS_OK) {
+                cudaStreamSynchronize(c->stream);
+                return rc > 0 ? fail(WAX_VS_ERR_CUDA, "search reported a device-side error") : rc;
+            }
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, ncand * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+        }
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < k_eff; ++i) {
+            const wax_vs_candidate &cd = c->h_out[i];
+            if (!cd.valid) continue;
+            out_ids[m] = e->ids_identity ? e->id_base + cd.row : e->ids[cd.row];
+            out_scores[m] = score_from_distance(e->similarity, cd.distance);
+            ++m;
+        }
+        out_n[0] = m;
+        return WAX_VS_OK;
+    }
     if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, qfloats, "query buffer"))) return rc;
     if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, qfloats, "query staging"))) return rc;
     if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, ncand, "result buffer"))) return rc;
@@ -1777,31 +1879,11 @@ int32_t wax_vs_shard_search_device(wax_vs_engine *e, const float *d_query, int64
                           static_cast<cudaStream_t>(cuda_stream), &launches, nullptr, &sp);
 }
 
-// Wait for the kernel's host-visible completion flag (mapped pinned memory): a few microseconds after the merge,
-// instead of an event/stream synchronisation.  The stream is polled now and then so that a launch failure surfaces.
 static int32_t shard_wait_host(wax_vs_engine *e, unsigned long long seq) {
-    auto &sh = e->shard;
-    volatile unsigned long long *flag = sh.h_flag;
-    const auto t0 = std::chrono::steady_clock::now();
-    uint32_t spins = 0;
-    for (;;) {
-        const unsigned long long v = *flag;
-        if ((v & ~kShardErrorBit) == seq) {
-            std::atomic_thread_fence(std::memory_order_acquire);
-            if (v & kShardErrorBit)
-                return fail(WAX_VS_ERR_CUDA, "shard exchange timed out: a peer rank did not deliver its candidates for query #%llu", seq);
-            return WAX_VS_OK;
-        }
-        if ((++spins & 0x3FFu) == 0) {
-            const cudaError_t q = cudaStreamQuery(sh.ctx->stream);
-            if (q != cudaSuccess && q != cudaErrorNotReady)
-                return fail(WAX_VS_ERR_CUDA, "sharded search failed on the device: %s", cudaGetErrorString(q));
-            if (q == cudaSuccess && ((*flag) & ~kShardErrorBit) != seq)
-                return fail(WAX_VS_ERR_CUDA, "sharded search finished without publishing its result");
-            if (std::chrono::steady_clock::now() - t0 > std::chrono::nanoseconds(sh.timeout_ns) + std::chrono::seconds(5))
-                return fail(WAX_VS_ERR_CUDA, "sharded search did not complete");
-        }
-    }
+    int32_t rc = wait_host_flag(e->shard.ctx->stream, e->shard.h_flag, seq, e->shard.timeout_ns);
+    if (rc == 1)
+        return fail(WAX_VS_ERR_CUDA, "shard exchange timed out: a peer rank did not deliver its candidates for query #%llu", seq);
+    return rc;
 }
 
 int32_t wax_vs_shard_search(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k, uint64_t *out_ids,
@@ -1823,16 +1905,13 @@ int32_t wax_vs_shard_search(wax_vs_engine *e, const float *query, uint32_t query
     std::lock_guard<std::mutex> sg(sh.mu);      // one host-path collective at a time: it owns sh.ctx and h_final
     SearchCtx *c = sh.ctx;
     int32_t rc;
-    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(e->dims), "query buffer"))) return rc;
-    if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, static_cast<size_t>(e->dims), "query staging"))) return rc;
     const uint64_t *d_ids = nullptr;
     if ((rc = sync_device_ids(e, &d_ids))) return rc;
-    memcpy(c->h_queries, query, e->dims * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, e->dims * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     ShardParams sp = shard_params_next(e);
     sp.host_out = sh.h_final; sp.host_flag = sh.h_flag;      // mapped pinned: the kernel delivers the result itself
+    HostDelivery hd{query, nullptr, nullptr, 0};             // the query rides in the kernel parameters when it fits
     uint64_t launches = 0;
-    if ((rc = enqueue_search(e, c, c->d_queries, k_eff, sh.row_offset, sh.d_final, d_ids, c->stream, &launches, nullptr, &sp))) {
+    if ((rc = enqueue_search(e, c, nullptr, k_eff, sh.row_offset, sh.d_final, d_ids, c->stream, &launches, nullptr, &sp, &hd))) {
         cudaStreamSynchronize(c->stream);
         return rc;
     }
@@ -2296,6 +2375,8 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "filter_cap")) e->tune.filter_cap = v;
     else if (!strcmp(key, "single_shadow")) e->tune.single_shadow = v;
     else if (!strcmp(key, "shard_fused")) e->tune.shard_fused = v;
+    else if (!strcmp(key, "inline_query")) e->tune.inline_query = v;
+    else if (!strcmp(key, "host_delivery")) e->tune.host_delivery = v;
     else if (!strcmp(key, "shard_timeout_ms")) e->shard.timeout_ns = static_cast<unsigned long long>(std::max<int64_t>(value, 1)) * 1000000ull;
     else if (!strcmp(key, "time_overlap")) e->tune.time_overlap = v;
     else if (!strcmp(key, "ldg_ctas_per_sm")) e->tune.ldg_ctas_per_sm = std::max(1, v);

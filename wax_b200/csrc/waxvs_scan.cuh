@@ -29,6 +29,8 @@
 
 namespace waxvs {
 
+constexpr int kInlineQueryFloats = 512;
+
 struct ScanParams {
     const float *corpus;        // [n_rows][dims]
     const float *query;         // [dims]
@@ -47,6 +49,13 @@ struct ScanParams {
     uint32_t chunk_steps;       // > 0: dynamic scheduling, warps claim chunks of this many steps from work_counter
     uint32_t *work_counter;     // zero on entry, zero again on exit (reset by the last CTA)
     const uint32_t *mask;       // optional row filter: bit r of mask[r / 32] set = row r may be returned (nullptr = all)
+    // Host delivery (the synchronous single-query entry point): the last CTA also stores the result into mapped pinned
+    // host memory and then raises a host-visible flag, so the caller needs neither a D2H copy nor a stream
+    // synchronisation; and a short query travels in the kernel parameters instead of through an H2D copy.
+    wax_vs_candidate *host_out;         // [k] mapped pinned, or nullptr
+    unsigned long long *host_flag;      // mapped pinned: set to host_seq once host_out is complete
+    unsigned long long host_seq;
+    alignas(16) float query_inline[kInlineQueryFloats];   // used when query == nullptr (TMA-staged kernels, dims <= kInlineQueryFloats)
     ShardParams shard;          // shard.world > 0: `out` is this rank's local list and the last CTA goes on to exchange it
                                 // with the other ranks over NVLink and to merge (waxvs_shard.cuh): still the same launch
 };
@@ -67,6 +76,7 @@ __device__ __forceinline__ void write_candidate(const ScanParams &p, int slot, u
         c.frame_id = p.frame_ids ? p.frame_ids[row] : p.id_base + row;
     }
     p.out[slot] = c;
+    if (p.host_out) p.host_out[slot] = c;
 }
 
 // CTA merge + grid merge + output.  Called by every thread of the CTA after the scan loop.
@@ -134,6 +144,11 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
         for (int j = 0; j < E; ++j)
             if (j * 32 + lane < k) write_candidate(p, j * 32 + lane, tk.key[j]);
         if (lane == 0) { *p.ticket = 0u; if (p.work_counter) *p.work_counter = 0u; }
+        if (p.host_flag && !p.shard.world) {          // result complete in host memory: tell the waiting caller
+            __threadfence_system();
+            __syncwarp();
+            if (lane == 0) st_release_sys_u64(p.host_flag, p.host_seq);
+        }
     }
     // Row-sharded search: push the local list to every rank, wait for theirs, merge -- the block lists are done with,
     // their shared memory holds the distance keys of the merge (the host checks that world * k * 4 bytes fit).
@@ -170,12 +185,14 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
     // ---- query chunks in registers (C > 0) or shared memory (C == 0) + fused |q|^2 ----
     float4 q[C > 0 ? C : 1];
     const float4 *q4 = reinterpret_cast<const float4 *>(p.query);
+    const float4 *qp = reinterpret_cast<const float4 *>(p.query_inline);     // kernel-parameter copy (query == nullptr)
+    auto load_q = [&](int i) -> float4 { return q4 ? __ldg(q4 + i) : qp[i]; };
     if (C > 0) {
 #pragma unroll
-        for (int c = 0; c < (C > 0 ? C : 1); ++c) q[c] = __ldg(q4 + lane + 32 * c);
+        for (int c = 0; c < (C > 0 ? C : 1); ++c) q[c] = load_q(lane + 32 * c);
     } else {
         qs = reinterpret_cast<float4 *>((reinterpret_cast<uintptr_t>(qs) + 15) & ~uintptr_t(15));
-        for (int i = threadIdx.x; i < CN * 32; i += blockDim.x) qs[i] = (i < D4) ? __ldg(q4 + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = threadIdx.x; i < CN * 32; i += blockDim.x) qs[i] = (i < D4) ? load_q(i) : make_float4(0.f, 0.f, 0.f, 0.f);
         __syncthreads();
     }
     auto qchunk = [&](int c) -> float4 { return C > 0 ? q[C > 0 ? c : 0] : qs[lane + 32 * c]; };
