@@ -37,11 +37,15 @@ def needs_build() -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     if not force and not needs_build():
         return LIB
-    cmd = [nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(LIB),
+    # link into a temporary name and rename: a reader (or a snapshot of the tree) never sees a half-written library
+    tmp = LIB.with_suffix(".so.tmp%d" % os.getpid())
+    cmd = [nvcc(), *NVCC_FLAGS, *(["-Xptxas", "-v"] if verbose else []), "-o", str(tmp),
            *[str(CSRC / s) for s in SOURCES]]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
+        tmp.unlink(missing_ok=True)
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    os.replace(tmp, LIB)
     if verbose:
         sys.stderr.write(res.stdout + res.stderr)
     return LIB
