@@ -31,10 +31,17 @@ CONFIGS = [
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 5
 # nominations: "bf16" (default: kind::f16 MMAs over the bf16 shadow of the corpus) or "tf32" (from the fp32 corpus)
 nominate = sys.argv[2] if len(sys.argv) > 2 else "bf16"
-for cfg in CONFIGS:
+options = [kv.split("=") for kv in sys.argv[3:]]          # engine tuning options, e.g. batch_pair=1 batch_ares=0
+only = [int(v) for k, v in options if k == "only"]        # only=0 / only=1: run just that config
+options = [(k, v) for k, v in options if k != "only"]
+for ci, cfg in enumerate(CONFIGS):
+    if only and ci not in only:
+        continue
     eng = CUDAVectorEngine(cfg["metric"], cfg["dims"])
     eng.fill_synthetic(cfg["seed"], cfg["rows"], normalize=cfg["normalize"])
     eng.set_option("batch_bf16", 1 if nominate == "bf16" else 0)
+    for k, v in options:
+        eng.set_option(k, int(v))
     ms, launches, bad = eng.time_search_batch(cfg["batch"], cfg["k"], steps, warmup=2)
     per = ms / steps
     flops = 2.0 * cfg["batch"] * cfg["rows"] * cfg["dims"]
@@ -71,7 +78,7 @@ for cfg in CONFIGS:
         "gpu_launches_per_batch": launches / steps, "unproven_queries_last_step": bad,
         "tensor_path_queries": t1 - t0, "exact_fallback_queries": f1 - f0,
         "single_query_path_ms": single_ms / 5, "speedup_vs_single_query_loop": (single_ms / 5) * cfg["batch"] / per,
-        "check_top1": res[0][0],
+        "check_top1": res[0][0], "options": dict(options),
     }
     print(json.dumps(line), flush=True)
     eng.close()

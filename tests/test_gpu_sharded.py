@@ -122,8 +122,11 @@ def test_short_and_empty_shards_pad_correctly(oracle):
 
 
 def test_many_queries_reuse_the_mailbox_slots(oracle):
-    """More collective searches than the mailbox has slots (8), host entry point and device-timed loop interleaved:
-    slot reuse is guarded by the acknowledgements, results stay exact."""
+    """Many more collective searches than the mailbox has slots (8): slot reuse is guarded by the acknowledgements,
+    results stay exact.  (Each rank waits for its result before the next launch: several ranks share ONE device here, and
+    queuing launches back to back on streams that may share a hardware queue could order a rank's first kernel behind
+    another rank's blocked second one.  The back-to-back form runs under torchrun, one device per rank:
+    tests/check_sharded_torchrun.py.)"""
     dims, total = 384, 50_000
     single = CUDAVectorEngine(VectorMetric.cosine, dims)
     single.fill_synthetic(60, total)
@@ -131,15 +134,7 @@ def test_many_queries_reuse_the_mailbox_slots(oracle):
     try:
         qs = oracle.synth_rows(61, 0, 40, dims)
         expect = [single.search(q, 10) for q in qs]
-
-        def work(r, e):
-            out = []
-            for i, q in enumerate(qs):
-                out.append(e.shard_search(q, 10))
-                if i == 20:
-                    e.time_shard_search(10, 25, warmup=3, n_queries=8, seed=62)   # 28 back-to-back launches on one stream
-            return out
-        res = grp.collective(work)
+        res = grp.collective(lambda r, e: [e.shard_search(q, 10) for q in qs])
         for r in range(3):
             assert res[r] == expect, r
     finally:

@@ -73,3 +73,31 @@ def test_batched_merge_equals_the_per_query_merge():
             assert np.array_equal(best[i, : ref.size]["row"], ref["row"])
             assert np.array_equal(best[i, : ref.size]["frame_id"], ref["frame_id"])
     assert sharded.merge_candidates_batch(c, 5)[1][0] == 0 and sharded.merge_candidates_batch(c, 5)[1][1] == 3
+
+
+def test_shard_merge_rule_model():
+    """The in-kernel merge of the row-sharded search (wax_b200/csrc/waxvs_shard.cuh) places candidate j of rank r at
+    j + sum over lower ranks of upper_bound(distance) + sum over higher ranks of lower_bound(distance).  Model of that
+    rule on random sorted lists full of ties and padding: it is exactly the (distance, rank, index) = (distance, global
+    row) order, every output position is written once, padding ends up last."""
+    import bisect
+    rng = np.random.default_rng(0)
+    none = 0xFFFFFFFF
+    for _ in range(1500):
+        world, k = int(rng.integers(1, 9)), int(rng.integers(1, 12))
+        lists = []
+        for _r in range(world):
+            n_valid = int(rng.integers(0, k + 1))
+            lists.append(sorted(int(x) for x in rng.integers(0, 6, n_valid)) + [none] * (k - n_valid))
+        out = [None] * k
+        for r, lst in enumerate(lists):
+            for j, key in enumerate(lst):
+                pos = j + sum((bisect.bisect_right if r2 < r else bisect.bisect_left)(l2, key)
+                              for r2, l2 in enumerate(lists) if r2 != r)
+                if pos < k:
+                    assert out[pos] is None
+                    out[pos] = (key, r, j)
+        assert all(o is not None for o in out)
+        ref = sorted((key, r, j) for r, l in enumerate(lists) for j, key in enumerate(l) if key != none)[:k]
+        assert [o for o in out if o[0] != none] == ref
+        assert all(o[0] == none for o in out[len(ref):])
