@@ -32,6 +32,7 @@ class Group:
             else:
                 eng.fill_synthetic(synth[0], hi - lo, first_row=lo, id_base=lo)
             eng.set_option("shard_fused", fused)
+            eng.set_option("shard_timeout_ms", 8000)         # a protocol bug must fail the test quickly, not hold the GPU
             self.engines.append(eng)
             self.ranges.append((lo, hi))
         blobs = [e.shard_open(r, world, self.ranges[r][0]) for r, e in enumerate(self.engines)]
