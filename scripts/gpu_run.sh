@@ -7,6 +7,8 @@
 #   tests      pytest -m gpu (whole suite)         bench      bench.py (N=1) + --impl reference
 #   batch      scripts/bench_batch.py (configs[2],[4]; bf16 then tf32)
 #   ingest     scripts/ingest_bench.py             latency    scripts/latency.py
+#   small-n    scripts/small_n_sweep.py (launch shape vs latency at 10 K .. 174 K rows)
+#   batch-sweep  kernel-shape options of the batched path on configs[2] / [4]
 #   launches   ncu launch list of bench.py         ncu-scan   ncu --set full of the fused scan kernel
 #   ncu-batch  ncu --set full of the batched nominate + finish kernels (configs[2] and [4] shapes)
 #   sharded:N  torchrun -N tests/check_sharded_torchrun.py + bench.py --gpus N      (needs gpurun --gpus N)
@@ -27,6 +29,9 @@ for step in "$@"; do
     batch) timeout 600 python scripts/bench_batch.py 20 2>&1 | tee $OUT/bench_batch_$TAG.jsonl | cut -c1-300
            timeout 600 python scripts/bench_batch.py 20 tf32 2>&1 | tee $OUT/bench_batch_tf32_$TAG.jsonl | cut -c1-300 ;;
     ingest) timeout 900 python scripts/ingest_bench.py 2>&1 | tail -1 | tee $OUT/ingest_$TAG.json ;;
+    small-n) timeout 900 python scripts/small_n_sweep.py 2>&1 | tee $OUT/small_n_$TAG.jsonl | cut -c1-260 ;;
+    batch-sweep) for o in "only=1 batch_pair=1" "only=1 batch_pair=1 batch_heap=16" "only=1 batch_heap=16" "only=0 batch_pair=1" "only=0 batch_ares=0" "only=0 batch_pair=1 batch_ares=0"; do
+             timeout 400 python scripts/bench_batch.py 10 bf16 $o 2>&1 | tail -1 | tee -a $OUT/batch_sweep_$TAG.jsonl | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['options'], d['ms_per_batch'], d['roofline']['frac'], d['exact_fallback_queries'])"; done ;;
     latency) timeout 600 python scripts/latency.py 2>&1 | tail -1 | tee $OUT/latency_$TAG.json ;;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file $OUT/ncu_launches_$TAG.csv \
                 python bench.py --steps 5 --warmup 3 --no-cpu-baseline > $OUT/ncu_launches_$TAG.log 2>&1; grep -c scan_tma $OUT/ncu_launches_$TAG.csv ;;
