@@ -243,6 +243,11 @@ int32_t wax_vs_debug_time_search(wax_vs_engine *engine, uint32_t n_queries, int6
 int32_t wax_vs_debug_time_shard_search(wax_vs_engine *engine, uint32_t n_queries, int64_t top_k, uint64_t seed,
                                        uint32_t warmup, uint32_t iters, float *out_ms_total, uint64_t *out_launches);
 
+/* Host <-> device transfer rates on this box (GB/s) for `bytes` of pageable host memory: out7 = {one-thread staging
+   memcpy, staging memcpy with the worker threads, DMA pinned->HBM, DMA HBM->pinned, upload pipeline pageable->HBM,
+   download pipeline HBM->pageable, worker threads}.  Explains what bounds wax_vs_add_batch / wax_vs_serialize. */
+int32_t wax_vs_debug_transfer_probe(wax_vs_engine *engine, uint64_t bytes, float *out7);
+
 /* Batched-path instrumentation: how many queries were answered by the tensor-core nomination path with a
    completed exactness proof, and how many had to be re-run on the exact single-query path. */
 int32_t wax_vs_debug_batch_stats(wax_vs_engine *engine, uint64_t *tensor_queries, uint64_t *fallback_queries);

@@ -65,6 +65,8 @@ t0 = time.perf_counter()
 blob = eng.serialize()                                                   # the mirror: fresh bytearray, no extra copies
 t_ser_mirror = time.perf_counter() - t0
 gb = total * dims * 4 / 1e9
+probe = (C.c_float * 7)()
+assert L.lib().wax_vs_debug_transfer_probe(eng.handle, 1 << 30, probe) == 0
 print(json.dumps({
     "rows": total, "dims": dims, "host_threads_for_staging": "min(8, cgroup cores)",
     "append_20x100k_rows_per_s": round(total / t_append), "append_20x100k_gb_per_s": round(gb / t_append, 2),
@@ -75,5 +77,9 @@ print(json.dumps({
     "serialize_s": round(t_ser, 3), "serialize_gb_per_s": round(buf.size / 1e9 / t_ser, 2),
     "deserialize_s": round(t_de, 3), "deserialize_gb_per_s": round(buf.size / 1e9 / t_de, 2),
     "mirror_serialize_s": round(t_ser_mirror, 3), "blob_gb": round(len(blob) / 1e9, 2),
+    "transfer_probe_gb_per_s": {"memcpy_1_thread": round(probe[0], 1), "memcpy_staging_threads": round(probe[1], 1),
+                                "dma_h2d_pinned": round(probe[2], 1), "dma_d2h_pinned": round(probe[3], 1),
+                                "upload_pipeline": round(probe[4], 1), "download_pipeline": round(probe[5], 1),
+                                "staging_threads": int(probe[6])},
     "round1": {"append_gb_per_s": 5.46, "upsert_100k_s": 0.0577, "remove_one_s": 0.0043, "serialize_s": 1.813, "deserialize_s": 0.284},
 }))

@@ -1134,6 +1134,20 @@ int32_t wax_vs_reserve(wax_vs_engine *e, uint64_t rows) {
     return set_capacity(e, rows);
 }
 
+// Phase trace of the mutators for performance work: WAXVS_TRACE_INGEST=1 prints "<what>: <phase> <us>" lines to stderr.
+struct IngestTrace {
+    bool on;
+    const char *what;
+    std::chrono::steady_clock::time_point t;
+    explicit IngestTrace(const char *w) : on(getenv("WAXVS_TRACE_INGEST") != nullptr), what(w), t(std::chrono::steady_clock::now()) {}
+    void mark(const char *phase) {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[waxvs] %s: %s %.1f us\n", what, phase, std::chrono::duration<double, std::micro>(now - t).count());
+        t = now;
+    }
+};
+
 // ---- bulk ingest / export plumbing ---------------------------------------------------------------
 // Host <-> HBM at device speed from PAGEABLE caller memory: the bytes go through two pinned staging buffers; worker
 // threads fill (or drain) one buffer while the DMA engine moves the other.  Caller memory that is already pinned
@@ -1266,13 +1280,17 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
     if (!frame_ids || !rows) return fail(WAX_VS_ERR_NULL, "NULL argument");
     if (vector_len != e->dims)     // :367-370
         return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, vector_len);
+    IngestTrace tr("add_batch");
     std::unique_lock<std::shared_mutex> w(e->rw);
     DeviceGuard g(e->device);
     drain_device_path(e);
+    tr.mark("lock+drain");
     int32_t rc = grow_for(e, e->n_rows + n);  // maxNewCount (:379-380)
     if (rc) return rc;
+    tr.mark("grow");
     materialize_ids(e);
     ensure_map(e);
+    tr.mark("ids+map");
 
     // Resolve the destination row of every batch item in order (the sequential loop at :384-398).
     std::vector<uint32_t> target(n);
@@ -1291,9 +1309,12 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
     }
     e->d_ids_dirty = true;
     const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
+    tr.mark("resolve targets");
     if (pure_append) {
         invalidate_row_caches(e, n0);          // the cached norms / shadow of rows [0, n0) stay valid
-        return upload_bytes(e, e->d_corpus + n0 * e->dims, rows, n * row_bytes);
+        rc = upload_bytes(e, e->d_corpus + n0 * e->dims, rows, n * row_bytes);
+        tr.mark("upload");
+        return rc;
     }
     invalidate_row_caches(e, 0);
     // Overwrites present: a later item for the same row wins; earlier ones are dropped.
@@ -1334,6 +1355,7 @@ int32_t wax_vs_remove_batch(wax_vs_engine *e, const uint64_t *frame_ids, uint64_
     if (out_removed) *out_removed = 0;
     if (n == 0) return WAX_VS_OK;
     if (!frame_ids) return fail(WAX_VS_ERR_NULL, "frame_ids is NULL");
+    IngestTrace tr("remove_batch");
     std::unique_lock<std::shared_mutex> w(e->rw);
     if (e->n_rows == 0) return WAX_VS_OK;  // :425
     // which rows go
@@ -1366,6 +1388,7 @@ int32_t wax_vs_remove_batch(wax_vs_engine *e, const uint64_t *frame_ids, uint64_
             src.push_back(static_cast<uint32_t>(r));
         }
     }
+    tr.mark("resolve rows + sources");
     int32_t rc = ingest_init(e);
     if (rc) return rc;
     auto &ig = e->ing;
@@ -1394,6 +1417,7 @@ int32_t wax_vs_remove_batch(wax_vs_engine *e, const uint64_t *frame_ids, uint64_
             CUDA_TRY(cudaStreamSynchronize(ig.stream));          // src / d_index are reused by the next slab
         }
     }
+    tr.mark("compact matrix");
     // ids: one compaction, one hash rebuild (lazily, on the next lookup)
     for (uint64_t j = 0; j < moving; ++j) e->ids[first + j] = e->ids[src[j]];
     e->ids.resize(new_n);
@@ -1401,6 +1425,7 @@ int32_t wax_vs_remove_batch(wax_vs_engine *e, const uint64_t *frame_ids, uint64_
     e->map_valid = false;
     e->d_ids_dirty = true;
     invalidate_row_caches(e, first);           // rows below the first removed row did not move
+    tr.mark("compact ids");
     if (out_removed) *out_removed = gone.size();
     return WAX_VS_OK;
 }
@@ -2280,6 +2305,34 @@ int32_t wax_vs_debug_stream_read(wax_vs_engine *e, uint32_t iters, float *out_be
     return WAX_VS_OK;
 }
 
+// Host <-> device transfer rates on this box, in GB/s, for `bytes` of pageable host memory (profiles/ingest_*.json):
+//   [0] one-thread memcpy pageable -> pinned     [1] the staging copy with the engine's worker threads
+//   [2] DMA pinned -> HBM                         [3] DMA HBM -> pinned
+//   [4] upload pipeline pageable -> HBM           [5] download pipeline HBM -> pageable       [6] worker threads
+int32_t wax_vs_debug_transfer_probe(wax_vs_engine *e, uint64_t bytes, float *out7) {
+    if (!e || !out7) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    bytes = std::max<uint64_t>(bytes, 1u << 20);
+    int32_t rc = ingest_staging(e, bytes);
+    if (rc) return rc;
+    auto &ig = e->ing;
+    if ((rc = ensure_dev(&ig.d_stage, &ig.d_stage_cap, static_cast<size_t>((bytes + 3) / 4), "probe buffer"))) return rc;
+    std::vector<uint8_t> host(bytes, 1);
+    auto secs = [](auto t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
+    const size_t chunk = std::min<size_t>(ig.pin_bytes, bytes);
+    auto best = [&](auto fn) { double b = 1e30; for (int i = 0; i < 3; ++i) { auto t0 = std::chrono::steady_clock::now(); fn(); b = std::min(b, secs(t0)); } return b; };
+    out7[0] = static_cast<float>(chunk / 1e9 / best([&] { memcpy(ig.pin[0], host.data(), chunk); }));
+    out7[1] = static_cast<float>(chunk / 1e9 / best([&] { parallel_memcpy(ig.pin[0], host.data(), chunk, ig.threads); }));
+    out7[2] = static_cast<float>(chunk / 1e9 / best([&] { cudaMemcpyAsync(ig.d_stage, ig.pin[0], chunk, cudaMemcpyHostToDevice, ig.stream); cudaStreamSynchronize(ig.stream); }));
+    out7[3] = static_cast<float>(chunk / 1e9 / best([&] { cudaMemcpyAsync(ig.pin[0], ig.d_stage, chunk, cudaMemcpyDeviceToHost, ig.stream); cudaStreamSynchronize(ig.stream); }));
+    out7[4] = static_cast<float>(bytes / 1e9 / best([&] { upload_bytes(e, ig.d_stage, host.data(), bytes); }));
+    out7[5] = static_cast<float>(bytes / 1e9 / best([&] { download_bytes(e, host.data(), ig.d_stage, bytes); }));
+    out7[6] = static_cast<float>(ig.threads);
+    CUDA_TRY(cudaGetLastError());
+    return WAX_VS_OK;
+}
+
 int32_t wax_vs_debug_batch_stats(wax_vs_engine *e, uint64_t *tensor_queries, uint64_t *fallback_queries) {
     if (!e) return fail(WAX_VS_ERR_NULL, "engine is NULL");
     std::lock_guard<std::mutex> g(e->pool_mu);
@@ -2295,7 +2348,8 @@ int32_t wax_vs_debug_counter(wax_vs_engine *e, const char *name, uint64_t *out) 
     else if (!strcmp(name, "batch_fallback_queries")) *out = e->batch_fallback_queries;
     else if (!strcmp(name, "batch_bf16_queries")) *out = e->batch_bf16_queries;
     else if (!strcmp(name, "batch_retry_queries")) *out = e->batch_retry_queries;
-    else if (!strcmp(name, "shadow_bytes")) *out = e->shadow_valid ? e->shadow_cap * sizeof(__nv_bfloat16) : 0;
+    else if (!strcmp(name, "shadow_bytes")) *out = e->shadow_valid ? e->shadow_rows * e->dims * sizeof(__nv_bfloat16) : 0;   // live rows
+    else if (!strcmp(name, "shadow_capacity_bytes")) *out = e->shadow_cap * sizeof(__nv_bfloat16);                            // HBM held
     else if (!strcmp(name, "shadow_unavailable")) *out = e->shadow_unavailable ? 1 : 0;   // bf16 shadow did not fit: TF32 level runs
     else if (!strcmp(name, "batch_tf32_queries")) *out = e->batch_tf32_queries;
     else if (!strcmp(name, "ingest_h2d_bytes")) *out = e->ingest_h2d_bytes;
