@@ -28,7 +28,8 @@ for step in "$@"; do
            timeout 600 python bench.py --impl reference 2>/dev/null | tail -1 > $OUT/bench_reference_$TAG.json; cut -c1-300 $OUT/bench_reference_$TAG.json ;;
     batch) timeout 600 python scripts/bench_batch.py 20 2>&1 | tee $OUT/bench_batch_$TAG.jsonl | cut -c1-300
            timeout 600 python scripts/bench_batch.py 20 tf32 2>&1 | tee $OUT/bench_batch_tf32_$TAG.jsonl | cut -c1-300 ;;
-    ingest) timeout 900 python scripts/ingest_bench.py 2>&1 | tail -1 | tee $OUT/ingest_$TAG.json ;;
+    ingest) timeout 900 python scripts/ingest_bench.py 2> $OUT/ingest_$TAG.err | tail -1 | tee $OUT/ingest_$TAG.json; tail -3 $OUT/ingest_$TAG.err
+            WAXVS_TRACE_INGEST=1 timeout 900 python scripts/ingest_bench.py 2> $OUT/ingest_trace_$TAG.txt > /dev/null; grep -c waxvs $OUT/ingest_trace_$TAG.txt ;;
     small-n) timeout 900 python scripts/small_n_sweep.py 2>&1 | tee $OUT/small_n_$TAG.jsonl | cut -c1-260 ;;
     batch-sweep) for o in "only=1 batch_pair=1" "only=1 batch_pair=1 batch_heap=16" "only=1 batch_heap=16" "only=0 batch_pair=1" "only=0 batch_ares=0" "only=0 batch_pair=1 batch_ares=0"; do
              timeout 400 python scripts/bench_batch.py 10 bf16 $o 2>&1 | tail -1 | tee -a $OUT/batch_sweep_$TAG.jsonl | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['options'], d['ms_per_batch'], d['roofline']['frac'], d['exact_fallback_queries'])"; done ;;

@@ -62,7 +62,8 @@ def test_batch_with_near_duplicates_stays_exact(oracle):
     assert got == _single(eng, qs, 10)
     r, _, s = oracle.search(oracle.COSINE, corpus, qs[0], 10, mode=oracle.ACC_F32_TREE, threads=4)
     assert [g[0] for g in got[0]] == r.tolist()
-    assert eng.batch_stats()[1] >= 1          # at least the adversarial queries fell back
+    # the adversarial queries could not be proven at level 1: they were answered by a filter pass or by the exact scan
+    assert eng.batch_stats()[1] + eng.counter("batch_filter_bf16_queries") + eng.counter("batch_retry_queries") >= 1
 
 
 def test_batch_edge_rows_and_mutation_invalidates_norm_cache(oracle):
@@ -185,6 +186,7 @@ def test_bf16_unproven_queries_retry_on_tf32_before_the_exact_scan(oracle):
     eng = CUDAVectorEngine(VectorMetric.cosine, dims)
     eng.add_batch(list(range(n)), corpus)
     eng.set_option("batch_bf16", 1)
+    eng.set_option("filter_bf16", 0)      # this test is about the TF32 filter level; the bf16-shadow one is tested below
     qs = np.stack([q, q * np.float32(2.0), q * np.float32(0.5), q * np.float32(3.0), q * np.float32(1.5),
                    oracle.synth_row(4200, 0, dims, True)])
     t0, f0 = eng.batch_stats()
@@ -205,6 +207,37 @@ def test_bf16_unproven_queries_retry_on_tf32_before_the_exact_scan(oracle):
     got2 = eng.search_batch(qs, 10)
     assert got2 == got
     assert eng.counter("batch_bf16_queries") == n_bf16 + len(qs)
+    assert eng.batch_stats()[1] - f0 >= 5
+
+
+def test_unproven_queries_take_a_filter_pass_over_the_bf16_shadow_first(oracle):
+    """Same planted neighbours.  By default the queries the bf16 nominations cannot prove get ONE filter pass over the
+    bf16 shadow (half the bytes of an exact scan, so it is used even for a single unproven query): every row within
+    the bf16 bound of the exact k-th score is listed and re-scored exactly -- complete by construction.  No TF32 pass,
+    no exact scan, identical results; with a tiny candidate cap the lists overflow and the later levels answer."""
+    dims, n = 384, 60_000
+    q, corpus = _planted(oracle, dims, n, 600, 0.95, 2e-5, seed=4100, stride=100)
+    eng = CUDAVectorEngine(VectorMetric.cosine, dims)
+    eng.add_batch(list(range(n)), corpus)
+    qs = np.stack([q, q * np.float32(2.0), q * np.float32(0.5), q * np.float32(3.0), q * np.float32(1.5),
+                   oracle.synth_row(4200, 0, dims, True)])
+    expect = _single(eng, qs, 10)
+    t0, f0 = eng.batch_stats()
+    assert eng.search_batch(qs, 10) == expect
+    assert eng.counter("batch_filter_bf16_queries") >= 5 and eng.counter("batch_retry_queries") == 0
+    assert eng.batch_stats()[1] - f0 == 0
+    # ONE unprovable query in an otherwise easy batch: still the shadow filter pass, not a 2x more expensive exact scan
+    eng.set_option("batch_bf16", 1)                       # re-arm the bf16 level (the adaptive choice suspended it)
+    easy = oracle.synth_rows(4300, 0, 12, dims)
+    mixed = np.concatenate([easy[:5], q[None, :], easy[5:]])
+    b0 = eng.counter("batch_filter_bf16_queries")
+    got = eng.search_batch(mixed, 10)
+    assert got == _single(eng, mixed, 10) and got[5] == expect[0]
+    assert eng.counter("batch_filter_bf16_queries") - b0 == 1 and eng.batch_stats()[1] - f0 == 0
+    # overflow of the bf16 list -> TF32 filter (sub-batch large enough) -> exact scan: same answers
+    eng.set_option("batch_bf16", 1)
+    eng.set_option("filter_cap", 64)
+    assert eng.search_batch(qs, 10) == expect
     assert eng.batch_stats()[1] - f0 >= 5
 
 
@@ -295,7 +328,7 @@ def test_filter_level_answers_tight_clusters_without_exact_scans(oracle, metric,
     r, d, s = oracle.search(metric.value, corpus, qs[3], 10, mode=oracle.ACC_F32_TREE, threads=4)
     assert [g[0] for g in got[3]] == r.tolist()
     assert np.array_equal(np.float32([g[1] for g in got[3]]).view(np.uint32), s.view(np.uint32))
-    assert eng.counter("batch_retry_queries") >= 48, "the filter level was not exercised"
+    assert eng.counter("batch_retry_queries") + eng.counter("batch_filter_bf16_queries") >= 48, "no filter level was exercised"
     assert f1 - f0 == 0, f"{f1 - f0} queries needed an exact scan"
     # a list that overflows is reported, not truncated: those queries take the exact scan, same answers
     eng.set_option("batch_bf16", bf16)

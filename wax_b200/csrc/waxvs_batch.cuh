@@ -1005,9 +1005,10 @@ struct FinishParams {
     uint32_t pow2_all;          // next pow2 >= slices*kprime
     uint32_t rescore;           // nominees re-scored exactly per query: a power of two in [256, kBatchRescoreMax]
     float eps_rel;              // kTf32Eps or kBf16Eps: |score' - score| <= eps_rel * |q||v|
-    float *tau_star;            // [n_queries] or nullptr: threshold for the filter level, in score' units:
-                                // (exact k-th score of the re-scored nominees) - filter_eps_rel * |q| (* max|v|); -inf if none
-    float filter_eps_rel;       // bound of the operand type the FILTER pass will use (TF32)
+    float *tau_star;            // [2][n_queries] or nullptr: thresholds for the filter levels, in score' units:
+                                // (exact k-th score of the re-scored nominees) - eps * |q| (* max|v|); -inf if none.
+                                // [0][q]: eps of a TF32 filter pass, [1][q]: eps of a bf16-shadow filter pass
+    uint32_t tau_stride;        // n_queries of the whole batch (distance between the two arrays)
 };
 
 // One CTA per query.  Union of the slices' nominee heaps -> best kBatchRescore by score' -> exact re-score ->
@@ -1078,7 +1079,7 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
         uint32_t n_exact = 0;
         while (n_exact < kpp && ek[n_exact] != WAXVS_KEY_NONE) ++n_exact;
         uint32_t ok = 1;
-        float tau_star = -INFINITY;
+        float tau_star = -INFINITY, tau_star16 = -INFINITY;
         if (n_exact >= p.k) {
             const float dk = from_orderable_u32(static_cast<uint32_t>(ek[p.k - 1] >> 32));
             const float qn = s_sqrt_a2;
@@ -1096,14 +1097,17 @@ __global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p)
             // are a subset of the corpus), hence score' >= sk_exact - eps_filter: a pass that collects EVERY row above
             // that fixed threshold misses none of them.  A relative 2^-20 margin absorbs the rounding of this
             // subtraction and of the fp32 products sk_exact was built from.
-            const float feps = p.filter_eps_rel * scale * 1.01f + acc_slack + ulp_slack + 1e-30f;
+            const float feps = kTf32Eps * scale * 1.01f + acc_slack + ulp_slack + 1e-30f;
             const float t = sk_exact - feps;
             tau_star = finite_f32(t) ? t - fabsf(t) * 0x1p-20f - 1e-30f : -INFINITY;
+            const float feps16 = kBf16Eps * scale * 1.01f + acc_slack + ulp_slack + 1e-30f;
+            const float t16 = sk_exact - feps16;
+            tau_star16 = finite_f32(t16) ? t16 - fabsf(t16) * 0x1p-20f - 1e-30f : -INFINITY;
         } else if (excluded_any) {
             ok = 0;
         }
         p.ok[q] = ok;
-        if (p.tau_star) p.tau_star[q] = tau_star;
+        if (p.tau_star) { p.tau_star[q] = tau_star; p.tau_star[p.tau_stride + q] = tau_star16; }
     }
     ScanParams sp{};
     sp.out = p.out + static_cast<size_t>(q) * p.k;

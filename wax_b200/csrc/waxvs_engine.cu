@@ -130,6 +130,7 @@ struct Tuning {
     int batch_ares = 1;     // with batch_bf16: keep the CTA's queries resident in shared memory when they fit (dims <= 512)
     int batch_rescore = 0;  // 0 auto; else nominees re-scored exactly per query (256, 512 or 1024)
     int batch_retry = 1;    // queries level 1 cannot prove go through the filter level (TF32, complete by construction) before an exact scan
+    int filter_bf16 = 1;    // unproven queries first get a filter pass over the bf16 shadow (half the bytes of an exact scan)
     int filter_cap = 8192;  // candidates per query the filter level may collect (power of two <= 16384); overflow -> exact scan
     int inline_query = 1;   // host entry points: a query of <= 512 floats travels in the kernel parameters (no H2D copy)
     int host_delivery = 1;  // host entry points: the kernel stores the result in mapped host memory + flag (no D2H copy / sync)
@@ -164,6 +165,7 @@ struct SearchCtx {
     float *d_tau_star = nullptr; size_t tau_star_cap = 0;         // level 1 -> filter level: per-query thresholds
     float *h_tau_star = nullptr; size_t h_tau_star_cap = 0;       // pinned
     float *d_filter_tau = nullptr; size_t filter_tau_cap = 0;     // compacted thresholds of the unproven queries
+    float *h_filter_tau = nullptr; size_t h_filter_tau_cap = 0;   // pinned
     uint32_t *d_cand_count = nullptr; size_t cand_count_cap = 0;
     uint32_t *d_cand_rows = nullptr; size_t cand_rows_cap = 0;
     uint64_t *d_cand_keys = nullptr; size_t cand_keys_cap = 0;
@@ -210,7 +212,7 @@ struct wax_vs_engine {
     uint64_t shadow_rows = 0;      // rows [0, shadow_rows) of d_shadow are valid; shadow_valid = covers every live row
     bool shadow_valid = false, shadow_unavailable = false;
     uint64_t batch_tensor_queries = 0, batch_fallback_queries = 0;   // instrumentation
-    uint64_t batch_bf16_queries = 0, batch_retry_queries = 0, batch_tf32_queries = 0;
+    uint64_t batch_bf16_queries = 0, batch_retry_queries = 0, batch_tf32_queries = 0, batch_filter_bf16_queries = 0;
     // Adaptive level choice: when more than a quarter of a batch fails the coarse bf16 bound (tightly clustered
     // neighbours), the next 16 batches nominate in TF32 straight away, then bf16 is probed again.
     uint32_t bf16_skip_batches = 0;
@@ -289,6 +291,7 @@ static void ctx_free(SearchCtx *c) {
     if (c->d_tau_star) cudaFree(c->d_tau_star);
     if (c->h_tau_star) cudaFreeHost(c->h_tau_star);
     if (c->d_filter_tau) cudaFree(c->d_filter_tau);
+    if (c->h_filter_tau) cudaFreeHost(c->h_filter_tau);
     if (c->d_cand_count) cudaFree(c->d_cand_count);
     if (c->d_cand_rows) cudaFree(c->d_cand_rows);
     if (c->d_cand_keys) cudaFree(c->d_cand_keys);
@@ -823,6 +826,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
             chk(set_smem_attr(batch_tf32_ts_kernel<16>, batch_ts_smem_bytes(16)));
             chk(set_smem_attr(batch_tf32_ts_kernel<64>, batch_ts_smem_bytes(64)));
             chk(set_smem_attr(batch_nominate_kernel<4, 16, false, false, false, true>, batch_smem_bytes(4, 16)));
+            chk(set_smem_attr(batch_nominate_kernel<4, 16, false, true, false, true>, batch_smem_bytes(4, 16)));
+            chk(set_smem_attr(batch_nominate_kernel<3, 16, false, true, true, true>, 227u * 1024u));
             chk(set_smem_attr(filter_select_kernel, 16384 * 8));
             chk(set_smem_attr(batch_finish_kernel<kCosine>, (16384 + kBatchRescoreMax) * 8));
             chk(set_smem_attr(batch_finish_kernel<kDot>, (16384 + kBatchRescoreMax) * 8));
@@ -945,7 +950,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         fp.rescore = rescore;
         fp.eps_rel = bf16 ? kBf16Eps : kTf32Eps;
         fp.tau_star = d_tau_star ? d_tau_star + q0 : nullptr;
-        fp.filter_eps_rel = kTf32Eps;
+        fp.tau_stride = n_queries;
         const size_t fsmem = static_cast<size_t>(pow2 + rescore) * sizeof(uint64_t);
         if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 256, fsmem, stream>>>(fp);
         else batch_finish_kernel<kDot><<<nq, 256, fsmem, stream>>>(fp);
@@ -1439,11 +1444,22 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
 // re-scored nominees - eps_tf32, so no true top-k row can be missing) to the query's candidate list; every candidate
 // is re-scored exactly, the k best are the answer.  Complete by construction -- d_ok[i] = 0 only if a list
 // overflowed (more than filter_cap rows within 2 eps of the k-th score: near-duplicates en masse).
+// bf16 = true: the pass reads the bf16 shadow (half the bytes of the fp32 corpus; d_tau must then be the thresholds built
+// with the bf16 bound, which admit more candidates); false: TF32 from the fp32 corpus.
 static int32_t enqueue_filter_level(wax_vs_engine *e, SearchCtx *c, const float *d_queries, const float *d_tau,
                                     uint32_t n_queries, uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out,
-                                    uint32_t *d_ok, const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches) {
+                                    uint32_t *d_ok, const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
+                                    bool bf16 = false) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
+    if (bf16) {
+        const size_t qn = static_cast<size_t>(n_queries) * e->dims;
+        if ((rc = ensure_dev(&c->d_queries_bf16, &c->queries_bf16_cap, qn, "bf16 queries"))) return rc;
+        const int g = static_cast<int>(std::min<size_t>((qn / 4 + 255) / 256, static_cast<size_t>(e->sm_count) * 8));
+        shadow_bf16_kernel<<<std::max(g, 1), 256, 0, stream>>>(d_queries, nullptr, n_queries, e->dims, c->d_queries_bf16);
+        CUDA_TRY(cudaGetLastError());
+        ++*launches;
+    }
     uint32_t cap = 64;                      // a power of two in [64, 16384], at least k
     while ((cap < static_cast<uint32_t>(std::max(e->tune.filter_cap, 64)) || cap < k_eff) && cap < 16384u) cap <<= 1;
     if ((rc = ensure_dev(&c->d_cand_count, &c->cand_count_cap, static_cast<size_t>(n_queries), "filter counts"))) return rc;
@@ -1458,18 +1474,34 @@ static int32_t enqueue_filter_level(wax_vs_engine *e, SearchCtx *c, const float 
         const uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(static_cast<uint32_t>(e->sm_count) / groups, tiles_total));
         CUtensorMap map_q, map_c;
         const float *qbase = d_queries + static_cast<size_t>(q0) * e->dims;
-        if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
-        if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, kBatchN))) return rc;
+        if (bf16) {
+            if ((rc = make_tensor_map(&map_q, c->d_queries_bf16 + static_cast<size_t>(q0) * e->dims, nq, e->dims, kBatchM, true))) return rc;
+            if ((rc = make_tensor_map(&map_c, e->d_shadow, e->n_rows, e->dims, kBatchN, true))) return rc;
+        } else {
+            if ((rc = make_tensor_map(&map_q, qbase, nq, e->dims, kBatchM))) return rc;
+            if ((rc = make_tensor_map(&map_c, e->d_corpus, e->n_rows, e->dims, kBatchN))) return rc;
+        }
         BatchParams bp{};
         bp.n_rows = static_cast<uint32_t>(e->n_rows); bp.dims = e->dims; bp.n_queries = nq; bp.groups = groups;
         bp.slices = slices; bp.tiles_total = tiles_total; bp.kprime = 16; bp.metric = e->similarity;
-        bp.row_scale = e->similarity == WAX_VS_COSINE ? e->d_inv_norm : nullptr;
+        bp.row_scale = (e->similarity == WAX_VS_COSINE && !bf16) ? e->d_inv_norm : nullptr;   // shadow rows are pre-normalised
         bp.tau_fixed = d_tau + q0;
         bp.cand_count = c->d_cand_count + q0;
         bp.cand_rows = c->d_cand_rows + static_cast<size_t>(q0) * cap;
         bp.cand_cap = cap;
-        CUDA_TRY(launch_nominate(batch_nominate_kernel<4, 16, false, false, false, true>, groups * slices, batch_smem_bytes(4, 16),
-                                 false, stream, map_q, map_c, bp));
+        if (bf16) {
+            const uint32_t num_kb = e->dims / kBatchKBlockBf16;
+            const int st = e->tune.batch_ares ? ares_stages(false, 16, num_kb, 3) : 0;
+            if (st >= 3)
+                CUDA_TRY(launch_nominate(batch_nominate_kernel<3, 16, false, true, true, true>, groups * slices,
+                                         batch_ares_smem_bytes(3, 16, false, static_cast<int>(num_kb)), false, stream, map_q, map_c, bp));
+            else
+                CUDA_TRY(launch_nominate(batch_nominate_kernel<4, 16, false, true, false, true>, groups * slices, batch_smem_bytes(4, 16),
+                                         false, stream, map_q, map_c, bp));
+        } else {
+            CUDA_TRY(launch_nominate(batch_nominate_kernel<4, 16, false, false, false, true>, groups * slices, batch_smem_bytes(4, 16),
+                                     false, stream, map_q, map_c, bp));
+        }
         const dim3 rgrid(32, nq);
         if (e->similarity == WAX_VS_COSINE)
             filter_rescore_kernel<kCosine><<<rgrid, 256, 0, stream>>>(e->d_corpus, qbase, e->dims, bp.cand_count, bp.cand_rows, cap,
@@ -1509,14 +1541,14 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         // proves completeness; unproven queries (rare) are re-run on the exact single-query path below.
         if ((rc = ensure_dev(&c->d_ok, &c->ok_cap, static_cast<size_t>(n_queries), "proof flags"))) return rc;
         if ((rc = ensure_pinned(&c->h_ok, &c->h_ok_cap, static_cast<size_t>(n_queries), "proof flag staging"))) return rc;
-        if ((rc = ensure_dev(&c->d_tau_star, &c->tau_star_cap, static_cast<size_t>(n_queries), "filter thresholds"))) return rc;
-        if ((rc = ensure_pinned(&c->h_tau_star, &c->h_tau_star_cap, static_cast<size_t>(n_queries), "filter threshold staging"))) return rc;
+        if ((rc = ensure_dev(&c->d_tau_star, &c->tau_star_cap, static_cast<size_t>(n_queries) * 2, "filter thresholds"))) return rc;
+        if ((rc = ensure_pinned(&c->h_tau_star, &c->h_tau_star_cap, static_cast<size_t>(n_queries) * 2, "filter threshold staging"))) return rc;
         bool used_bf16 = false;
         rc = enqueue_batch_tensor(e, c, d_queries, n_queries, k_eff, row_offset, d_out, c->d_ok, d_ids, c->stream, launches,
                                   allow_bf16, &used_bf16, c->d_tau_star);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-        CUDA_TRY(cudaMemcpyAsync(c->h_tau_star, c->d_tau_star, n_queries * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+        CUDA_TRY(cudaMemcpyAsync(c->h_tau_star, c->d_tau_star, 2 * n_queries * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         std::vector<uint32_t> unproven;
         for (uint32_t qi = 0; qi < n_queries; ++qi) if (!c->h_ok[qi]) unproven.push_back(qi);
@@ -1524,38 +1556,58 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
             std::lock_guard<std::mutex> pg(e->pool_mu);
             e->bf16_skip_batches = 16;
         }
-        uint64_t retried = 0;
-        if (e->tune.batch_retry && unproven.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1))) {
-            // Level 2, the filter level: the unproven queries with a finite threshold, as one compacted sub-batch.
-            std::vector<uint32_t> sub, rest;
-            for (uint32_t qi : unproven) (std::isfinite(c->h_tau_star[qi]) ? sub : rest).push_back(qi);
-            const uint32_t nf = static_cast<uint32_t>(sub.size());
-            if (nf) {
-                retried = nf;
-                if ((rc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "filter-level queries"))) return rc;
-                if ((rc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "filter-level results"))) return rc;
-                if ((rc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "filter-level flags"))) return rc;
-                if ((rc = ensure_dev(&c->d_filter_tau, &c->filter_tau_cap, static_cast<size_t>(nf), "filter-level thresholds"))) return rc;
-                // compact on the host side of the pinned staging (h_tau_star is free again after the read above)
-                std::vector<float> taus(nf);
-                for (uint32_t i = 0; i < nf; ++i) taus[i] = c->h_tau_star[sub[i]];
-                memcpy(c->h_tau_star, taus.data(), nf * sizeof(float));
-                CUDA_TRY(cudaMemcpyAsync(c->d_filter_tau, c->h_tau_star, nf * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-                for (uint32_t i = 0; i < nf; ++i)
-                    CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
-                                             d_queries + static_cast<size_t>(sub[i]) * e->dims, e->dims * sizeof(float),
-                                             cudaMemcpyDeviceToDevice, c->stream));
-                rc = enqueue_filter_level(e, c, c->d_retry_q, c->d_filter_tau, nf, k_eff, row_offset, c->d_retry_out,
-                                          c->d_retry_ok, d_ids, c->stream, launches);
-                if (rc) { cudaStreamSynchronize(c->stream); return rc; }
-                for (uint32_t i = 0; i < nf; ++i)
-                    CUDA_TRY(cudaMemcpyAsync(d_out + static_cast<size_t>(sub[i]) * k_eff,
+        uint64_t retried = 0, retried_bf16 = 0;
+        // Level 2, the filter levels: the unproven queries that have a finite threshold, as one compacted sub-batch, get
+        // ONE more tensor-core pass that keeps no heap -- it lists every row above the query's fixed threshold (complete
+        // by construction).  First over the bf16 shadow when level 1 used it (half the bytes of an exact scan, so it pays
+        // even for a single query; its wider bound admits more candidates), then -- for the lists that overflowed, and
+        // only for sub-batches worth a tensor pass -- in TF32 over the fp32 corpus.  What is left takes the exact scan.
+        auto filter_pass = [&](std::vector<uint32_t> &todo, bool bf16lvl) -> int32_t {
+            const uint32_t nf = static_cast<uint32_t>(todo.size());
+            int32_t frc;
+            if ((frc = ensure_dev(&c->d_retry_q, &c->retry_q_cap, static_cast<size_t>(nf) * e->dims, "filter-level queries"))) return frc;
+            if ((frc = ensure_dev(&c->d_retry_out, &c->retry_out_cap, static_cast<size_t>(nf) * k_eff, "filter-level results"))) return frc;
+            if ((frc = ensure_dev(&c->d_retry_ok, &c->retry_ok_cap, static_cast<size_t>(nf), "filter-level flags"))) return frc;
+            if ((frc = ensure_dev(&c->d_filter_tau, &c->filter_tau_cap, static_cast<size_t>(nf), "filter-level thresholds"))) return frc;
+            if ((frc = ensure_pinned(&c->h_filter_tau, &c->h_filter_tau_cap, static_cast<size_t>(nf), "filter-level threshold staging"))) return frc;
+            const float *taus = c->h_tau_star + (bf16lvl ? n_queries : 0u);      // [0]: TF32 bound, [1]: bf16 bound
+            for (uint32_t i = 0; i < nf; ++i) c->h_filter_tau[i] = taus[todo[i]];
+            CUDA_TRY(cudaMemcpyAsync(c->d_filter_tau, c->h_filter_tau, nf * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+            for (uint32_t i = 0; i < nf; ++i)
+                CUDA_TRY(cudaMemcpyAsync(c->d_retry_q + static_cast<size_t>(i) * e->dims,
+                                         d_queries + static_cast<size_t>(todo[i]) * e->dims, e->dims * sizeof(float),
+                                         cudaMemcpyDeviceToDevice, c->stream));
+            frc = enqueue_filter_level(e, c, c->d_retry_q, c->d_filter_tau, nf, k_eff, row_offset, c->d_retry_out,
+                                       c->d_retry_ok, d_ids, c->stream, launches, bf16lvl);
+            if (frc) { cudaStreamSynchronize(c->stream); return frc; }
+            CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+            CUDA_TRY(cudaStreamSynchronize(c->stream));
+            std::vector<uint32_t> overflowed;
+            for (uint32_t i = 0; i < nf; ++i) {
+                if (c->h_ok[i])
+                    CUDA_TRY(cudaMemcpyAsync(d_out + static_cast<size_t>(todo[i]) * k_eff,
                                              c->d_retry_out + static_cast<size_t>(i) * k_eff, k_eff * sizeof(wax_vs_candidate),
                                              cudaMemcpyDeviceToDevice, c->stream));
-                CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-                CUDA_TRY(cudaStreamSynchronize(c->stream));
-                for (uint32_t i = 0; i < nf; ++i) if (!c->h_ok[i]) rest.push_back(sub[i]);
+                else
+                    overflowed.push_back(todo[i]);
             }
+            todo.swap(overflowed);
+            return WAX_VS_OK;
+        };
+        if (e->tune.batch_retry && !unproven.empty()) {
+            std::vector<uint32_t> todo, rest;
+            for (uint32_t qi : unproven)
+                ((std::isfinite(c->h_tau_star[qi]) && std::isfinite(c->h_tau_star[n_queries + qi])) ? todo : rest).push_back(qi);
+            if (!todo.empty() && used_bf16 && e->tune.filter_bf16) {
+                retried_bf16 = todo.size();
+                if ((rc = filter_pass(todo, true))) return rc;
+            }
+            if (todo.size() >= static_cast<size_t>(std::max(e->tune.batch_min, 1))) {
+                retried = todo.size();
+                if ((rc = filter_pass(todo, false))) return rc;
+            }
+            rest.insert(rest.end(), todo.begin(), todo.end());
+            std::sort(rest.begin(), rest.end());
             unproven.swap(rest);
         }
         for (uint32_t qi : unproven) {
@@ -1570,6 +1622,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
             if (used_bf16) e->batch_bf16_queries += n_queries;
             else e->batch_tf32_queries += n_queries;
             e->batch_retry_queries += retried;
+            e->batch_filter_bf16_queries += retried_bf16;
         }
     } else {
         for (uint32_t qi = 0; qi < n_queries; ++qi) {
@@ -2347,7 +2400,8 @@ int32_t wax_vs_debug_counter(wax_vs_engine *e, const char *name, uint64_t *out) 
     if (!strcmp(name, "batch_tensor_queries")) *out = e->batch_tensor_queries;
     else if (!strcmp(name, "batch_fallback_queries")) *out = e->batch_fallback_queries;
     else if (!strcmp(name, "batch_bf16_queries")) *out = e->batch_bf16_queries;
-    else if (!strcmp(name, "batch_retry_queries")) *out = e->batch_retry_queries;
+    else if (!strcmp(name, "batch_retry_queries")) *out = e->batch_retry_queries;               // TF32 filter level
+    else if (!strcmp(name, "batch_filter_bf16_queries")) *out = e->batch_filter_bf16_queries;   // bf16-shadow filter level
     else if (!strcmp(name, "shadow_bytes")) *out = e->shadow_valid ? e->shadow_rows * e->dims * sizeof(__nv_bfloat16) : 0;   // live rows
     else if (!strcmp(name, "shadow_capacity_bytes")) *out = e->shadow_cap * sizeof(__nv_bfloat16);                            // HBM held
     else if (!strcmp(name, "shadow_unavailable")) *out = e->shadow_unavailable ? 1 : 0;   // bf16 shadow did not fit: TF32 level runs
@@ -2427,6 +2481,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_rescore")) e->tune.batch_rescore = v;
     else if (!strcmp(key, "batch_retry")) e->tune.batch_retry = v;
     else if (!strcmp(key, "filter_cap")) e->tune.filter_cap = v;
+    else if (!strcmp(key, "filter_bf16")) e->tune.filter_bf16 = v;
     else if (!strcmp(key, "single_shadow")) e->tune.single_shadow = v;
     else if (!strcmp(key, "shard_fused")) e->tune.shard_fused = v;
     else if (!strcmp(key, "inline_query")) e->tune.inline_query = v;
