@@ -134,6 +134,7 @@ struct Tuning {
     int filter_cap = 8192;  // candidates per query the filter level may collect (power of two <= 16384); overflow -> exact scan
     int inline_query = 1;   // host entry points: a query of <= 512 floats travels in the kernel parameters (no H2D copy)
     int host_delivery = 1;  // host entry points: the kernel stores the result in mapped host memory + flag (no D2H copy / sync)
+    int tail_select = 0;    // TMA-staged kernels: radix-selection tail instead of pairwise list merges (same results)
     int shard_fused = 1;    // sharded search: exchange + merge inside the scan launch (0: separate 1-CTA launch)
     int single_shadow = 0;  // 1: single queries / batches below batch_min also take the bf16-shadow nominations
                             // (half the HBM bytes per query: 1.19 vs 2.04 ms at 10 M x 384, same results); off by
@@ -388,7 +389,7 @@ struct TmaConfig { int C, R, warps, stages; size_t smem; };
 static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
     const uint32_t d = e->dims;
     if (d % 4u != 0) return false;                      // rows must be 16-byte multiples for the bulk copy
-    const size_t budget = e->smem_optin ? e->smem_optin : 232448;
+    const size_t budget = (e->smem_optin ? e->smem_optin : 232448) - 4096;   // minus the kernels' static shared memory
     int C = 0;
     if (d % 128u == 0) {
         const int c = static_cast<int>(d / 128u);
@@ -592,9 +593,14 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         p.host_out = host->host_out; p.host_flag = host->host_flag; p.host_seq = host->seq;
         const_cast<HostDelivery *>(host)->delivered = true;
     }
+    if (use_tma && !emit && e->tune.tail_select) {   // selection tail: the idle ring is its staging area
+        p.tail_select = 1u;
+        p.tail_smem_bytes = static_cast<uint32_t>(static_cast<size_t>(cfg.warps) * cfg.stages * cfg.R * e->dims * sizeof(float));
+    }
     bool fused_exchange = false;
     if (shard && !emit) {     // the merge keys (world * k uint32) live in the kernel's block-list shared memory
-        const size_t list_bytes = static_cast<size_t>(use_tma ? cfg.warps : 8) * 32 * (mode == 0 ? 1 : 4) * sizeof(uint64_t);
+        const size_t list_bytes = p.tail_select ? p.tail_smem_bytes
+                                                : static_cast<size_t>(use_tma ? cfg.warps : 8) * 32 * (mode == 0 ? 1 : 4) * sizeof(uint64_t);
         fused_exchange = e->tune.shard_fused != 0 && static_cast<size_t>(shard->world) * k_eff * sizeof(uint32_t) <= list_bytes;
         if (fused_exchange) { p.shard = *shard; p.shard.final_out = d_merged; }
     }
@@ -2484,6 +2490,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "filter_bf16")) e->tune.filter_bf16 = v;
     else if (!strcmp(key, "single_shadow")) e->tune.single_shadow = v;
     else if (!strcmp(key, "shard_fused")) e->tune.shard_fused = v;
+    else if (!strcmp(key, "tail_select")) e->tune.tail_select = v;
     else if (!strcmp(key, "inline_query")) e->tune.inline_query = v;
     else if (!strcmp(key, "host_delivery")) e->tune.host_delivery = v;
     else if (!strcmp(key, "shard_timeout_ms")) e->shard.timeout_ns = static_cast<unsigned long long>(std::max<int64_t>(value, 1)) * 1000000ull;

@@ -56,6 +56,11 @@ struct ScanParams {
     unsigned long long *host_flag;      // mapped pinned: set to host_seq once host_out is complete
     unsigned long long host_seq;
     alignas(16) float query_inline[kInlineQueryFloats];   // used when query == nullptr (TMA-staged kernels, dims <= kInlineQueryFloats)
+    // Tail of the launch: 0 = pairwise bitonic merges of sorted lists (warp lists -> block list -> last CTA merges the
+    // grid's block lists), 1 = exact radix SELECTION (finish_topk_select): block-wide k-th-smallest over the keys, the
+    // last CTA selects over grid x k keys staged in `tail_smem_bytes` of the (by then idle) ring.  Same result bits.
+    uint32_t tail_select;
+    uint32_t tail_smem_bytes;
     ShardParams shard;          // shard.world > 0: `out` is this rank's local list and the last CTA goes on to exchange it
                                 // with the other ranks over NVLink and to merge (waxvs_shard.cuh): still the same launch
 };
@@ -153,6 +158,136 @@ __device__ __forceinline__ void finish_topk(const ScanParams &p, WarpTopK<E> &tk
     // Row-sharded search: push the local list to every rank, wait for theirs, merge -- the block lists are done with,
     // their shared memory holds the distance keys of the merge (the host checks that world * k * 4 bytes fit).
     if (p.shard.world) shard_exchange_cta(p.shard, p.out, p.k, reinterpret_cast<uint32_t *>(lists));
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// Selection tail (round 2).  The merge tail above costs one ~150-instruction bitonic merge per pair of lists: 7 per
+// CTA plus ~150 for the grid in the last CTA -- ~20 us at k = 10 and ~65 us at k = 72, which is most of a search over a
+// real (<= 174 K-row) Wax index.  Selection does not care about order: a block-wide MSB-first radix select (8 bits a
+// pass, it stops as soon as the bin holding the k-th key holds one key) finds the k-th smallest key exactly, the keys
+// at or below it are the answer; only the final k are ranked (k x k compares) to come out sorted.
+struct SelectScratch {
+    uint32_t hist[256];
+    uint64_t sel[128];          // the selected keys of the final stage
+    uint32_t digit, k_rem, in_bin, n_sel;
+    unsigned long long found;
+};
+
+// All threads of the CTA call.  for_each(f): f(key) for every key the calling thread owns (WAXVS_KEY_NONE = absent; it
+// is the largest key, so it only matters when fewer than k real keys exist).  Returns the k-th smallest key of the CTA's
+// keys (WAXVS_KEY_NONE when there are fewer than k real ones): the selection is {key <= result, key != NONE}.
+template <typename ForEach>
+__device__ __forceinline__ uint64_t block_select_kth(ForEach for_each, uint32_t k, SelectScratch *ss) {
+    const uint32_t tid = threadIdx.x;
+    uint64_t prefix = 0;
+    uint32_t k_rem = k;
+#pragma unroll 1
+    for (int shift = 56; shift >= 0; shift -= 8) {
+        for (uint32_t i = tid; i < 256u; i += blockDim.x) ss->hist[i] = 0;
+        __syncthreads();
+        const uint64_t want = (shift == 56) ? 0ull : (prefix >> (shift + 8));
+        for_each([&](uint64_t key) {
+            if (shift == 56 || (key >> (shift + 8)) == want) atomicAdd(&ss->hist[(key >> shift) & 255u], 1u);
+        });
+        __syncthreads();
+        if (tid < 32) {             // the digit whose cumulative count reaches k_rem: 8 bins per lane + a warp scan
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { c[i] = ss->hist[tid * 8 + i]; sum += c[i]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const uint32_t up = __shfl_up_sync(WAXVS_FULL_MASK, incl, off);
+                if (static_cast<int>(tid) >= off) incl += up;
+            }
+            const uint32_t excl = incl - sum;
+            if (excl < k_rem && k_rem <= incl) {      // exactly one lane
+                uint32_t run = excl;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    if (run < k_rem && k_rem <= run + c[i]) { ss->digit = tid * 8 + i; ss->k_rem = k_rem - run; ss->in_bin = c[i]; }
+                    run += c[i];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= static_cast<uint64_t>(ss->digit) << shift;
+        k_rem = ss->k_rem;
+        if (ss->in_bin == 1u && shift > 0) {          // one key carries this prefix: it is the k-th smallest -- fetch it
+            const uint64_t top = prefix >> shift;
+            for_each([&](uint64_t key) { if ((key >> shift) == top) ss->found = key; });
+            __syncthreads();
+            const uint64_t x = ss->found;
+            __syncthreads();
+            return x;
+        }
+    }
+    return prefix;
+}
+
+// The selection tail: called by every thread of the CTA after the scan loop (the warps' register lists need not be
+// merged, or even sorted, for this).  scratch = the dynamic shared memory (the idle ring), p.tail_smem_bytes of it.
+template <int E>
+__device__ __forceinline__ void finish_topk_select(const ScanParams &p, WarpTopK<E> &tk, unsigned char *scratch) {
+    __shared__ SelectScratch ss;
+    __shared__ uint32_t s_last2;
+    const uint32_t tid = threadIdx.x, nthr = blockDim.x, k = p.k;
+    // ---- stage A: this CTA's k smallest keys -> block_keys[blockIdx][0..k) (unordered, NONE-padded)
+    auto own_keys = [&](auto f) {
+#pragma unroll
+        for (int j = 0; j < E; ++j) f(tk.key[j]);
+    };
+    const uint64_t xa = block_select_kth(own_keys, k, &ss);
+    if (tid == 0) ss.n_sel = 0;
+    __syncthreads();
+    uint64_t *mine = p.block_keys + static_cast<size_t>(blockIdx.x) * k;
+#pragma unroll
+    for (int j = 0; j < E; ++j)
+        if (tk.key[j] != WAXVS_KEY_NONE && tk.key[j] <= xa) mine[atomicAdd(&ss.n_sel, 1u)] = tk.key[j];
+    __syncthreads();
+    for (uint32_t i = ss.n_sel + tid; i < k; i += nthr) mine[i] = WAXVS_KEY_NONE;
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last2 = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+    __syncthreads();
+    if (!s_last2) return;
+    __threadfence();
+    // ---- stage B (last CTA): the k smallest of the grid's gridDim.x * k keys, ranked, written out
+    const uint32_t total = gridDim.x * k;
+    const bool staged = static_cast<size_t>(total) * sizeof(uint64_t) <= p.tail_smem_bytes;
+    uint64_t *sk = reinterpret_cast<uint64_t *>(scratch);
+    if (staged) {
+        for (uint32_t i = tid; i < total; i += nthr) sk[i] = ld_cg_u64(p.block_keys + i);
+        __syncthreads();
+    }
+    auto grid_keys = [&](auto f) {
+        if (staged) { for (uint32_t i = tid; i < total; i += nthr) f(sk[i]); }
+        else { for (uint32_t i = tid; i < total; i += nthr) f(ld_cg_u64(p.block_keys + i)); }
+    };
+    const uint64_t xb = block_select_kth(grid_keys, k, &ss);
+    if (tid == 0) ss.n_sel = 0;
+    __syncthreads();
+    grid_keys([&](uint64_t key) { if (key != WAXVS_KEY_NONE && key <= xb) ss.sel[atomicAdd(&ss.n_sel, 1u)] = key; });
+    __syncthreads();
+    const uint32_t n_sel = ss.n_sel;                  // == k, or every real key when there are fewer than k
+    for (uint32_t i = tid; i < k; i += nthr) {
+        if (i < n_sel) {
+            const uint64_t key = ss.sel[i];
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < n_sel; ++j) rank += ss.sel[j] < key ? 1u : 0u;
+            write_candidate(p, static_cast<int>(rank), key);
+        } else {
+            write_candidate(p, static_cast<int>(i), WAXVS_KEY_NONE);      // padding after the n_sel ranked entries
+        }
+    }
+    if (p.host_flag && !p.shard.world) __threadfence_system();
+    __syncthreads();
+    if (tid == 0) {
+        *p.ticket = 0u;
+        if (p.work_counter) *p.work_counter = 0u;
+        if (p.host_flag && !p.shard.world) st_release_sys_u64(p.host_flag, p.host_seq);
+    }
+    if (p.shard.world) shard_exchange_cta(p.shard, p.out, p.k, reinterpret_cast<uint32_t *>(scratch));
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -348,7 +483,8 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
 
     if (!EMIT) {
         if (E > 1) tk.flush(lane, k);
-        finish_topk<E>(p, tk, lists, warp, lane, warps);
+        if (p.tail_select) finish_topk_select<E>(p, tk, smem);
+        else finish_topk<E>(p, tk, lists, warp, lane, warps);
     }
 }
 
