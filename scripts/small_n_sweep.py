@@ -19,12 +19,13 @@ q = rng.standard_normal(384).astype(np.float32)
 for rows in (10_000, 100_000, 174_000):
     eng = CUDAVectorEngine(VectorMetric.cosine, 384)
     eng.fill_synthetic(2, rows)
-    for grid, warps, chunk in itertools.product((0, 16, 32, 64, 96), (0, 4, 16), (8, 2)):
+    for tail, grid, warps, chunk in itertools.product((0, 1), (0, 16, 32, 64, 96), (0, 4, 16), (8, 2)):
         eng.set_option("grid", grid); eng.set_option("warps", warps); eng.set_option("chunk_steps", chunk)
+        eng.set_option("tail_select", tail)
         n = 300
         ms, _ = eng.time_search(10, n, warmup=10, n_queries=8)
         ms72, _ = eng.time_search(72, n, warmup=10, n_queries=8)
-        rec = {"rows": rows, "grid": grid or 148, "warps": warps or 8, "chunk_steps": chunk,
+        rec = {"rows": rows, "tail_select": tail, "grid": grid or 148, "warps": warps or 8, "chunk_steps": chunk,
                "kernel_us_k10": round(ms / n * 1e3, 2), "kernel_us_k72": round(ms72 / n * 1e3, 2)}
         if grid == 0 and warps == 0 and chunk == 8:
             for delivery, inline in ((1, 1), (1, 0), (0, 0)):
@@ -36,5 +37,11 @@ for rows in (10_000, 100_000, 174_000):
                     eng.search(q, 10)
                 rec[f"e2e_us_delivery{delivery}_inline{inline}"] = round((time.perf_counter() - t0) / 500 * 1e6, 2)
             eng.set_option("host_delivery", 1); eng.set_option("inline_query", 1)
+            if tail:                                   # what the selection tail does for the sharded form (world 1)
+                blob = eng.shard_open(0, 1, 0)
+                eng.shard_connect([blob])
+                msx, _ = eng.time_shard_search(10, n, warmup=10, n_queries=8)
+                rec["kernel_us_k10_with_exchange_world1"] = round(msx / n * 1e3, 2)
+                eng.shard_close()
         print(json.dumps(rec), flush=True)
     eng.close()
