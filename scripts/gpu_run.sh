@@ -8,6 +8,8 @@
 #   batch      scripts/bench_batch.py (configs[2],[4]; bf16 then tf32)
 #   ingest     scripts/ingest_bench.py             latency    scripts/latency.py
 #   ncu-small  ncu --set full of the fused scan at 10 K rows (k = 10, k = 72): where the fixed cost goes
+#   shape      scripts/shape_sweep.py (warps x tail at 174 K ... 10 M rows)
+#   c5-launches  ncu launch list of the configs[4] batch (nominate vs finish kernel time)
 #   small-n    scripts/small_n_sweep.py (launch shape vs latency at 10 K .. 174 K rows)
 #   batch-sweep  kernel-shape options of the batched path on configs[2] / [4]
 #   launches   ncu launch list of bench.py         ncu-scan   ncu --set full of the fused scan kernel
@@ -34,6 +36,9 @@ for step in "$@"; do
     ncu-small) timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_tma -s 4 -c 2 -o $OUT/ncu_small_$TAG -f \
                 python scripts/small_n_probe.py 10000 > $OUT/ncu_small_$TAG.log 2>&1
               ncu -i $OUT/ncu_small_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_small_${TAG}_summary.csv; cut -c1-300 $OUT/ncu_small_${TAG}_summary.csv ;;
+    shape) timeout 900 python scripts/shape_sweep.py 2>&1 | tee $OUT/shape_sweep_$TAG.jsonl | cut -c1-200 ;;
+    c5-launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/ncu_launches_c5_$TAG.csv \
+                python scripts/bench_batch.py 3 bf16 only=1 > $OUT/ncu_launches_c5_$TAG.log 2>&1; grep -E "batch_|shadow" $OUT/ncu_launches_c5_$TAG.csv | tail -8 | cut -c1-260 ;;
     small-n) timeout 900 python scripts/small_n_sweep.py 2>&1 | tee $OUT/small_n_$TAG.jsonl | cut -c1-260 ;;
     batch-sweep) for o in "only=1 batch_pair=1" "only=1 batch_pair=1 batch_heap=16" "only=1 batch_heap=16" "only=0 batch_pair=1" "only=0 batch_ares=0" "only=0 batch_pair=1 batch_ares=0"; do
              timeout 400 python scripts/bench_batch.py 10 bf16 $o 2>&1 | tail -1 | tee -a $OUT/batch_sweep_$TAG.jsonl | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['options'], d['ms_per_batch'], d['roofline']['frac'], d['exact_fallback_queries'])"; done ;;

@@ -281,7 +281,8 @@ def test_single_shadow_mode_routes_single_queries_through_the_shadow(oracle):
     eng.set_option("single_shadow", 0)
     assert got200 == eng.search(qs[0], 200)
     eng.set_option("single_shadow", 1)
-    # near-duplicates of the query: unprovable at bf16 -> exact scan, identical result, bf16 level suspended
+    # near-duplicates of the query: unprovable at bf16 level 1 -> one filter pass over the shadow (400 candidates, still
+    # half the bytes of the exact scan) answers it, identical result; the bf16 level is suspended for the next queries
     base = oracle.synth_row(1202, 0, dims, True)
     rng = np.random.default_rng(9)
     dup = base + rng.standard_normal((400, dims)).astype(np.float32) * np.float32(1e-6)
@@ -291,7 +292,8 @@ def test_single_shadow_mode_routes_single_queries_through_the_shadow(oracle):
     eng.set_option("single_shadow", 1)
     n0 = eng.counter("batch_bf16_queries")
     assert eng.search(base, 10) == want
-    assert eng.counter("batch_bf16_queries") == n0 + 1 and eng.batch_stats()[1] == 1
+    assert eng.counter("batch_bf16_queries") == n0 + 1
+    assert eng.batch_stats()[1] == 0 and eng.counter("batch_filter_bf16_queries") == 1
     assert eng.search(qs[1], 10) == expect[1]
     assert eng.counter("batch_bf16_queries") == n0 + 1          # suspended: answered by the fp32 scan
 

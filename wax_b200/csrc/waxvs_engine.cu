@@ -86,6 +86,12 @@ struct IdMap {
         mask = cap - 1;
         used = 0;
     }
+    void prefetch(uint64_t id) const {
+        if (vals.empty()) return;
+        const size_t i = mix(id) & mask;
+        __builtin_prefetch(&keys[i]);
+        __builtin_prefetch(&vals[i]);
+    }
     uint32_t find(uint64_t id) const {
         if (vals.empty()) return 0xFFFFFFFFu;
         for (size_t i = mix(id) & mask;; i = (i + 1) & mask) {
@@ -117,7 +123,8 @@ struct Tuning {
     int grid = 0;         // 0 = one CTA per SM
     int l2_hint = 0;
     int ldg_ctas_per_sm = 4;
-    int chunk_steps = 8;    // dynamic scheduling granularity of the TMA kernel (0 = static round-robin)
+    int chunk_steps = -1;   // dynamic scheduling granularity of the TMA kernel: -1 auto (8 steps, fewer when the corpus gives
+                            // each warp only a few steps: 10 K rows = 2 500 steps over 1 184 warps), 0 = static round-robin
     int fused_k_max = 128;  // k <= this stays in the single fused launch (register lists); larger k: emit + radix select
     int batch_tensor = 1;   // 1: batches take the tcgen05 TF32 nominate + exact re-score path when eligible
     int batch_min = 4;      // smallest batch routed to the tensor path
@@ -134,7 +141,7 @@ struct Tuning {
     int filter_cap = 8192;  // candidates per query the filter level may collect (power of two <= 16384); overflow -> exact scan
     int inline_query = 1;   // host entry points: a query of <= 512 floats travels in the kernel parameters (no H2D copy)
     int host_delivery = 1;  // host entry points: the kernel stores the result in mapped host memory + flag (no D2H copy / sync)
-    int tail_select = 0;    // TMA-staged kernels: radix-selection tail instead of pairwise list merges (same results)
+    int tail_select = 1;    // TMA-staged kernels: radix-selection tail instead of pairwise list merges (same results)
     int shard_fused = 1;    // sharded search: exchange + merge inside the scan launch (0: separate 1-CTA launch)
     int single_shadow = 0;  // 1: single queries / batches below batch_min also take the bf16-shadow nominations
                             // (half the HBM bytes per query: 1.19 vs 2.04 ms at 10 M x 384, same results); off by
@@ -560,7 +567,7 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     p.block_keys = c->d_block_keys; p.ticket = c->d_ticket; p.out = d_out;
     p.frame_ids = d_ids; p.id_base = e->id_base; p.row_offset = row_offset;
     p.use_l2_hint = e->tune.l2_hint ? 1u : 0u;
-    p.chunk_steps = e->tune.chunk_steps > 0 ? static_cast<uint32_t>(e->tune.chunk_steps) : 0u;
+    p.chunk_steps = e->tune.chunk_steps > 0 ? static_cast<uint32_t>(e->tune.chunk_steps) : 0u;   // auto: set below
     p.work_counter = c->d_ticket + 1;
     p.mask = d_mask;
 
@@ -612,6 +619,8 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
         const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count;
         grid = static_cast<int>(std::min<uint64_t>(max_grid, (steps + cfg.warps - 1) / cfg.warps));
         grid = std::max(std::min(grid, grid_cap), 1);
+        if (e->tune.chunk_steps < 0)     // auto: about two claims per warp at least (profiles/small_n_r02.jsonl), at most 8 steps
+            p.chunk_steps = static_cast<uint32_t>(std::max<uint64_t>(1, std::min<uint64_t>(8, steps / (static_cast<uint64_t>(grid) * cfg.warps * 2))));
         CUDA_TRY(launch_tma(e, p, grid, cfg, e->similarity, mode, stream));
     } else {
         const int max_grid = e->tune.grid > 0 ? e->tune.grid : e->sm_count * e->tune.ldg_ctas_per_sm;
@@ -1142,7 +1151,17 @@ int32_t wax_vs_reserve(wax_vs_engine *e, uint64_t rows) {
     std::unique_lock<std::shared_mutex> w(e->rw);
     DeviceGuard g(e->device);
     drain_device_path(e);
-    return set_capacity(e, rows);
+    int32_t rc = set_capacity(e, rows);
+    if (rc == WAX_VS_OK && !e->ids_identity && rows > e->ids.capacity()) {
+        e->ids.reserve(rows);                       // no id-array / hash-table regrowth during the appends that follow
+        if (e->map_valid && e->map.keys.size() < rows * 2 + 16) {
+            IdMap bigger;
+            bigger.reset(rows);
+            for (size_t r = 0; r < e->ids.size(); ++r) bigger.put(e->ids[r], static_cast<uint32_t>(r));
+            e->map = std::move(bigger);
+        }
+    }
+    return rc;
 }
 
 // Phase trace of the mutators for performance work: WAXVS_TRACE_INGEST=1 prints "<what>: <phase> <us>" lines to stderr.
@@ -1179,19 +1198,33 @@ static int32_t ingest_init(wax_vs_engine *e) {
     g.threads = static_cast<int>(std::max(1u, std::min(8u, hw ? hw : 1u)));
     return WAX_VS_OK;
 }
+// The two large pinned staging buffers are shared by every engine of the process (pinning 2 x 64 MB costs ~0.1 s, far
+// more than most transfers): whoever holds g_staging_mu owns them for the length of one upload / download.  Small
+// transfers use the engine's own 1 MB pair.
+static std::mutex g_staging_mu;
+static uint8_t *g_staging[2] = {nullptr, nullptr};
+constexpr size_t kStagingBytes = size_t(64) << 20;
+constexpr size_t kSmallStagingBytes = size_t(1) << 20;
+
 static int32_t ingest_staging(wax_vs_engine *e, size_t want_bytes) {
     auto &g = e->ing;
     int32_t rc = ingest_init(e);
     if (rc) return rc;
-    const size_t chunk = std::min<size_t>(size_t(64) << 20, std::max<size_t>(size_t(1) << 20, want_bytes));
-    if (g.pin_bytes >= chunk) return WAX_VS_OK;
+    (void)want_bytes;
+    if (g.pin_bytes >= kSmallStagingBytes) return WAX_VS_OK;
     for (int i = 0; i < 2; ++i) {
-        if (g.pin[i]) { cudaFreeHost(g.pin[i]); g.pin[i] = nullptr; }
-        g.pin_bytes = 0;
-        if (cudaHostAlloc(reinterpret_cast<void **>(&g.pin[i]), chunk, cudaHostAllocDefault) != cudaSuccess)
-            return fail(WAX_VS_ERR_CUDA, "failed to allocate pinned ingest staging (%zu bytes): %s", chunk, cudaGetErrorString(cudaGetLastError()));
+        if (cudaHostAlloc(reinterpret_cast<void **>(&g.pin[i]), kSmallStagingBytes, cudaHostAllocPortable) != cudaSuccess)
+            return fail(WAX_VS_ERR_CUDA, "failed to allocate pinned ingest staging: %s", cudaGetErrorString(cudaGetLastError()));
     }
-    g.pin_bytes = chunk;
+    g.pin_bytes = kSmallStagingBytes;
+    return WAX_VS_OK;
+}
+// caller holds g_staging_mu
+static int32_t shared_staging() {
+    for (int i = 0; i < 2; ++i) {
+        if (!g_staging[i] && cudaHostAlloc(reinterpret_cast<void **>(&g_staging[i]), kStagingBytes, cudaHostAllocPortable) != cudaSuccess)
+            return fail(WAX_VS_ERR_CUDA, "failed to allocate the shared pinned staging (%zu bytes): %s", kStagingBytes, cudaGetErrorString(cudaGetLastError()));
+    }
     return WAX_VS_OK;
 }
 static void ingest_free(wax_vs_engine *e) {
@@ -1240,13 +1273,18 @@ static int32_t upload_bytes(wax_vs_engine *e, void *d_dst, const void *h_src, si
         CUDA_TRY(cudaStreamSynchronize(g.stream));
         return WAX_VS_OK;
     }
+    const bool big = bytes > 2 * kSmallStagingBytes;
+    std::unique_lock<std::mutex> pool(g_staging_mu, std::defer_lock);
+    if (big) { pool.lock(); if ((rc = shared_staging())) return rc; }
+    uint8_t *const *pin = big ? g_staging : g.pin;
+    const size_t pin_bytes = big ? kStagingBytes : g.pin_bytes;
     size_t off = 0;
     for (int i = 0; off < bytes; ++i) {
         const int b = i & 1;
-        const size_t len = std::min(g.pin_bytes, bytes - off);
+        const size_t len = std::min(pin_bytes, bytes - off);
         CUDA_TRY(cudaEventSynchronize(g.ev[b]));                 // the DMA that last read this buffer is done
-        parallel_memcpy(g.pin[b], static_cast<const char *>(h_src) + off, len, g.threads);
-        CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, g.pin[b], len, cudaMemcpyHostToDevice, g.stream));
+        parallel_memcpy(pin[b], static_cast<const char *>(h_src) + off, len, g.threads);
+        CUDA_TRY(cudaMemcpyAsync(static_cast<char *>(d_dst) + off, pin[b], len, cudaMemcpyHostToDevice, g.stream));
         CUDA_TRY(cudaEventRecord(g.ev[b], g.stream));
         off += len;
     }
@@ -1266,10 +1304,15 @@ static int32_t download_bytes(wax_vs_engine *e, void *h_dst, const void *d_src, 
         CUDA_TRY(cudaStreamSynchronize(g.stream));
         return WAX_VS_OK;
     }
-    const size_t n_chunks = (bytes + g.pin_bytes - 1) / g.pin_bytes;
+    const bool big = bytes > 2 * kSmallStagingBytes;
+    std::unique_lock<std::mutex> pool(g_staging_mu, std::defer_lock);
+    if (big) { pool.lock(); if ((rc = shared_staging())) return rc; }
+    uint8_t *const *pin = big ? g_staging : g.pin;
+    const size_t pin_bytes = big ? kStagingBytes : g.pin_bytes;
+    const size_t n_chunks = (bytes + pin_bytes - 1) / pin_bytes;
     auto issue = [&](size_t i) -> cudaError_t {
-        const size_t off = i * g.pin_bytes, len = std::min(g.pin_bytes, bytes - off);
-        cudaError_t err = cudaMemcpyAsync(g.pin[i & 1], static_cast<const char *>(d_src) + off, len, cudaMemcpyDeviceToHost, g.stream);
+        const size_t off = i * pin_bytes, len = std::min(pin_bytes, bytes - off);
+        cudaError_t err = cudaMemcpyAsync(pin[i & 1], static_cast<const char *>(d_src) + off, len, cudaMemcpyDeviceToHost, g.stream);
         if (err == cudaSuccess) err = cudaEventRecord(g.ev[i & 1], g.stream);
         return err;
     };
@@ -1277,8 +1320,8 @@ static int32_t download_bytes(wax_vs_engine *e, void *h_dst, const void *d_src, 
     for (size_t i = 0; i < n_chunks; ++i) {
         if (i + 1 < n_chunks) CUDA_TRY(issue(i + 1));            // its buffer was drained in iteration i-1
         CUDA_TRY(cudaEventSynchronize(g.ev[i & 1]));
-        const size_t off = i * g.pin_bytes, len = std::min(g.pin_bytes, bytes - off);
-        parallel_memcpy(static_cast<char *>(h_dst) + off, g.pin[i & 1], len, g.threads);
+        const size_t off = i * pin_bytes, len = std::min(pin_bytes, bytes - off);
+        parallel_memcpy(static_cast<char *>(h_dst) + off, pin[i & 1], len, g.threads);
     }
     CUDA_TRY(cudaStreamSynchronize(g.stream));
     return WAX_VS_OK;
@@ -1308,6 +1351,7 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
     const uint64_t n0 = e->n_rows;
     bool pure_append = true;
     for (uint64_t i = 0; i < n; ++i) {
+        if (i + 8 < n) e->map.prefetch(frame_ids[i + 8]);      // the table is far bigger than the caches: hide the miss
         uint32_t row = e->map.find(frame_ids[i]);
         if (row == 0xFFFFFFFFu) {
             row = static_cast<uint32_t>(e->n_rows);
@@ -2379,12 +2423,18 @@ int32_t wax_vs_debug_transfer_probe(wax_vs_engine *e, uint64_t bytes, float *out
     if ((rc = ensure_dev(&ig.d_stage, &ig.d_stage_cap, static_cast<size_t>((bytes + 3) / 4), "probe buffer"))) return rc;
     std::vector<uint8_t> host(bytes, 1);
     auto secs = [](auto t0) { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count(); };
-    const size_t chunk = std::min<size_t>(ig.pin_bytes, bytes);
+    uint8_t *probe_pin = nullptr;
+    {
+        std::lock_guard<std::mutex> pool(g_staging_mu);
+        if ((rc = shared_staging())) return rc;
+        probe_pin = g_staging[0];
+    }
+    const size_t chunk = std::min<size_t>(kStagingBytes, bytes);
     auto best = [&](auto fn) { double b = 1e30; for (int i = 0; i < 3; ++i) { auto t0 = std::chrono::steady_clock::now(); fn(); b = std::min(b, secs(t0)); } return b; };
-    out7[0] = static_cast<float>(chunk / 1e9 / best([&] { memcpy(ig.pin[0], host.data(), chunk); }));
-    out7[1] = static_cast<float>(chunk / 1e9 / best([&] { parallel_memcpy(ig.pin[0], host.data(), chunk, ig.threads); }));
-    out7[2] = static_cast<float>(chunk / 1e9 / best([&] { cudaMemcpyAsync(ig.d_stage, ig.pin[0], chunk, cudaMemcpyHostToDevice, ig.stream); cudaStreamSynchronize(ig.stream); }));
-    out7[3] = static_cast<float>(chunk / 1e9 / best([&] { cudaMemcpyAsync(ig.pin[0], ig.d_stage, chunk, cudaMemcpyDeviceToHost, ig.stream); cudaStreamSynchronize(ig.stream); }));
+    out7[0] = static_cast<float>(chunk / 1e9 / best([&] { memcpy(probe_pin, host.data(), chunk); }));
+    out7[1] = static_cast<float>(chunk / 1e9 / best([&] { parallel_memcpy(probe_pin, host.data(), chunk, ig.threads); }));
+    out7[2] = static_cast<float>(chunk / 1e9 / best([&] { cudaMemcpyAsync(ig.d_stage, probe_pin, chunk, cudaMemcpyHostToDevice, ig.stream); cudaStreamSynchronize(ig.stream); }));
+    out7[3] = static_cast<float>(chunk / 1e9 / best([&] { cudaMemcpyAsync(probe_pin, ig.d_stage, chunk, cudaMemcpyDeviceToHost, ig.stream); cudaStreamSynchronize(ig.stream); }));
     out7[4] = static_cast<float>(bytes / 1e9 / best([&] { upload_bytes(e, ig.d_stage, host.data(), bytes); }));
     out7[5] = static_cast<float>(bytes / 1e9 / best([&] { download_bytes(e, host.data(), ig.d_stage, bytes); }));
     out7[6] = static_cast<float>(ig.threads);
