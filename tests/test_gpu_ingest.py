@@ -134,3 +134,47 @@ def test_appends_extend_the_cached_norms_and_shadow_instead_of_rebuilding(oracle
     eng.add_batch(list(range(50_000, 60_000)), rows[50_000:])              # append past the reserved capacity: grows
     check()
     assert eng.count == 59_998 and eng.counter("shadow_rows") == 59_998
+
+
+def test_sorted_id_fast_path_and_the_switch_to_the_hash_table(oracle):
+    """Frame ids normally arrive in increasing order: appends then touch no hash table and lookups are binary searches in
+    the id array (order-preserving removes and in-place upserts keep it sorted).  The first out-of-order id switches the
+    engine to the hash table.  The list model must agree before, across and after the switch."""
+    dims = 24
+    rng = np.random.default_rng(21)
+    eng, model = CUDAVectorEngine(VectorMetric.cosine, dims), EngineModel(oracle, 0, dims)
+
+    def both(fn_name, *args):
+        getattr(eng, fn_name)(*args)
+        if fn_name == "remove_batch":
+            for i in args[0]:
+                model.remove(i)
+        else:
+            getattr(model, fn_name)(*args)
+
+    def check():
+        assert eng.count == len(model.ids)
+        assert np.array_equal(eng.read_rows(0, eng.count), model.corpus())
+        q = rng.standard_normal(dims).astype(np.float32)
+        assert [g[0] for g in eng.search(q, 25)] == [m[0] for m in model.search(q, 25)]
+        allow = [int(x) for x in rng.choice(model.ids, 12, replace=False)]
+        got = eng.search_filtered(q, 5, allow=allow)          # the filtered search resolves ids the same way
+        assert set(g[0] for g in got) <= set(allow) and len(got) == 5
+    vecs = lambda n: rng.standard_normal((n, dims)).astype(np.float32)   # noqa: E731
+    both("add_batch", list(range(1000, 1400)), list(vecs(400)))           # increasing: the fast path
+    both("add_batch", list(range(2000, 2100)), list(vecs(100)))
+    check()
+    both("remove_batch", [1000, 1399, 2050, 1200, 777])
+    both("add_batch", [1100, 2099, 3000, 3001], list(vecs(4)))            # upserts + larger ids: still sorted
+    both("add", 1100, vecs(1)[0])
+    check()
+    both("add_batch", [50, 3002, 1300, 50], list(vecs(4)))                # 50 is out of order: hash table from here on
+    check()
+    both("remove_batch", [50, 3002, 1001])
+    both("add_batch", list(range(10, 40)) + [3001], list(vecs(31)))
+    check()
+    blob = eng.serialize()
+    other = CUDAVectorEngine(VectorMetric.cosine, dims)
+    other.deserialize(blob)                                               # unsorted ids in the blob: detected on load
+    other.add(1300, model.rows[model.ids.index(1300)])
+    assert other.count == eng.count and other.search(model.rows[5], 3) == eng.search(model.rows[5], 3)

@@ -1016,7 +1016,7 @@ struct FinishParams {
 // root (a slice only ever filtered by its own root or by a root another slice had published); nominated rows
 // beyond the first kBatchRescore have score' <= the (kBatchRescore+1)-th nominee.
 template <int METRIC>
-__global__ void __launch_bounds__(256) batch_finish_kernel(const FinishParams p) {
+__global__ void __launch_bounds__(512) batch_finish_kernel(const FinishParams p) {
     extern __shared__ uint64_t fsm[];
     uint64_t *sk = fsm;                 // [pow2_all] nominee keys of every slice
     uint64_t *ek = fsm + p.pow2_all;    // [rescore] exact keys

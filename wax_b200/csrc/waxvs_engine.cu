@@ -200,6 +200,10 @@ struct wax_vs_engine {
     std::vector<uint64_t> ids;
     IdMap map;
     bool map_valid = true;
+    // Frame ids are handed out in increasing order by the store, so the id array is normally SORTED: then a lookup is a
+    // binary search in it and bulk appends touch no hash table at all; the table is built only once an out-of-order id
+    // arrives (and kept from then on).  Order-preserving removes and in-place upserts keep the array sorted.
+    bool ids_sorted = true;
     uint64_t *d_ids = nullptr; size_t d_ids_cap = 0; bool d_ids_dirty = true;
     std::mutex ids_mu;
 
@@ -967,8 +971,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         fp.tau_star = d_tau_star ? d_tau_star + q0 : nullptr;
         fp.tau_stride = n_queries;
         const size_t fsmem = static_cast<size_t>(pow2 + rescore) * sizeof(uint64_t);
-        if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 256, fsmem, stream>>>(fp);
-        else batch_finish_kernel<kDot><<<nq, 256, fsmem, stream>>>(fp);
+        if (e->similarity == WAX_VS_COSINE) batch_finish_kernel<kCosine><<<nq, 512, fsmem, stream>>>(fp);
+        else batch_finish_kernel<kDot><<<nq, 512, fsmem, stream>>>(fp);
         CUDA_TRY(cudaGetLastError());
         *launches += 2;
     }
@@ -1032,6 +1036,7 @@ static void materialize_ids(wax_vs_engine *e) {
     for (uint64_t r = 0; r < e->n_rows; ++r) e->ids[r] = e->id_base + r;
     e->ids_identity = false;
     e->map_valid = false;
+    e->ids_sorted = true;            // id_base + row
     e->d_ids_dirty = true;
 }
 static void ensure_map(wax_vs_engine *e) {
@@ -1039,6 +1044,15 @@ static void ensure_map(wax_vs_engine *e) {
     e->map.reset(e->ids.size());
     for (size_t r = 0; r < e->ids.size(); ++r) e->map.put(e->ids[r], static_cast<uint32_t>(r));
     e->map_valid = true;
+}
+// frameId -> row (0xFFFFFFFF = absent) for explicit ids: binary search while the id array is sorted, else the hash table.
+static uint32_t find_row(wax_vs_engine *e, uint64_t id) {
+    if (e->ids_sorted) {
+        const auto it = std::lower_bound(e->ids.begin(), e->ids.end(), id);
+        return (it != e->ids.end() && *it == id) ? static_cast<uint32_t>(it - e->ids.begin()) : 0xFFFFFFFFu;
+    }
+    ensure_map(e);
+    return e->map.find(id);
 }
 static int32_t sync_device_ids(wax_vs_engine *e, const uint64_t **out) {
     std::lock_guard<std::mutex> g(e->ids_mu);
@@ -1154,7 +1168,7 @@ int32_t wax_vs_reserve(wax_vs_engine *e, uint64_t rows) {
     int32_t rc = set_capacity(e, rows);
     if (rc == WAX_VS_OK && !e->ids_identity && rows > e->ids.capacity()) {
         e->ids.reserve(rows);                       // no id-array / hash-table regrowth during the appends that follow
-        if (e->map_valid && e->map.keys.size() < rows * 2 + 16) {
+        if (!e->ids_sorted && e->map_valid && e->map.keys.size() < rows * 2 + 16) {
             IdMap bigger;
             bigger.reset(rows);
             for (size_t r = 0; r < e->ids.size(); ++r) bigger.put(e->ids[r], static_cast<uint32_t>(r));
@@ -1343,24 +1357,39 @@ int32_t wax_vs_add_batch(wax_vs_engine *e, const uint64_t *frame_ids, const floa
     if (rc) return rc;
     tr.mark("grow");
     materialize_ids(e);
-    ensure_map(e);
-    tr.mark("ids+map");
+    tr.mark("ids");
 
     // Resolve the destination row of every batch item in order (the sequential loop at :384-398).
     std::vector<uint32_t> target(n);
     const uint64_t n0 = e->n_rows;
     bool pure_append = true;
-    for (uint64_t i = 0; i < n; ++i) {
-        if (i + 8 < n) e->map.prefetch(frame_ids[i + 8]);      // the table is far bigger than the caches: hide the miss
-        uint32_t row = e->map.find(frame_ids[i]);
-        if (row == 0xFFFFFFFFu) {
-            row = static_cast<uint32_t>(e->n_rows);
-            e->ids.push_back(frame_ids[i]);
-            e->map.put(frame_ids[i], row);
-            ++e->n_rows;
+    bool increasing = e->ids_sorted && (e->ids.empty() || frame_ids[0] > e->ids.back());
+    for (uint64_t i = 1; i < n && increasing; ++i) increasing = frame_ids[i] > frame_ids[i - 1];
+    if (increasing) {
+        // the common bulk-ingest case: every id is new and larger than all stored ones -- no lookups, no hash table
+        e->ids.insert(e->ids.end(), frame_ids, frame_ids + n);
+        for (uint64_t i = 0; i < n; ++i) target[i] = static_cast<uint32_t>(n0 + i);
+        e->n_rows += n;
+        e->map_valid = false;
+    } else {
+        for (uint64_t i = 0; i < n; ++i) {
+            if (!e->ids_sorted && i + 8 < n) e->map.prefetch(frame_ids[i + 8]);   // the table is far bigger than the caches
+            uint32_t row = find_row(e, frame_ids[i]);
+            if (row == 0xFFFFFFFFu) {
+                row = static_cast<uint32_t>(e->n_rows);
+                if (e->ids_sorted && !e->ids.empty() && frame_ids[i] < e->ids.back()) {
+                    e->ids_sorted = false;                   // first out-of-order id: from now on the hash table answers
+                    e->map_valid = false;
+                    ensure_map(e);
+                }
+                e->ids.push_back(frame_ids[i]);
+                if (!e->ids_sorted) e->map.put(frame_ids[i], row);
+                else e->map_valid = false;
+                ++e->n_rows;
+            }
+            target[i] = row;
+            if (row != n0 + i) pure_append = false;
         }
-        target[i] = row;
-        if (row != n0 + i) pure_append = false;
     }
     e->d_ids_dirty = true;
     const size_t row_bytes = static_cast<size_t>(e->dims) * sizeof(float);
@@ -1420,9 +1449,8 @@ int32_t wax_vs_remove_batch(wax_vs_engine *e, const uint64_t *frame_ids, uint64_
         for (uint64_t i = 0; i < n; ++i)
             if (frame_ids[i] >= e->id_base && frame_ids[i] - e->id_base < e->n_rows) gone.push_back(static_cast<uint32_t>(frame_ids[i] - e->id_base));
     } else {
-        ensure_map(e);
         for (uint64_t i = 0; i < n; ++i) {
-            const uint32_t r = e->map.find(frame_ids[i]);
+            const uint32_t r = find_row(e, frame_ids[i]);
             if (r != 0xFFFFFFFFu) gone.push_back(r);                // :426 unknown id = no-op
         }
     }
@@ -2116,14 +2144,14 @@ int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t qu
     std::vector<uint32_t> listed;
     {
         std::lock_guard<std::mutex> g(e->ids_mu);   // the lazily built id map is shared by concurrent readers
-        if (!e->ids_identity) ensure_map(e);
+        // (find_row builds the lazily constructed hash table when it is needed: serialised by ids_mu)
         for (uint64_t i = 0; i < n_ids; ++i) {
             uint64_t row;
             if (e->ids_identity) {
                 if (frame_ids[i] < e->id_base || frame_ids[i] - e->id_base >= n_rows) continue;
                 row = frame_ids[i] - e->id_base;
             } else {
-                const uint32_t f = e->map.find(frame_ids[i]);
+                const uint32_t f = find_row(e, frame_ids[i]);
                 if (f == 0xFFFFFFFFu) continue;
                 row = f;
             }
@@ -2282,6 +2310,8 @@ int32_t wax_vs_deserialize(wax_vs_engine *e, const uint8_t *src, uint64_t len) {
     if (count) memcpy(e->ids.data(), src + 36 + vbytes + 8, ibytes);  // :809-811
     e->ids_identity = false;
     e->map_valid = false;
+    e->ids_sorted = true;
+    for (uint64_t i = 1; i < count && e->ids_sorted; ++i) e->ids_sorted = e->ids[i] > e->ids[i - 1];
     e->d_ids_dirty = true;
     invalidate_row_caches(e, 0);
     return WAX_VS_OK;
@@ -2315,7 +2345,7 @@ int32_t wax_vs_debug_fill_synthetic(wax_vs_engine *e, uint64_t seed, uint64_t fi
     e->n_rows = rows;
     e->ids.clear(); e->ids.shrink_to_fit();
     e->ids_identity = true; e->id_base = id_base;
-    e->map = IdMap(); e->map_valid = true;
+    e->map = IdMap(); e->map_valid = true; e->ids_sorted = true;
     e->d_ids_dirty = true;
     invalidate_row_caches(e, 0);
     return WAX_VS_OK;
