@@ -24,6 +24,13 @@ t0 = time.perf_counter()
 for start in range(0, total, chunk):
     eng.add_batch(np.arange(start, start + chunk, dtype=np.uint64), block)
 t_append = time.perf_counter() - t0
+e0 = CUDAVectorEngine(VectorMetric.cosine, dims)
+e0.reserve(total)                                                        # the same 20 calls into reserved capacity
+t0 = time.perf_counter()
+for start in range(0, total, chunk):
+    e0.add_batch(np.arange(start, start + chunk, dtype=np.uint64), block)
+t_append_reserved = time.perf_counter() - t0
+e0.close()
 e1 = CUDAVectorEngine(VectorMetric.cosine, dims)
 e1.reserve(total)
 e1.add_batch(np.arange(10, dtype=np.uint64), block[:10]); e1.remove_batch(np.arange(10, dtype=np.uint64))
@@ -70,6 +77,7 @@ assert L.lib().wax_vs_debug_transfer_probe(eng.handle, 1 << 30, probe) == 0
 print(json.dumps({
     "rows": total, "dims": dims, "host_threads_for_staging": "min(8, cgroup cores)",
     "append_20x100k_rows_per_s": round(total / t_append), "append_20x100k_gb_per_s": round(gb / t_append, 2),
+    "append_20x100k_reserved_gb_per_s": round(gb / t_append_reserved, 2),
     "append_one_call_gb_per_s": round(gb / t_one, 2),
     "upsert_100k_s": round(t_upsert, 4), "remove_one_s": round(t_remove, 4),
     "remove_batch_1000_s": round(t_remove_batch, 4), "remove_batch_removed": int(n_gone),

@@ -397,7 +397,7 @@ static int32_t ensure_pinned(T **p, size_t *cap, size_t need, const char *what) 
 // kernel dispatch
 struct TmaConfig { int C, R, warps, stages; size_t smem; };
 
-static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
+static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg, int mode = 0) {
     const uint32_t d = e->dims;
     if (d % 4u != 0) return false;                      // rows must be 16-byte multiples for the bulk copy
     const size_t budget = (e->smem_optin ? e->smem_optin : 232448) - 4096;   // minus the kernels' static shared memory
@@ -418,6 +418,10 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg) {
         R = e->tune.rows_per_step == 4 || e->tune.rows_per_step == 8 ? e->tune.rows_per_step : (C <= 2 ? 8 : 4);
         if (C == 1) warps_default = 16;
         else if (C == 2) warps_default = 12;
+        // wide lists (33 <= k <= 128, four keys per lane): 16 warps per CTA spread the list upkeep and beat 8 warps up to
+        // a few GB of corpus (profiles/shape_sweep_r02.jsonl, k = 72: 72 vs 87 us at 174 K rows, 296 vs 315 us at
+        // 1.25 M, 555 vs 577 at 2.5 M; at 10 M rows the 8-warp shape's 48 KB in flight wins again)
+        else if (mode == 1 && static_cast<uint64_t>(e->n_rows) * d * 4 < (8ull << 30)) warps_default = 16;
     }
     // Default ring depth 2: measured best on B200 (profiles/sweep_r01_call2.json: ~48 KB in flight per SM beats
     // deeper rings by 5-10 %).
@@ -586,7 +590,7 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     }
 
     TmaConfig cfg{};
-    bool use_tma = (e->tune.variant != 2) && pick_tma_config(e, &cfg);
+    bool use_tma = (e->tune.variant != 2) && pick_tma_config(e, &cfg, mode);
     if (e->tune.variant == 1 && !use_tma)
         return fail(WAX_VS_ERR_UNSUPPORTED, "TMA-staged kernel does not support dims=%u", e->dims);
     if (host && host->h_query) {
