@@ -248,6 +248,11 @@ int32_t wax_vs_debug_time_shard_search(wax_vs_engine *engine, uint32_t n_queries
    download pipeline HBM->pageable, worker threads}.  Explains what bounds wax_vs_add_batch / wax_vs_serialize. */
 int32_t wax_vs_debug_transfer_probe(wax_vs_engine *engine, uint64_t bytes, float *out7);
 
+/* Where one fused search spends its time, from %globaltimer stamps inside the kernel (averages over `iters` searches,
+   microseconds): out5 = {kernel start -> last warp leaves the scan loop, -> last CTA has selected its k, -> the last CTA
+   starts the grid stage, -> result written, CUDA-event duration of the launch on its stream}. */
+int32_t wax_vs_debug_phase_trace(wax_vs_engine *engine, int64_t top_k, uint32_t iters, float *out5);
+
 /* Batched-path instrumentation: how many queries were answered by the tensor-core nomination path with a
    completed exactness proof, and how many had to be re-run on the exact single-query path. */
 int32_t wax_vs_debug_batch_stats(wax_vs_engine *engine, uint64_t *tensor_queries, uint64_t *fallback_queries);

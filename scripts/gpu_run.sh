@@ -40,6 +40,7 @@ for step in "$@"; do
     c5-launches) timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file $OUT/ncu_launches_c5_$TAG.csv \
                 python scripts/bench_batch.py 3 bf16 only=1 > $OUT/ncu_launches_c5_$TAG.log 2>&1; grep -E "batch_|shadow" $OUT/ncu_launches_c5_$TAG.csv | tail -8 | cut -c1-260 ;;
     c5-proof) timeout 600 python scripts/c5_proof_probe.py 2>&1 | tee $OUT/c5_proof_$TAG.jsonl | cut -c1-400 ;;
+    phases) timeout 300 python scripts/phase_trace.py 2>&1 | tee $OUT/phase_trace_$TAG.jsonl ;;
     small-n) timeout 900 python scripts/small_n_sweep.py 2>&1 | tee $OUT/small_n_$TAG.jsonl | cut -c1-260 ;;
     batch-sweep) for o in "only=1 batch_pair=1" "only=1 batch_pair=1 batch_heap=16" "only=1 batch_heap=16" "only=0 batch_pair=1" "only=0 batch_ares=0" "only=0 batch_pair=1 batch_ares=0"; do
              timeout 400 python scripts/bench_batch.py 10 bf16 $o 2>&1 | tail -1 | tee -a $OUT/batch_sweep_$TAG.jsonl | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['options'], d['ms_per_batch'], d['roofline']['frac'], d['exact_fallback_queries'])"; done ;;

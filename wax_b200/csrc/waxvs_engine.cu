@@ -248,6 +248,7 @@ struct wax_vs_engine {
     // caller's stream.  Mutators must not touch the corpus under them: every mutator drains the device first when
     // this flag says something was enqueued since the last drain.
     std::atomic<bool> async_pending{false};
+    unsigned long long *debug_trace = nullptr;   // wax_vs_debug_phase_trace: device buffer the scan kernels stamp (else nullptr)
 
     // Row-sharded search (wax_vs_shard_*): this engine is rank `rank` of `world`; box[r] = rank r's mailbox.
     struct Shard {
@@ -578,6 +579,7 @@ static int32_t enqueue_search(wax_vs_engine *e, SearchCtx *c, const float *d_que
     p.chunk_steps = e->tune.chunk_steps > 0 ? static_cast<uint32_t>(e->tune.chunk_steps) : 0u;   // auto: set below
     p.work_counter = c->d_ticket + 1;
     p.mask = d_mask;
+    p.trace = e->debug_trace;
 
     const bool emit = k_eff > static_cast<uint32_t>(e->tune.fused_k_max);
     const int mode = emit ? 2 : (k_eff <= 32 ? 0 : 1);
@@ -2472,6 +2474,51 @@ int32_t wax_vs_debug_transfer_probe(wax_vs_engine *e, uint64_t bytes, float *out
     out7[4] = static_cast<float>(bytes / 1e9 / best([&] { upload_bytes(e, ig.d_stage, host.data(), bytes); }));
     out7[5] = static_cast<float>(bytes / 1e9 / best([&] { download_bytes(e, host.data(), ig.d_stage, bytes); }));
     out7[6] = static_cast<float>(ig.threads);
+    CUDA_TRY(cudaGetLastError());
+    return WAX_VS_OK;
+}
+
+// Where a single fused search spends its time (TMA-staged kernels with the selection tail): averages over `iters`
+// searches, microseconds: [0] kernel start -> last warp leaves the scan loop, [1] -> last CTA has selected its k,
+// [2] -> the last CTA starts the grid stage, [3] -> result written (kernel end), [4] event-timed duration of the
+// launch on the stream (launch overhead = [4] - [3]).
+int32_t wax_vs_debug_phase_trace(wax_vs_engine *e, int64_t top_k, uint32_t iters, float *out5) {
+    if (!e || !out5) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    std::unique_lock<std::shared_mutex> w(e->rw);
+    DeviceGuard g(e->device);
+    SearchCtx *c = nullptr;
+    int32_t rc = ctx_acquire(e, &c);
+    if (rc) return rc;
+    struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); e->debug_trace = nullptr; } } rel{e, c};
+    const uint32_t k_eff = clamp_topk(top_k);
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(e->dims), "query buffer"))) return rc;
+    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, static_cast<size_t>(k_eff), "result buffer"))) return rc;
+    synth_fill_kernel<<<1, 256, 0, c->stream>>>(c->d_queries, 1, e->dims, 99, 0, 1);
+    unsigned long long *d_trace = nullptr;
+    CUDA_TRY(cudaMalloc(&d_trace, 8 * sizeof(unsigned long long)));
+    double acc[5] = {0, 0, 0, 0, 0};
+    uint64_t launches = 0;
+    for (uint32_t it = 0; it < iters + 3; ++it) {
+        const unsigned long long init[8] = {~0ull, 0, 0, 0, 0, 0, 0, 0};
+        cudaMemcpyAsync(d_trace, init, sizeof init, cudaMemcpyHostToDevice, c->stream);
+        cudaStreamSynchronize(c->stream);
+        e->debug_trace = d_trace;
+        cudaEventRecord(c->ev0, c->stream);
+        rc = enqueue_search(e, c, c->d_queries, k_eff, 0, c->d_out, nullptr, c->stream, &launches);
+        cudaEventRecord(c->ev1, c->stream);
+        e->debug_trace = nullptr;
+        if (rc) { cudaStreamSynchronize(c->stream); cudaFree(d_trace); return rc; }
+        unsigned long long t[8];
+        cudaMemcpyAsync(t, d_trace, sizeof t, cudaMemcpyDeviceToHost, c->stream);
+        cudaStreamSynchronize(c->stream);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+        if (it < 3) continue;
+        for (int i = 0; i < 4; ++i) acc[i] += (t[i + 1] > t[0] && t[0] != ~0ull) ? (t[i + 1] - t[0]) * 1e-3 : 0.0;
+        acc[4] += ms * 1e3;
+    }
+    cudaFree(d_trace);
+    for (int i = 0; i < 5; ++i) out5[i] = static_cast<float>(acc[i] / std::max(iters, 1u));
     CUDA_TRY(cudaGetLastError());
     return WAX_VS_OK;
 }

@@ -61,6 +61,9 @@ struct ScanParams {
     // last CTA selects over grid x k keys staged in `tail_smem_bytes` of the (by then idle) ring.  Same result bits.
     uint32_t tail_select;
     uint32_t tail_smem_bytes;
+    unsigned long long *trace;  // instrumentation (wax_vs_debug_phase_trace) or nullptr: [0] min kernel start, [1] max end of a
+                                // warp's scan loop, [2] max end of a CTA's selection, [3] start and [4] end of the last CTA's
+                                // grid stage -- %globaltimer nanoseconds
     ShardParams shard;          // shard.world > 0: `out` is this rank's local list and the last CTA goes on to exchange it
                                 // with the other ranks over NVLink and to merge (waxvs_shard.cuh): still the same launch
 };
@@ -248,10 +251,12 @@ __device__ __forceinline__ void finish_topk_select(const ScanParams &p, WarpTopK
     for (uint32_t i = ss.n_sel + tid; i < k; i += nthr) mine[i] = WAXVS_KEY_NONE;
     __threadfence();
     __syncthreads();
+    if (p.trace && tid == 0) atomicMax(p.trace + 2, global_timer_ns());
     if (tid == 0) s_last2 = (atomicAdd(p.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
     __syncthreads();
     if (!s_last2) return;
     __threadfence();
+    if (p.trace && tid == 0) p.trace[3] = global_timer_ns();
     // ---- stage B (last CTA): the k smallest of the grid's gridDim.x * k keys, ranked, written out
     const uint32_t total = gridDim.x * k;
     const bool staged = static_cast<size_t>(total) * sizeof(uint64_t) <= p.tail_smem_bytes;
@@ -286,6 +291,7 @@ __device__ __forceinline__ void finish_topk_select(const ScanParams &p, WarpTopK
         *p.ticket = 0u;
         if (p.work_counter) *p.work_counter = 0u;
         if (p.host_flag && !p.shard.world) st_release_sys_u64(p.host_flag, p.host_seq);
+        if (p.trace) p.trace[4] = global_timer_ns();
     }
     if (p.shard.world) shard_exchange_cta(p.shard, p.out, p.k, reinterpret_cast<uint32_t *>(scratch));
 }
@@ -344,6 +350,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
         sqrt_a2 = __fsqrt_rn(a2);
     }
 
+    if (p.trace && threadIdx.x == 0) atomicMin(p.trace + 0, global_timer_ns());
     const uint32_t total_warps = gridDim.x * warps;
     const uint32_t gwarp = blockIdx.x * warps + warp;
     const uint32_t n_steps = (p.n_rows + R - 1) / R;
@@ -481,6 +488,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
         }
     }
 
+    if (p.trace && lane == 0) atomicMax(p.trace + 1, global_timer_ns());
     if (!EMIT) {
         if (E > 1) tk.flush(lane, k);
         if (p.tail_select) finish_topk_select<E>(p, tk, smem);
