@@ -16,6 +16,8 @@
 #   ncu-batch  ncu --set full of the batched nominate + finish kernels (configs[2] and [4] shapes)
 #   sharded:N  torchrun -N tests/check_sharded_torchrun.py + bench.py --gpus N      (needs gpurun --gpus N)
 #   c4         torchrun -8 tests/check_sharded_torchrun.py 100000000 light          (needs gpurun --gpus 8)
+#   ncu-batch-c5 / ncu-batch-c3  ncu --set full of the nominate + finish kernels of configs[4] / configs[2] (NCU_OPTS="batch_pair=1" ...)
+#   power      clocks + power draw sampled while the batched configs run (is the tensor path power-capped?)
 #   sass       cuobjdump opcode histogram of libwaxvs_cuda.so -> profiles-style text
 set -u
 TAG=${1:?tag}; shift
@@ -53,6 +55,17 @@ for step in "$@"; do
     ncu-batch) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'batch_nominate|batch_finish' -s 6 -c 2 -o $OUT/ncu_batch_$TAG -f \
                 python scripts/bench_batch.py 2 > $OUT/ncu_batch_$TAG.log 2>&1
               ncu -i $OUT/ncu_batch_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_batch_${TAG}_summary.csv; cut -c1-400 $OUT/ncu_batch_${TAG}_summary.csv ;;
+    ncu-batch-c5) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'batch_nominate|batch_finish' -s 4 -c 2 -o $OUT/ncu_batch_c5_$TAG -f \
+                python scripts/bench_batch.py 2 bf16 only=1 > $OUT/ncu_batch_c5_$TAG.log 2>&1
+              ncu -i $OUT/ncu_batch_c5_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_batch_c5_${TAG}_summary.csv; cut -c1-400 $OUT/ncu_batch_c5_${TAG}_summary.csv ;;
+    ncu-batch-c3) timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'batch_nominate|batch_finish' -s 4 -c 2 -o $OUT/ncu_batch_c3_$TAG -f \
+                python scripts/bench_batch.py 2 bf16 only=0 ${NCU_OPTS:-} > $OUT/ncu_batch_c3_$TAG.log 2>&1
+              ncu -i $OUT/ncu_batch_c3_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_batch_c3_${TAG}_summary.csv; cut -c1-400 $OUT/ncu_batch_c3_${TAG}_summary.csv ;;
+    power) # SM clock / power draw / throttle reasons sampled every 50 ms WHILE the batched configs run 60 steps each
+           nvidia-smi --query-gpu=timestamp,clocks.sm,power.draw,power.limit,clocks_throttle_reasons.active,temperature.gpu --format=csv,noheader -lms 50 > $OUT/power_$TAG.csv 2>&1 &
+           SMI=$!
+           timeout 600 python scripts/bench_batch.py 60 bf16 2>&1 | tee $OUT/bench_batch_power_$TAG.jsonl | cut -c1-260
+           kill $SMI; sort -t, -k3 -n $OUT/power_$TAG.csv | tail -3 ;;
     sharded:*) N=${step#sharded:}
            timeout 900 $TR --nproc-per-node $N tests/check_sharded_torchrun.py > $OUT/sharded_parity_${TAG}_n$N.txt 2>&1; tail -12 $OUT/sharded_parity_${TAG}_n$N.txt
            timeout 900 $TR --nproc-per-node $N bench.py --gpus $N 2> $OUT/bench_${TAG}_n$N.err | tail -1 > $OUT/bench_${TAG}_n$N.json; cut -c1-700 $OUT/bench_${TAG}_n$N.json; tail -3 $OUT/bench_${TAG}_n$N.err ;;

@@ -161,6 +161,26 @@ def test_bf16_shadow_nominations_equal_single_query_path(oracle, metric, dims, n
         assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"
 
 
+@pytest.mark.parametrize("dims,n,b,k", [(768, 60_001, 256, 100), (384, 100_003, 130, 128), (64, 9_999, 8, 1)])
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+def test_bf16_mid_heap_shape_equals_single_query_path(oracle, metric, dims, n, b, k):
+    """<4 stages, 24-entry heaps> (bf16, streamed queries): the shape picked when k exceeds the slice count (configs[4]:
+    top-100 over 74 slices).  Forced here; same answers as the single-query path, ids and score bits."""
+    eng = _engine(oracle, metric, n, dims, seed=770 + dims, normalize=(metric is VectorMetric.cosine))
+    eng.set_option("batch_bf16", 1)
+    eng.set_option("batch_ares", 0)
+    eng.set_option("batch_heap", 24)
+    qs = oracle.synth_rows(771 + b, 0, b, dims, normalize=True)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, k)
+    t1, f1 = eng.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == b
+    assert eng.counter("batch_bf16_queries") == b
+    assert got == _single(eng, qs, k)
+    if n >= 1000:
+        assert f1 - f0 <= max(1, b // 50), f"{f1 - f0} of {b} queries fell back to the exact path"
+
+
 def _planted(oracle, dims, n, n_planted, top, step, seed, stride):
     """Random unit corpus; row i*stride (i < n_planted) has cosine top - i*step to a unit query q.  The planted rows
     are spread out so that no row slice's 16-entry nominee heap fills up with them."""

@@ -39,7 +39,10 @@ constexpr int kBatchKBlockBf16 = 64;    // bf16 elements per k-block (the same 1
 //   <4, 16>: four TMA stages (192 KB) + 16-entry nominee heaps (16 KB)  -- the pipeline is latency-bound on TMA
 //            (profiles/ncu_batch_tf32_r01b_summary.csv: 3 stages keep the tensor pipe 54 % busy), so the 4th stage
 //            matters; used whenever 16 nominees per slice are plenty (16 * slices >= 8 * k);
-//   <3, 64>: three stages + 64-entry heaps, for few slices or large k.
+//   <3, 64>: three stages + 64-entry heaps, for few slices or large k;
+//   <4, 24> (bf16 only: no scale area): four stages + 24-entry heaps, when k exceeds the slice count -- configs[4]'s
+//            top-100 over 74 slices left 1 query in 1 000 unproven with 16 nominees per slice (a slice that holds 16 rows
+//            within the bf16 bound of the 100th score), and every unproven query costs the batch a second pass.
 // PAIR = true is the cta_group::2 form: two CTAs of a cluster (two query groups, the same row slice) issue ONE
 // 256 x 256 x 8 MMA; each CTA stages only its own 128 query rows and HALF of the corpus tile (16 + 16 KB per
 // k-block instead of 16 + 32), so six stages fit where four did and the L2->SM traffic per SM drops by a third.
@@ -360,14 +363,17 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
     const uint32_t ares_bytes = ARES ? num_kb * kBatchABytes : 0u;   // resident queries: [kb][128 rows x 128 B]
     uint8_t *a_res = smem;
     uint8_t *stages = smem + ares_bytes;                               // [stage][A 16 KB | B 32 KB], 1024-aligned
+    // bf16 nominations never scale in the epilogue (the cosine shadow rows are pre-normalised): no scale area, which is
+    // what lets the <4 stages, 24-entry heaps> shape fit
+    constexpr uint32_t SCALE_BYTES = BF16 ? 0u : 2u * kBatchN * 4u;
     float *scale_smem = reinterpret_cast<float *>(stages + STAGES * STAGE_BYTES);   // [2][256]
-    uint64_t *full = reinterpret_cast<uint64_t *>(scale_smem + 2 * kBatchN);                 // [stages]
+    uint64_t *full = reinterpret_cast<uint64_t *>(stages + STAGES * STAGE_BYTES + SCALE_BYTES);   // [stages]
     uint64_t *empty = full + STAGES;                                                   // [stages]
     uint64_t *tmem_full = empty + STAGES;                                              // [2]
     uint64_t *tmem_empty = tmem_full + 2;                                                    // [2]
     uint64_t *a_full = tmem_empty + 2;                                                       // [1] (ARES)
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(a_full + 1);
-    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(stages + STAGES * STAGE_BYTES + 2048 + 256);  // [slots][128]
+    uint64_t *stage_smem = reinterpret_cast<uint64_t *>(stages + STAGES * STAGE_BYTES + SCALE_BYTES + 256);  // [slots][128]
     uint64_t *heap_smem = stage_smem + kBatchStageSlots * kBatchM;                                            // [64][128]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -530,7 +536,7 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
             const uint32_t acc = t & 1u, acc_phase = (t >> 1) & 1u;
             const uint32_t row0 = tile * kBatchN;
             float *sc = scale_smem + acc * kBatchN;
-            if (p.row_scale) {
+            if (!BF16 && p.row_scale) {
 #pragma unroll
                 for (uint32_t h = 0; h < 2; ++h) {
                     const uint32_t r = row0 + tid + h * 128u;
@@ -554,7 +560,7 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                 // fully unrolled max tree with the flush inlined at every leaf -- 200 KB of SASS, so every entry
                 // missed the instruction cache, which cost a quarter of the kernel once bf16 halved the MMA time.
                 float sv[32];
-                if (p.row_scale) {
+                if (!BF16 && p.row_scale) {
                     const float4 *sc4 = reinterpret_cast<const float4 *>(sc + chunk * 32u);
 #pragma unroll
                     for (uint32_t j4 = 0; j4 < 8; ++j4) {
@@ -943,6 +949,50 @@ __device__ __forceinline__ float exact_row_distance(const float *q, const float 
     return METRIC == kDot ? finish_dot(s0) : finish_l2(s0);
 }
 
+// Four rows per warp pass: the re-score kernels are latency-bound (a warp that scores one row at a time has a single
+// row's loads in flight), so four independent rows are interleaved.  Per row the operations and their order are exactly
+// those of exact_row_distance -- same bits.
+template <int METRIC>
+__device__ __forceinline__ void exact_row_distance_x4(const float *q, const float *const (&v)[4], uint32_t dims, float a2,
+                                                      float sqrt_a2, int lane, float (&d)[4]) {
+    if ((dims % 4u) != 0u) {
+#pragma unroll
+        for (int r = 0; r < 4; ++r) d[r] = exact_row_distance<METRIC>(q, v[r], dims, a2, sqrt_a2, lane);
+        return;
+    }
+    float a[4][4], b[4][4];
+#pragma unroll
+    for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { a[r][j] = 0.f; b[r][j] = 0.f; }
+    auto acc = [&](float qx, float vx, float &aa, float &bb) {
+        if (METRIC == kL2) { const float dd = __fsub_rn(qx, vx); aa = __fmaf_rn(dd, dd, aa); }
+        else { aa = __fmaf_rn(qx, vx, aa); if (METRIC == kCosine) bb = __fmaf_rn(vx, vx, bb); }
+    };
+    const float4 *q4 = reinterpret_cast<const float4 *>(q);
+    for (uint32_t c = lane; c < dims / 4u; c += 32u) {
+        float4 x[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) x[r] = __ldg(reinterpret_cast<const float4 *>(v[r]) + c);
+        const float4 y = __ldg(q4 + c);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            acc(y.x, x[r].x, a[r][0], b[r][0]); acc(y.y, x[r].y, a[r][1], b[r][1]);
+            acc(y.z, x[r].z, a[r][2], b[r][2]); acc(y.w, x[r].w, a[r][3], b[r][3]);
+        }
+    }
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+        const float s0 = warp_butterfly_sum(__fadd_rn(__fadd_rn(a[r][0], a[r][1]), __fadd_rn(a[r][2], a[r][3])));
+        if (METRIC == kCosine) {
+            const float s1 = warp_butterfly_sum(__fadd_rn(__fadd_rn(b[r][0], b[r][1]), __fadd_rn(b[r][2], b[r][3])));
+            d[r] = finish_cos(s0, a2, sqrt_a2, s1);
+        } else {
+            d[r] = METRIC == kDot ? finish_dot(s0) : finish_l2(s0);
+        }
+    }
+}
+
 __device__ __forceinline__ void block_bitonic_sort(uint64_t *sk, uint32_t pow2) {
     for (uint32_t size = 2; size <= pow2; size <<= 1) {
         for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
@@ -976,10 +1026,24 @@ __global__ void __launch_bounds__(256) gather_score_kernel(const float *corpus, 
         sqrt_a2 = __fsqrt_rn(a2);
     }
     const uint32_t warps = (gridDim.x * blockDim.x) >> 5;
-    for (uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
-        const uint32_t row = rows[i];
-        const float d = exact_row_distance<METRIC>(query, corpus + static_cast<size_t>(row) * dims, dims, a2, sqrt_a2, lane);
-        if (lane == 0) keys[i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
+    for (uint32_t i0 = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i0 < n; i0 += 4u * warps) {
+        uint32_t rr[4];
+        const float *vp[4];
+        float d[4];
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) {
+            const uint32_t i = i0 + r * warps;
+            rr[r] = rows[i < n ? i : i0];
+            vp[r] = corpus + static_cast<size_t>(rr[r]) * dims;
+        }
+        exact_row_distance_x4<METRIC>(query, vp, dims, a2, sqrt_a2, lane, d);
+        if (lane == 0) {
+#pragma unroll
+            for (uint32_t r = 0; r < 4; ++r) {
+                const uint32_t i = i0 + r * warps;
+                if (i < n) keys[i] = finite_f32(d[r]) ? make_key(d[r], rr[r]) : WAXVS_KEY_NONE;
+            }
+        }
     }
 }
 
@@ -1016,7 +1080,7 @@ struct FinishParams {
 // root (a slice only ever filtered by its own root or by a root another slice had published); nominated rows
 // beyond the first kBatchRescore have score' <= the (kBatchRescore+1)-th nominee.
 template <int METRIC>
-__global__ void __launch_bounds__(512) batch_finish_kernel(const FinishParams p) {
+__global__ void __launch_bounds__(512, 2) batch_finish_kernel(const FinishParams p) {
     extern __shared__ uint64_t fsm[];
     uint64_t *sk = fsm;                 // [pow2_all] nominee keys of every slice
     uint64_t *ek = fsm + p.pow2_all;    // [rescore] exact keys
@@ -1066,11 +1130,25 @@ __global__ void __launch_bounds__(512) batch_finish_kernel(const FinishParams p)
 
     for (uint32_t i = threadIdx.x; i < p.rescore; i += blockDim.x) ek[i] = WAXVS_KEY_NONE;
     __syncthreads();
-    for (uint32_t i = warp; i < kpp; i += (blockDim.x >> 5)) {
-        const uint32_t row = static_cast<uint32_t>(sk[i]);
-        const float d = exact_row_distance<METRIC>(qv, p.corpus + static_cast<size_t>(row) * p.dims, p.dims, s_a2,
-                                                   s_sqrt_a2, lane);
-        if (lane == 0) ek[i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
+    const uint32_t nwarps = blockDim.x >> 5;
+    for (uint32_t i0 = warp; i0 < kpp; i0 += 4u * nwarps) {      // four nominees per warp pass (warp-uniform bounds)
+        uint32_t rows[4];
+        const float *vp[4];
+        float d[4];
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) {
+            const uint32_t i = i0 + r * nwarps;
+            rows[r] = static_cast<uint32_t>(sk[i < kpp ? i : i0]);
+            vp[r] = p.corpus + static_cast<size_t>(rows[r]) * p.dims;
+        }
+        exact_row_distance_x4<METRIC>(qv, vp, p.dims, s_a2, s_sqrt_a2, lane, d);
+        if (lane == 0) {
+#pragma unroll
+            for (uint32_t r = 0; r < 4; ++r) {
+                const uint32_t i = i0 + r * nwarps;
+                if (i < kpp) ek[i] = finite_f32(d[r]) ? make_key(d[r], rows[r]) : WAXVS_KEY_NONE;
+            }
+        }
     }
     __syncthreads();
     block_bitonic_sort(ek, p.rescore);
@@ -1141,10 +1219,24 @@ __global__ void __launch_bounds__(256) filter_rescore_kernel(const float *corpus
         a2 = warp_butterfly_sum(__fadd_rn(__fadd_rn(s0, s1), __fadd_rn(s2, s3)));
         sqrt_a2 = __fsqrt_rn(a2);
     }
-    for (; i < n; i += warps) {
-        const uint32_t row = cand_rows[static_cast<size_t>(q) * cand_cap + i];
-        const float d = exact_row_distance<METRIC>(qv, corpus + static_cast<size_t>(row) * dims, dims, a2, sqrt_a2, lane);
-        if (lane == 0) keys[static_cast<size_t>(q) * cand_cap + i] = finite_f32(d) ? make_key(d, row) : WAXVS_KEY_NONE;
+    for (uint32_t i0 = i; i0 < n; i0 += 4u * warps) {
+        uint32_t rr[4];
+        const float *vp[4];
+        float d[4];
+#pragma unroll
+        for (uint32_t r = 0; r < 4; ++r) {
+            const uint32_t j = i0 + r * warps;
+            rr[r] = cand_rows[static_cast<size_t>(q) * cand_cap + (j < n ? j : i0)];
+            vp[r] = corpus + static_cast<size_t>(rr[r]) * dims;
+        }
+        exact_row_distance_x4<METRIC>(qv, vp, dims, a2, sqrt_a2, lane, d);
+        if (lane == 0) {
+#pragma unroll
+            for (uint32_t r = 0; r < 4; ++r) {
+                const uint32_t j = i0 + r * warps;
+                if (j < n) keys[static_cast<size_t>(q) * cand_cap + j] = finite_f32(d[r]) ? make_key(d[r], rr[r]) : WAXVS_KEY_NONE;
+            }
+        }
     }
 }
 

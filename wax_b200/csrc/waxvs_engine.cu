@@ -131,7 +131,7 @@ struct Tuning {
     int time_overlap = 0;   // wax_vs_debug_time_search: alternate consecutive queries over two streams
     int batch_pair = 0;     // 1: cta_group::2 CTA pairs for the SS shapes (validated; no net gain)
     int batch_ts = 0;       // 1: queries in TMEM + CTA pairs (dims <= 384, dims % 128 == 0)
-    int batch_heap = 0;     // 0 auto, 16 or 64: nominee heap size per (slice, query) = kernel shape
+    int batch_heap = 0;     // 0 auto, 16, 24 (bf16 streamed shape) or 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
     int batch_bf16 = 1;     // 1: nominate from a bf16 shadow of the corpus when HBM allows (kind::f16 MMAs, 2x the TF32 rate; +dims*2 B/row)
     int batch_ares = 1;     // with batch_bf16: keep the CTA's queries resident in shared memory when they fit (dims <= 512)
@@ -839,6 +839,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
             chk(set_smem_attr(batch_nominate_kernel<4, 64, true>, batch_smem_bytes(4, 64, true)));
             chk(set_smem_attr(batch_nominate_kernel<4, 16, false, true>, batch_smem_bytes(4, 16)));
             chk(set_smem_attr(batch_nominate_kernel<3, 64, false, true>, batch_smem_bytes(3, 64)));
+            chk(set_smem_attr(batch_nominate_kernel<4, 24, false, true>, batch_smem_bytes(4, 24) - 2048u));
             chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true>, batch_smem_bytes(6, 16, true)));
             chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true>, batch_smem_bytes(4, 64, true)));
             // ARES shapes: the ring depth is chosen at run time (<= the template's STAGES is what the kernel uses)
@@ -893,7 +894,16 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(unit_slots / units, tiles_total));
         // kernel shape: 16-entry heaps + more stages when 16 nominees per slice comfortably cover k, else 64-entry heaps
         const bool small_heap = e->tune.batch_heap == 16 || (e->tune.batch_heap == 0 && 16u * slices >= 8u * k_eff);
-        const uint32_t kprime = small_heap ? 16u : 64u;
+        // resident queries (bf16) when they leave room for a useful ring: >= 3 corpus stages (pair: >= 4 half-tile stages)
+        const uint32_t num_kb16 = e->dims / kBatchKBlockBf16;
+        const int ares_st = (bf16 && !ts && e->tune.batch_ares) ? ares_stages(pair, small_heap ? 16 : 64, num_kb16, pair ? 6 : 3) : 0;
+        const bool ares = bf16 && !ts && ares_st >= (pair ? 4 : 2) && !(pair && !small_heap && ares_st < 4);
+        // 24-entry heaps (streamed-query bf16 shape only, where they fit beside four stages): when k exceeds the slice
+        // count a slice can hold 16 rows within the bf16 bound of the k-th score and the proof fails (1 query in 1 000
+        // on configs[4]); 24 nominees per slice make that a non-event for the cost of 8 KB.
+        const bool mid_heap = bf16 && !ts && !pair && !ares && (e->tune.batch_heap == 24 ||
+                              (e->tune.batch_heap == 0 && small_heap && slices < k_eff));
+        const uint32_t kprime = mid_heap ? 24u : (small_heap ? 16u : 64u);
         slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));   // union fits the finish sort
         const uint32_t grid = groups * slices;
         if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
@@ -929,11 +939,9 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
             if (small_heap) { cfg.dynamicSmemBytes = batch_ts_smem_bytes(16); lerr = cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<16>, map_c, qbase, bp); }
             else { cfg.dynamicSmemBytes = batch_ts_smem_bytes(64); lerr = cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<64>, map_c, qbase, bp); }
         } else if (bf16) {
-            const uint32_t num_kb = e->dims / kBatchKBlockBf16;
+            const uint32_t num_kb = num_kb16;
             const int heap = small_heap ? 16 : 64;
-            // resident queries when they leave room for a useful ring: >= 3 corpus stages (pair: >= 4 half-tile stages)
-            const int st = e->tune.batch_ares ? ares_stages(pair, heap, num_kb, pair ? 6 : 3) : 0;
-            const bool ares = st >= (pair ? 4 : 2) && !(pair && heap == 64 && st < 4);
+            const int st = ares_st;
             if (ares) {
                 const uint32_t smem = batch_ares_smem_bytes(st, heap, pair, static_cast<int>(num_kb));
                 if (pair) {
@@ -949,7 +957,8 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
                 if (small_heap) lerr = launch_nominate(batch_nominate_kernel<6, 16, true, true>, grid, batch_smem_bytes(6, 16, true), true, stream, map_q, map_c, bp);
                 else lerr = launch_nominate(batch_nominate_kernel<4, 64, true, true>, grid, batch_smem_bytes(4, 64, true), true, stream, map_q, map_c, bp);
             } else {
-                if (small_heap) lerr = launch_nominate(batch_nominate_kernel<4, 16, false, true>, grid, batch_smem_bytes(4, 16), false, stream, map_q, map_c, bp);
+                if (mid_heap) lerr = launch_nominate(batch_nominate_kernel<4, 24, false, true>, grid, batch_smem_bytes(4, 24) - 2048u, false, stream, map_q, map_c, bp);
+                else if (small_heap) lerr = launch_nominate(batch_nominate_kernel<4, 16, false, true>, grid, batch_smem_bytes(4, 16), false, stream, map_q, map_c, bp);
                 else lerr = launch_nominate(batch_nominate_kernel<3, 64, false, true>, grid, batch_smem_bytes(3, 64), false, stream, map_q, map_c, bp);
             }
         } else if (pair) {
