@@ -145,6 +145,16 @@ int32_t wax_vs_search_filtered(wax_vs_engine *engine, const float *query, uint32
                                const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
                                float *out_scores, uint32_t out_cap, uint32_t *out_n);
 
+/* The batched form: ONE filter, n_queries queries, one pass over the corpus (results of query i start at
+   out_ids[i*out_stride], count out_n[i]; out_stride >= min(clamp(top_k), #allowed)).  Allow-lists of <= 16 384 rows
+   score only the listed rows; otherwise the row filter rides below the top-k of the tensor-core levels (nominations,
+   filter level and the exact fall-back consult the same bitset) or of the fused scan.  Results are identical to
+   n_queries calls of wax_vs_search_filtered. */
+int32_t wax_vs_search_batch_filtered(wax_vs_engine *engine, const float *queries, uint32_t n_queries,
+                                     uint32_t query_len, int64_t top_k, const uint64_t *frame_ids, uint64_t n_ids,
+                                     int32_t mode, uint64_t *out_ids, float *out_scores, uint32_t out_stride,
+                                     uint32_t *out_n);
+
 /* Device-resident form used by the row-sharded engine: `d_queries` (n_queries x dims) and
    `d_candidates` (n_queries x k_eff entries, k_eff = min(clamp(top_k), 10000) -- NOT clipped to N, padding
    has valid = 0) are DEVICE pointers on the engine's device; the work is enqueued on `cuda_stream`
@@ -196,6 +206,12 @@ int32_t wax_vs_shard_close(wax_vs_engine *engine);
    wax_vs_search); blocks until the merged result is in the caller's buffers.  out_cap >= clamp(top_k). */
 int32_t wax_vs_shard_search(wax_vs_engine *engine, const float *query, uint32_t query_len, int64_t top_k,
                             uint64_t *out_ids, float *out_scores, uint32_t out_cap, uint32_t *out_n);
+/* wax_vs_search_filtered over the whole sharded corpus: every rank passes the SAME frame_ids / mode; a rank resolves
+   the ids its own shard holds (the rest are unknown to it and ignored), its fused scan applies the row filter below
+   the top-k and the in-kernel exchange merges the ranks' lists.  Still one launch per query per rank. */
+int32_t wax_vs_shard_search_filtered(wax_vs_engine *engine, const float *query, uint32_t query_len, int64_t top_k,
+                                     const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
+                                     float *out_scores, uint32_t out_cap, uint32_t *out_n);
 /* Device-resident form: d_query (dims floats) and d_candidates (clamp(top_k) merged entries, padding valid = 0) are
    device pointers; enqueued on `cuda_stream`, returns without synchronising. */
 int32_t wax_vs_shard_search_device(wax_vs_engine *engine, const float *d_query, int64_t top_k,

@@ -85,6 +85,18 @@ int main() {
         EXPECT(allowed.size() == 2 && (allowed[0].first == 1002 || allowed[0].first == 1003));
         auto denied = engine.searchFiltered(qs[0], 3, {1005}, false);
         EXPECT(denied.size() == 3 && !contains(denied, 1005));
+        // ... and its batched form: one filter, every query, the same answers as the per-query calls
+        std::vector<uint64_t> deny;
+        for (uint64_t i = 0; i < 2000; ++i) deny.push_back(1000 + i);
+        auto fb = engine.searchBatchFiltered(qs, 5, deny, false);
+        EXPECT(fb.size() == 130);
+        for (size_t q : {size_t(0), size_t(77), size_t(129)}) {
+            auto one = engine.searchFiltered(qs[q], 5, deny, false);
+            EXPECT(fb[q].size() == 5 && one.size() == 5);
+            for (size_t i = 0; i < 5; ++i) EXPECT(fb[q][i].first == one[i].first && fb[q][i].second == one[i].second && fb[q][i].first >= 3000);
+        }
+        auto fa = engine.searchBatchFiltered(qs, 2, {1002, 1003}, true);
+        EXPECT(fa.size() == 130 && fa[5].size() == 2 && (fa[5][0].first == 1002 || fa[5][0].first == 1003));
     }
     {   // load(from:): committed blob + pending embeddings replayed as upserts (MetalVectorEngine.swift:318-328)
         CUDAVectorEngine src(VectorMetric::cosine, 4);

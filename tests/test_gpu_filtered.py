@@ -74,3 +74,44 @@ def test_filter_replaces_the_reference_overfetch(oracle):
     eng.add_batch([0, 1, 2, 3], [[1, 0, 0, 0], [0.9, 0.1, 0, 0], [0.5, 0.5, 0, 0], [0, 1, 0, 0]])
     assert [i for i, _ in eng.search([1, 0, 0, 0], 2)] == [0, 1]
     assert [i for i, _ in eng.search_filtered([1, 0, 0, 0], 2, allow=[2, 3])] == [2, 3]
+
+
+@pytest.mark.parametrize("metric", list(VectorMetric))
+def test_batched_filtered_search_equals_the_per_query_filtered_search(oracle, metric):
+    """wax_vs_search_batch_filtered: one filter, a batch of queries, one pass.  Small allow-lists take the batched gather,
+    larger ones the tensor-core levels with the row filter below the top-k (cosine / dot) or the fused scan (l2); every
+    answer equals the single-query filtered search (itself checked against the oracle above), and the first query is
+    checked against the oracle directly."""
+    n, dims, b = 80_000, 384, 130
+    rng = np.random.default_rng(21 + metric.value)
+    corpus = oracle.synth_rows(1500, 0, n, dims, normalize=(metric is not VectorMetric.dot))
+    ids = (np.arange(n, dtype=np.uint64) * 3 + 77)
+    eng = CUDAVectorEngine(metric, dims)
+    eng.add_batch(ids, corpus)
+    qs = oracle.synth_rows(1501, 0, b, dims, normalize=True)
+    small = rng.choice(n, 700, replace=False)
+    large = rng.choice(n, 40_000, replace=False)
+    deny = rng.choice(n, 50_000, replace=False)
+    cases = [("allow", small, set(small.tolist())), ("allow", large, set(large.tolist())),
+             ("deny", deny, set(range(n)) - set(deny.tolist()))]
+    for kind, rows, allowed in cases:
+        for k in (10, 72):
+            kw = {kind: ids[rows]}
+            t0, f0 = eng.batch_stats()
+            got = eng.search_batch_filtered(qs, k, **kw)
+            t1, f1 = eng.batch_stats()
+            assert len(got) == b
+            assert got[0] == _expect(oracle, metric, corpus, ids, allowed, qs[0], k)
+            for qi in range(0, b, 9):
+                assert got[qi] == eng.search_filtered(qs[qi], k, **kw), (kind, len(rows), k, qi)
+            if metric is not VectorMetric.l2 and len(rows) > 16_384:
+                assert (t1 - t0) + (f1 - f0) == b, "a large filtered batch must take the tensor-core levels"
+                assert f1 - f0 <= 3, f"{f1 - f0} of {b} filtered queries fell back to the exact scan"
+    # the best unfiltered hits of every query denied at once: none of them may come back
+    best = sorted({i for q in qs[:8] for i, _ in eng.search(q, 10)})
+    got = eng.search_batch_filtered(qs[:8], 10, deny=best)
+    assert all(not (set(i for i, _ in hits) & set(best)) for hits in got)
+    assert eng.search_batch_filtered(qs[:8], 10, deny=[]) == eng.search_batch(qs[:8], 10)
+    assert eng.search_batch_filtered(qs[:8], 10, allow=[]) == [[] for _ in range(8)]
+    assert eng.search_batch_filtered(qs[:8], 10, allow=ids[:3]) == [eng.search_filtered(q, 10, allow=ids[:3]) for q in qs[:8]]
+    assert eng.search_batch_filtered([], 10, allow=ids[:3]) == []

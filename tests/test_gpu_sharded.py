@@ -166,3 +166,39 @@ def test_sharded_engine_uses_the_fused_transport_on_one_rank(oracle):
     assert eng.search(q, 200) == eng.engine.search(q, 200)     # k > 128: the all-gather transport
     ms, launches = eng.time_search(10, 10, warmup=3, n_queries=4)
     assert ms > 0 and launches == 10                              # one launch per query: the exchange is inside the scan
+
+
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.l2])
+def test_sharded_filtered_search_equals_the_single_engine_filtered_search(oracle, metric):
+    """wax_vs_shard_search_filtered: every rank passes the same ids, resolves the ones its shard holds, applies the row
+    filter inside its fused scan; the in-kernel exchange merges.  Equal to the single-engine filtered search (itself
+    oracle-checked in test_gpu_filtered.py) for allow- and deny-lists, including lists that leave whole shards empty."""
+    dims, total, world = 256, 50_011, 4
+    corpus = oracle.synth_rows(3100, 0, total, dims, normalize=True)
+    ids = np.arange(total, dtype=np.uint64) * 5 + 9
+    single = CUDAVectorEngine(metric, dims)
+    single.add_batch(ids, corpus)
+    grp = Group(metric, dims, corpus=corpus, ids=ids, world=world)
+    rng = np.random.default_rng(5)
+    try:
+        def both(q, k, **kw):
+            res = grp.collective(lambda r, e: e.shard_search_filtered(q, k, **kw))
+            assert all(x == res[0] for x in res), "ranks disagree on the merged result"
+            return res[0], single.search_filtered(q, k, **kw)
+        for qi in range(3):
+            q = oracle.synth_row(3101 + qi, 0, dims, True)
+            allow = ids[rng.choice(total, 20_000, replace=False)]
+            got, want = both(q, 10, allow=allow)
+            assert got == want
+            got, want = both(q, 72, deny=[i for i, _ in single.search(q, 40)])
+            assert got == want
+            first_shard_only = ids[: grp.ranges[0][1]][rng.choice(grp.ranges[0][1], 300, replace=False)]
+            got, want = both(q, 10, allow=first_shard_only)             # every other shard contributes nothing
+            assert got == want and len(got) == 10
+            got, want = both(q, 10, allow=ids[[3, total - 1]])          # fewer allowed rows than k
+            assert got == want and len(got) == 2
+            assert both(q, 10, allow=[1, 2, 3])[0] == []                # unknown ids only
+        assert grp.search(q, 10) == single.search(q, 10)                # the unfiltered path still works afterwards
+    finally:
+        grp.close()
+        single.close()

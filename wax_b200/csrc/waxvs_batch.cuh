@@ -89,6 +89,9 @@ struct BatchParams {
     uint32_t *cand_count;   // [n_queries] appended so far (may exceed cand_cap: overflow)
     uint32_t *cand_rows;    // [n_queries][cand_cap]
     uint32_t cand_cap;
+    // filtered batches (wax_vs_search_batch_filtered): 1 bit per row, set = the row may be returned; nullptr = all rows.
+    // Consulted only on the rare path (a chunk of 32 rows that holds a score above the query's threshold).
+    const uint32_t *allow_bits;
 };
 
 // ---- PTX wrappers (tcgen05 / TMA tensor) ---------------------------------------------------------------------
@@ -587,6 +590,8 @@ batch_nominate_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_c
                     for (uint32_t j = 0; j < 32; ++j) mask |= (sv[j] > tau ? 1u : 0u) << j;
                     const uint32_t cols = rows_here - chunk * 32u;                 // >= 1 here
                     if (cols < 32u) mask &= (1u << cols) - 1u;
+                    // row0 + chunk * 32 is a multiple of 32: the chunk's 32 rows are exactly one word of the row filter
+                    if (p.allow_bits) mask &= __ldg(p.allow_bits + ((row0 + chunk * 32u) >> 5));
                     while (mask) {
                         if (cnt + __popc(mask) > kBatchStageSlots) flush();       // empties the slots, may raise tau
                         uint32_t take = mask;
@@ -1010,9 +1015,11 @@ __device__ __forceinline__ void block_bitonic_sort(uint64_t *sk, uint32_t pow2) 
 // ---- small allow-lists: score only the listed rows (O(n_allow), not O(N)) --------------------------------------------
 // One warp per listed row, exact distance in the kernels' order; then one CTA sorts the keys.
 template <int METRIC>
-__global__ void __launch_bounds__(256) gather_score_kernel(const float *corpus, const float *query, uint32_t dims,
-                                                           const uint32_t *rows, uint32_t n, uint64_t *keys) {
+__global__ void __launch_bounds__(256) gather_score_kernel(const float *corpus, const float *queries, uint32_t dims,
+                                                           const uint32_t *rows, uint32_t n, uint64_t *keys_all) {
     const int lane = threadIdx.x & 31;
+    const float *query = queries + static_cast<size_t>(blockIdx.y) * dims;     // grid.y = queries of a filtered batch
+    uint64_t *keys = keys_all + static_cast<size_t>(blockIdx.y) * n;
     float a2 = 0.0f, sqrt_a2 = 0.0f;
     if (METRIC == kCosine) {
         float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
@@ -1047,8 +1054,10 @@ __global__ void __launch_bounds__(256) gather_score_kernel(const float *corpus, 
     }
 }
 
-__global__ void __launch_bounds__(1024) gather_sort_kernel(const uint64_t *keys, uint32_t n, uint32_t pow2, ScanParams p) {
+__global__ void __launch_bounds__(1024) gather_sort_kernel(const uint64_t *keys_all, uint32_t n, uint32_t pow2, ScanParams p) {
     extern __shared__ uint64_t gsk[];
+    const uint64_t *keys = keys_all + static_cast<size_t>(blockIdx.x) * n;     // one CTA per query
+    p.out += static_cast<size_t>(blockIdx.x) * p.k;
     for (uint32_t i = threadIdx.x; i < pow2; i += blockDim.x) gsk[i] = (i < n) ? keys[i] : WAXVS_KEY_NONE;
     __syncthreads();
     block_bitonic_sort(gsk, pow2);

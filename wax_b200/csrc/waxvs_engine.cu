@@ -818,7 +818,8 @@ static int ares_stages(bool pair, int heap, uint32_t num_kb, int want) {
 static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
                                     uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, uint32_t *d_ok,
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
-                                    bool allow_bf16 = true, bool *used_bf16 = nullptr, float *d_tau_star = nullptr) {
+                                    bool allow_bf16 = true, bool *used_bf16 = nullptr, float *d_tau_star = nullptr,
+                                    const uint32_t *d_mask = nullptr) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
     bool bf16 = allow_bf16 && batch_bf16_wanted(e);
@@ -884,7 +885,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         // cta_group::2: CTA pairs (two query groups, one row slice) issue one 256-row MMA and each stages only half of
         // the corpus tile.  Needs at least two groups; an odd group count is padded with an all-out-of-range group.
         // TS shape: queries in TMEM + CTA pair (dims <= 384, dims % 128 == 0): shared memory carries only the corpus
-        const bool ts = !bf16 && e->tune.batch_ts != 0 && groups >= 2 && e->dims <= 384 && e->dims % 128u == 0;
+        const bool ts = !bf16 && !d_mask && e->tune.batch_ts != 0 && groups >= 2 && e->dims <= 384 && e->dims % 128u == 0;
         const bool pair = ts || (e->tune.batch_pair != 0 && groups >= 2);
         if (pair) groups = (groups + 1u) & ~1u;
         const uint32_t tile_rows = ts ? static_cast<uint32_t>(kTsN) : static_cast<uint32_t>(kBatchN);
@@ -928,6 +929,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         bp.heaps = c->d_heaps;
         bp.tau_global = c->d_tau;
         bp.no_insert = e->tune.batch_noinsert ? 1u : 0u;
+        bp.allow_bits = d_mask;
         cudaError_t lerr = cudaSuccess;
         if (ts) {
             cudaLaunchConfig_t cfg{};
@@ -1542,7 +1544,7 @@ int32_t wax_vs_remove(wax_vs_engine *e, uint64_t frame_id) {
 static int32_t enqueue_filter_level(wax_vs_engine *e, SearchCtx *c, const float *d_queries, const float *d_tau,
                                     uint32_t n_queries, uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out,
                                     uint32_t *d_ok, const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
-                                    bool bf16 = false) {
+                                    bool bf16 = false, const uint32_t *d_mask = nullptr) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
     if (bf16) {
@@ -1582,6 +1584,7 @@ static int32_t enqueue_filter_level(wax_vs_engine *e, SearchCtx *c, const float 
         bp.cand_count = c->d_cand_count + q0;
         bp.cand_rows = c->d_cand_rows + static_cast<size_t>(q0) * cap;
         bp.cand_cap = cap;
+        bp.allow_bits = d_mask;
         if (bf16) {
             const uint32_t num_kb = e->dims / kBatchKBlockBf16;
             const int st = e->tune.batch_ares ? ares_stages(false, 16, num_kb, 3) : 0;
@@ -1620,7 +1623,7 @@ static int32_t enqueue_filter_level(wax_vs_engine *e, SearchCtx *c, const float 
 // levels read their proof flags back, so they synchronise c->stream; the scan loop only enqueues.
 static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float *d_queries, uint32_t n_queries,
                                      uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, const uint64_t *d_ids,
-                                     uint64_t *launches) {
+                                     uint64_t *launches, const uint32_t *d_mask = nullptr) {
     int32_t rc = WAX_VS_OK;
     bool tensor_path = batch_tensor_eligible(e, n_queries, k_eff), allow_bf16 = true;
     if (tensor_path) {
@@ -1638,7 +1641,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         if ((rc = ensure_pinned(&c->h_tau_star, &c->h_tau_star_cap, static_cast<size_t>(n_queries) * 2, "filter threshold staging"))) return rc;
         bool used_bf16 = false;
         rc = enqueue_batch_tensor(e, c, d_queries, n_queries, k_eff, row_offset, d_out, c->d_ok, d_ids, c->stream, launches,
-                                  allow_bf16, &used_bf16, c->d_tau_star);
+                                  allow_bf16, &used_bf16, c->d_tau_star, d_mask);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->h_tau_star, c->d_tau_star, 2 * n_queries * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1671,7 +1674,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
                                          d_queries + static_cast<size_t>(todo[i]) * e->dims, e->dims * sizeof(float),
                                          cudaMemcpyDeviceToDevice, c->stream));
             frc = enqueue_filter_level(e, c, c->d_retry_q, c->d_filter_tau, nf, k_eff, row_offset, c->d_retry_out,
-                                       c->d_retry_ok, d_ids, c->stream, launches, bf16lvl);
+                                       c->d_retry_ok, d_ids, c->stream, launches, bf16lvl, d_mask);
             if (frc) { cudaStreamSynchronize(c->stream); return frc; }
             CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_retry_ok, nf * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
             CUDA_TRY(cudaStreamSynchronize(c->stream));
@@ -1705,7 +1708,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         }
         for (uint32_t qi : unproven) {
             rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
-                                d_out + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, launches);
+                                d_out + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, launches, d_mask);
             if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         }
         {
@@ -1720,7 +1723,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
     } else {
         for (uint32_t qi = 0; qi < n_queries; ++qi) {
             rc = enqueue_search(e, c, d_queries + static_cast<size_t>(qi) * e->dims, k_eff, row_offset,
-                                d_out + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, launches);
+                                d_out + static_cast<size_t>(qi) * k_eff, d_ids, c->stream, launches, d_mask);
             if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         }
     }
@@ -2139,47 +2142,56 @@ int32_t wax_vs_debug_time_shard_search(wax_vs_engine *e, uint32_t n_queries, int
 // The reference filters AFTER the engine call and over-fetches 3 x topK to compensate (UnifiedSearch.swift:58,
 // 371-442, 1195-1200, 1241-1258).  Here the filter is pushed below the top-k: a row bitset consulted only for rows
 // that would enter the list, or -- for small allow-lists -- a gather that scores only the listed rows.
-int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k,
-                               const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
-                               float *out_scores, uint32_t out_cap, uint32_t *out_n) {
+// frameIds -> rows of this engine (unknown ids are ignored), as a bitset (bit set = the row may be returned) and as the
+// list of rows the ids named.  Returns the number of rows that may be returned.
+static uint64_t build_row_filter(wax_vs_engine *e, const uint64_t *frame_ids, uint64_t n_ids, int32_t mode,
+                                 std::vector<uint32_t> &bits, std::vector<uint32_t> &listed) {
+    const uint64_t n_rows = e->n_rows;
+    bits.assign((n_rows + 31) / 32, mode == 0 ? 0u : 0xFFFFFFFFu);
+    if (mode == 1 && (n_rows & 31u)) bits.back() = (1u << (n_rows & 31u)) - 1u;
+    listed.clear();
+    std::lock_guard<std::mutex> g(e->ids_mu);   // the lazily built id map is shared by concurrent readers
+    // (find_row builds the lazily constructed hash table when it is needed: serialised by ids_mu)
+    for (uint64_t i = 0; i < n_ids; ++i) {
+        uint64_t row;
+        if (e->ids_identity) {
+            if (frame_ids[i] < e->id_base || frame_ids[i] - e->id_base >= n_rows) continue;
+            row = frame_ids[i] - e->id_base;
+        } else {
+            const uint32_t f = find_row(e, frame_ids[i]);
+            if (f == 0xFFFFFFFFu) continue;
+            row = f;
+        }
+        const uint32_t w = static_cast<uint32_t>(row >> 5), b = 1u << (row & 31u);
+        if (mode == 0) { if (!(bits[w] & b)) { bits[w] |= b; listed.push_back(static_cast<uint32_t>(row)); } }
+        else if (bits[w] & b) { bits[w] &= ~b; listed.push_back(static_cast<uint32_t>(row)); }
+    }
+    return mode == 0 ? listed.size() : n_rows - listed.size();
+}
+
+// One filter, n_queries queries.  Small allow-lists: gather + exact score of the listed rows only (grid.y = query), one
+// CTA per query sorts.  Otherwise the row bitset rides below the top-k: in the fused scan (one query, or a batch the
+// tensor path cannot take) or in the tensor-core levels (nominations, filter level and the exact fall-back all consult
+// the same bitset, so the completeness proof is a statement about the ALLOWED rows).
+static int32_t search_filtered_host(wax_vs_engine *e, const float *queries, uint32_t n_queries, uint32_t query_len,
+                                    int64_t top_k, const uint64_t *frame_ids, uint64_t n_ids, int32_t mode,
+                                    uint64_t *out_ids, float *out_scores, uint32_t out_stride, uint32_t *out_n) {
     if (!e || !out_n) return fail(WAX_VS_ERR_NULL, "NULL argument");
     if (mode != 0 && mode != 1) return fail(WAX_VS_ERR_ARGUMENT, "filter mode must be 0 (allow-list) or 1 (deny-list)");
     if (n_ids && !frame_ids) return fail(WAX_VS_ERR_NULL, "frame_ids is NULL");
     std::shared_lock<std::shared_mutex> r(e->rw);
-    *out_n = 0;
-    if (e->n_rows == 0) return WAX_VS_OK;
-    if (!query) return fail(WAX_VS_ERR_NULL, "query is NULL");
+    for (uint32_t i = 0; i < n_queries; ++i) out_n[i] = 0;
+    if (e->n_rows == 0 || n_queries == 0) return WAX_VS_OK;
+    if (!queries) return fail(WAX_VS_ERR_NULL, "query is NULL");
     if (query_len != e->dims)
         return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, query_len);
 
-    // ids -> rows (unknown ids are ignored), as a bitset and as a list
-    const uint64_t n_rows = e->n_rows;
-    std::vector<uint32_t> bits((n_rows + 31) / 32, mode == 0 ? 0u : 0xFFFFFFFFu);
-    if (mode == 1 && (n_rows & 31u)) bits.back() = (1u << (n_rows & 31u)) - 1u;
-    std::vector<uint32_t> listed;
-    {
-        std::lock_guard<std::mutex> g(e->ids_mu);   // the lazily built id map is shared by concurrent readers
-        // (find_row builds the lazily constructed hash table when it is needed: serialised by ids_mu)
-        for (uint64_t i = 0; i < n_ids; ++i) {
-            uint64_t row;
-            if (e->ids_identity) {
-                if (frame_ids[i] < e->id_base || frame_ids[i] - e->id_base >= n_rows) continue;
-                row = frame_ids[i] - e->id_base;
-            } else {
-                const uint32_t f = find_row(e, frame_ids[i]);
-                if (f == 0xFFFFFFFFu) continue;
-                row = f;
-            }
-            const uint32_t w = static_cast<uint32_t>(row >> 5), b = 1u << (row & 31u);
-            if (mode == 0) { if (!(bits[w] & b)) { bits[w] |= b; listed.push_back(static_cast<uint32_t>(row)); } }
-            else if (bits[w] & b) { bits[w] &= ~b; listed.push_back(static_cast<uint32_t>(row)); }
-        }
-    }
-    const uint64_t allowed = mode == 0 ? listed.size() : n_rows - listed.size();
+    std::vector<uint32_t> bits, listed;
+    const uint64_t allowed = build_row_filter(e, frame_ids, n_ids, mode, bits, listed);
     const uint32_t k_eff = static_cast<uint32_t>(std::min<uint64_t>(clamp_topk(top_k), allowed));
     if (k_eff == 0) return WAX_VS_OK;
     if (!out_ids || !out_scores) return fail(WAX_VS_ERR_NULL, "output buffer is NULL");
-    if (out_cap < k_eff) return fail(WAX_VS_ERR_BUFFER, "output buffers hold %u entries, need %u", out_cap, k_eff);
+    if (out_stride < k_eff) return fail(WAX_VS_ERR_BUFFER, "output buffers hold %u entries, need %u", out_stride, k_eff);
 
     DeviceGuard g(e->device);
     if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
@@ -2187,28 +2199,23 @@ int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t qu
     int32_t rc = ctx_acquire(e, &c);
     if (rc) return rc;
     struct Rel { wax_vs_engine *e; SearchCtx *c; ~Rel() { ctx_release(e, c); } } rel{e, c};
-    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, static_cast<size_t>(e->dims), "query buffer"))) return rc;
-    if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, static_cast<size_t>(e->dims), "query staging"))) return rc;
-    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, static_cast<size_t>(k_eff), "result buffer"))) return rc;
-    if ((rc = ensure_pinned(&c->h_out, &c->h_out_cap, static_cast<size_t>(k_eff), "result staging"))) return rc;
-    memcpy(c->h_queries, query, e->dims * sizeof(float));
-    CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, e->dims * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    const size_t qfloats = static_cast<size_t>(n_queries) * e->dims;
+    const size_t ncand = static_cast<size_t>(n_queries) * k_eff;
+    if ((rc = ensure_dev(&c->d_queries, &c->d_queries_cap, qfloats, "query buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_queries, &c->h_queries_cap, qfloats, "query staging"))) return rc;
+    if ((rc = ensure_dev(&c->d_out, &c->d_out_cap, ncand, "result buffer"))) return rc;
+    if ((rc = ensure_pinned(&c->h_out, &c->h_out_cap, ncand, "result staging"))) return rc;
+    memcpy(c->h_queries, queries, qfloats * sizeof(float));
+    CUDA_TRY(cudaMemcpyAsync(c->d_queries, c->h_queries, qfloats * sizeof(float), cudaMemcpyHostToDevice, c->stream));
 
     uint64_t launches = 0;
     if (mode == 0 && listed.size() <= 16384) {
-        // small allow-list: gather + exact score of the listed rows only, then one-CTA sort
+        // small allow-list: gather + exact score of the listed rows only, then one-CTA sorts
         std::sort(listed.begin(), listed.end());
         const uint32_t n = static_cast<uint32_t>(listed.size());
         if ((rc = ensure_dev(&c->d_mask, &c->mask_cap, static_cast<size_t>(std::max<uint32_t>(n, 1)), "listed rows"))) return rc;
-        if ((rc = ensure_dev(&c->d_gather_keys, &c->gather_cap, static_cast<size_t>(std::max<uint32_t>(n, 1)), "gather keys"))) return rc;
+        if ((rc = ensure_dev(&c->d_gather_keys, &c->gather_cap, static_cast<size_t>(std::max<uint32_t>(n, 1)) * n_queries, "gather keys"))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->d_mask, listed.data(), n * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        const int ggrid = static_cast<int>(std::min<uint32_t>((n + 7) / 8, static_cast<uint32_t>(e->sm_count) * 8));
-        switch (e->similarity) {
-            case WAX_VS_COSINE: gather_score_kernel<kCosine><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, c->d_queries, e->dims, c->d_mask, n, c->d_gather_keys); break;
-            case WAX_VS_DOT: gather_score_kernel<kDot><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, c->d_queries, e->dims, c->d_mask, n, c->d_gather_keys); break;
-            default: gather_score_kernel<kL2><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, c->d_queries, e->dims, c->d_mask, n, c->d_gather_keys); break;
-        }
-        CUDA_TRY(cudaGetLastError());
         uint32_t pow2 = 64;
         while (pow2 < n) pow2 <<= 1;
         {
@@ -2218,24 +2225,113 @@ int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t qu
                 e->gather_attr_set = true;
             }
         }
-        ScanParams sp{};
-        sp.k = k_eff; sp.out = c->d_out; sp.id_base = e->id_base;
-        gather_sort_kernel<<<1, 1024, pow2 * sizeof(uint64_t), c->stream>>>(c->d_gather_keys, n, pow2, sp);
-        CUDA_TRY(cudaGetLastError());
-        launches += 2;
+        const uint32_t gx = std::max<uint32_t>(1, std::min<uint32_t>((n + 31) / 32, static_cast<uint32_t>(e->sm_count) * 8));
+        for (uint32_t q0 = 0; q0 < n_queries; q0 += 32768u) {       // grid.y limit
+            const uint32_t nq = std::min<uint32_t>(n_queries - q0, 32768u);
+            const dim3 ggrid(gx, nq);
+            const float *dq = c->d_queries + static_cast<size_t>(q0) * e->dims;
+            uint64_t *keys = c->d_gather_keys + static_cast<size_t>(q0) * n;
+            switch (e->similarity) {
+                case WAX_VS_COSINE: gather_score_kernel<kCosine><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, dq, e->dims, c->d_mask, n, keys); break;
+                case WAX_VS_DOT: gather_score_kernel<kDot><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, dq, e->dims, c->d_mask, n, keys); break;
+                default: gather_score_kernel<kL2><<<ggrid, 256, 0, c->stream>>>(e->d_corpus, dq, e->dims, c->d_mask, n, keys); break;
+            }
+            CUDA_TRY(cudaGetLastError());
+            ScanParams sp{};
+            sp.k = k_eff; sp.out = c->d_out + static_cast<size_t>(q0) * k_eff; sp.id_base = e->id_base;
+            gather_sort_kernel<<<nq, 1024, pow2 * sizeof(uint64_t), c->stream>>>(keys, n, pow2, sp);
+            CUDA_TRY(cudaGetLastError());
+            launches += 2;
+        }
     } else {
         if ((rc = ensure_dev(&c->d_mask, &c->mask_cap, bits.size(), "row filter"))) return rc;
         CUDA_TRY(cudaMemcpyAsync(c->d_mask, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-        rc = enqueue_search(e, c, c->d_queries, k_eff, 0, c->d_out, nullptr, c->stream, &launches, c->d_mask);
-        if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        if (n_queries == 1) {
+            rc = enqueue_search(e, c, c->d_queries, k_eff, 0, c->d_out, nullptr, c->stream, &launches, c->d_mask);
+            if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        } else if ((rc = run_queries_on_device(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, nullptr, &launches, c->d_mask))) {
+            return rc;
+        }
     }
-    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, k_eff * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
+    CUDA_TRY(cudaMemcpyAsync(c->h_out, c->d_out, ncand * sizeof(wax_vs_candidate), cudaMemcpyDeviceToHost, c->stream));
     CUDA_TRY(cudaStreamSynchronize(c->stream));   // also keeps `bits` / `listed` alive until the copies are done
+    for (uint32_t qi = 0; qi < n_queries; ++qi) {
+        uint32_t m = 0;
+        for (uint32_t i = 0; i < k_eff; ++i) {
+            const wax_vs_candidate &cd = c->h_out[static_cast<size_t>(qi) * k_eff + i];
+            if (!cd.valid) continue;
+            out_ids[static_cast<size_t>(qi) * out_stride + m] = e->ids_identity ? e->id_base + cd.row : e->ids[cd.row];
+            out_scores[static_cast<size_t>(qi) * out_stride + m] = score_from_distance(e->similarity, cd.distance);
+            ++m;
+        }
+        out_n[qi] = m;
+    }
+    return WAX_VS_OK;
+}
+
+int32_t wax_vs_search_filtered(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k,
+                               const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
+                               float *out_scores, uint32_t out_cap, uint32_t *out_n) {
+    return search_filtered_host(e, query, 1, query_len, top_k, frame_ids, n_ids, mode, out_ids, out_scores, out_cap, out_n);
+}
+
+int32_t wax_vs_search_batch_filtered(wax_vs_engine *e, const float *queries, uint32_t n_queries, uint32_t query_len,
+                                     int64_t top_k, const uint64_t *frame_ids, uint64_t n_ids, int32_t mode,
+                                     uint64_t *out_ids, float *out_scores, uint32_t out_stride, uint32_t *out_n) {
+    return search_filtered_host(e, queries, n_queries, query_len, top_k, frame_ids, n_ids, mode, out_ids, out_scores,
+                                out_stride, out_n);
+}
+
+// The row-sharded form: every rank passes the SAME ids; a rank resolves the ones its shard holds (the others are
+// unknown to it and ignored), its fused scan consults the bitset below the top-k, and the usual in-kernel exchange
+// merges the ranks' lists -- the answer is the filtered top-k of the whole corpus, identical on every rank.
+int32_t wax_vs_shard_search_filtered(wax_vs_engine *e, const float *query, uint32_t query_len, int64_t top_k,
+                                     const uint64_t *frame_ids, uint64_t n_ids, int32_t mode, uint64_t *out_ids,
+                                     float *out_scores, uint32_t out_cap, uint32_t *out_n) {
+    if (!e || !out_n) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (mode != 0 && mode != 1) return fail(WAX_VS_ERR_ARGUMENT, "filter mode must be 0 (allow-list) or 1 (deny-list)");
+    if (n_ids && !frame_ids) return fail(WAX_VS_ERR_NULL, "frame_ids is NULL");
+    std::shared_lock<std::shared_mutex> r(e->rw);
+    *out_n = 0;
+    if (!e->shard.connected) return fail(WAX_VS_ERR_ARGUMENT, "the shard group is not connected (wax_vs_shard_open / _connect)");
+    if (!query) return fail(WAX_VS_ERR_NULL, "query is NULL");
+    if (query_len != e->dims)
+        return fail(WAX_VS_ERR_DIMENSION, "vector dimension mismatch: expected %u, got %u", e->dims, query_len);
+    const uint32_t k_eff = clamp_topk(top_k);
+    if (k_eff > static_cast<uint32_t>(kShardKCap))
+        return fail(WAX_VS_ERR_UNSUPPORTED, "sharded search supports top_k <= %d (got %u)", kShardKCap, k_eff);
+    if (!out_ids || !out_scores) return fail(WAX_VS_ERR_NULL, "output buffer is NULL");
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    std::vector<uint32_t> bits, listed;
+    if (e->n_rows) build_row_filter(e, frame_ids, n_ids, mode, bits, listed);
+    auto &sh = e->shard;
+    std::lock_guard<std::mutex> sg(sh.mu);      // one host-path collective at a time: it owns sh.ctx and h_final
+    SearchCtx *c = sh.ctx;
+    int32_t rc;
+    const uint64_t *d_ids = nullptr;
+    if ((rc = sync_device_ids(e, &d_ids))) return rc;
+    if (!bits.empty()) {
+        if ((rc = ensure_dev(&c->d_mask, &c->mask_cap, bits.size(), "row filter"))) return rc;
+        CUDA_TRY(cudaMemcpyAsync(c->d_mask, bits.data(), bits.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+    }
+    ShardParams sp = shard_params_next(e);
+    sp.host_out = sh.h_final; sp.host_flag = sh.h_flag;
+    HostDelivery hd{query, nullptr, nullptr, 0};
+    uint64_t launches = 0;
+    if ((rc = enqueue_search(e, c, nullptr, k_eff, sh.row_offset, sh.d_final, d_ids, c->stream, &launches,
+                             bits.empty() ? nullptr : c->d_mask, &sp, &hd))) {
+        cudaStreamSynchronize(c->stream);
+        return rc;
+    }
+    if ((rc = shard_wait_host(e, sp.seq))) { cudaStreamSynchronize(c->stream); return rc; }
+    CUDA_TRY(cudaStreamSynchronize(c->stream));   // `bits` must outlive its upload
     uint32_t m = 0;
     for (uint32_t i = 0; i < k_eff; ++i) {
-        const wax_vs_candidate &cd = c->h_out[i];
-        if (!cd.valid) continue;
-        out_ids[m] = e->ids_identity ? e->id_base + cd.row : e->ids[cd.row];
+        const wax_vs_candidate &cd = sh.h_final[i];
+        if (cd.valid != 1u) continue;
+        if (m >= out_cap) return fail(WAX_VS_ERR_BUFFER, "output buffers hold %u entries, need more", out_cap);
+        out_ids[m] = cd.frame_id;
         out_scores[m] = score_from_distance(e->similarity, cd.distance);
         ++m;
     }

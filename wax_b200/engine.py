@@ -238,6 +238,29 @@ class CUDAVectorEngine:
                                               scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return [(int(out_ids[i]), float(scores[i])) for i in range(n.value)]
 
+    def search_batch_filtered(self, vectors, top_k: int, allow: Optional[Sequence[int]] = None,
+                              deny: Optional[Sequence[int]] = None) -> List[List[Tuple[int, float]]]:
+        """`search_filtered` for a batch of queries under ONE filter, in one pass over the corpus
+        (wax_vs_search_batch_filtered); the same answers as calling search_filtered per query."""
+        if (allow is None) == (deny is None):
+            raise ValueError("pass exactly one of allow= / deny=")
+        fids = np.ascontiguousarray(allow if allow is not None else deny, dtype=np.uint64).reshape(-1)
+        qs = _as_rows(vectors, self.dimensions) if len(vectors) else np.zeros((0, self.dimensions), np.float32)
+        b = qs.shape[0]
+        if b == 0:
+            return []
+        cap = _clamp_topk(top_k)
+        ids = np.zeros((b, cap), np.uint64)
+        scores = np.zeros((b, cap), np.float32)
+        ns = np.zeros(b, np.uint32)
+        idp = fids.ctypes.data_as(C.POINTER(C.c_uint64)) if fids.size else None
+        _check(L.lib().wax_vs_search_batch_filtered(self._h, qs.ctypes.data_as(C.POINTER(C.c_float)), b, qs.shape[1],
+                                                    int(top_k), idp, fids.size, 0 if allow is not None else 1,
+                                                    ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                    scores.ctypes.data_as(C.POINTER(C.c_float)), cap,
+                                                    ns.ctypes.data_as(C.POINTER(C.c_uint32))))
+        return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(b)]
+
     def search_batch(self, vectors, top_k: int) -> List[List[Tuple[int, float]]]:
         ids, scores, ns = self.search_batch_arrays(vectors, top_k)
         return [[(int(ids[i, j]), float(scores[i, j])) for j in range(int(ns[i]))] for i in range(ids.shape[0])]
@@ -342,6 +365,25 @@ class CUDAVectorEngine:
         _check(L.lib().wax_vs_shard_search(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k),
                                            ids.ctypes.data_as(C.POINTER(C.c_uint64)),
                                            scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
+        return [(int(ids[i]), float(scores[i])) for i in range(n.value)]
+
+    def shard_search_filtered(self, vector: Sequence[float], top_k: int, allow: Optional[Sequence[int]] = None,
+                              deny: Optional[Sequence[int]] = None) -> List[Tuple[int, float]]:
+        """COLLECTIVE filtered search (every rank passes the same query and the same ids): each rank's fused scan
+        applies the filter to the rows of its own shard, the in-kernel exchange merges -- one launch per rank."""
+        if (allow is None) == (deny is None):
+            raise ValueError("pass exactly one of allow= / deny=")
+        fids = np.ascontiguousarray(allow if allow is not None else deny, dtype=np.uint64).reshape(-1)
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        cap = _clamp_topk(top_k)
+        ids = np.empty(cap, np.uint64)
+        scores = np.empty(cap, np.float32)
+        n = C.c_uint32(0)
+        idp = fids.ctypes.data_as(C.POINTER(C.c_uint64)) if fids.size else None
+        _check(L.lib().wax_vs_shard_search_filtered(self._h, q.ctypes.data_as(C.POINTER(C.c_float)), q.size, int(top_k),
+                                                    idp, fids.size, 0 if allow is not None else 1,
+                                                    ids.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                    scores.ctypes.data_as(C.POINTER(C.c_float)), cap, C.byref(n)))
         return [(int(ids[i]), float(scores[i])) for i in range(n.value)]
 
     def time_shard_search(self, top_k: int, iters: int, warmup: int = 3, n_queries: int = 1, seed: int = 7):

@@ -140,6 +140,33 @@ public:
         return out;
     }
 
+    // searchFiltered for a batch of queries under ONE filter, one pass over the corpus (wax_vs_search_batch_filtered).
+    std::vector<std::vector<Hit>> searchBatchFiltered(const std::vector<std::vector<float>> &vectors, int64_t topK,
+                                                      const std::vector<uint64_t> &frameIds, bool allow) const {
+        std::vector<std::vector<Hit>> out(vectors.size());
+        if (vectors.empty()) return out;
+        std::vector<float> flat;
+        flat.reserve(vectors.size() * dimensions_);
+        for (const auto &v : vectors) {
+            if (v.size() != dimensions_)
+                throw EncodingError("vector dimension mismatch: expected " + std::to_string(dimensions_) + ", got " +
+                                    std::to_string(v.size()));
+            flat.insert(flat.end(), v.begin(), v.end());
+        }
+        const uint32_t lim = static_cast<uint32_t>(topK < 1 ? 1 : (topK > WAX_VS_MAX_RESULTS ? WAX_VS_MAX_RESULTS : topK));
+        std::vector<uint64_t> ids(vectors.size() * lim);
+        std::vector<float> scores(vectors.size() * lim);
+        std::vector<uint32_t> ns(vectors.size());
+        check(wax_vs_search_batch_filtered(h_, flat.data(), static_cast<uint32_t>(vectors.size()), dimensions_, topK,
+                                           frameIds.data(), frameIds.size(), allow ? 0 : 1, ids.data(), scores.data(), lim,
+                                           ns.data()));
+        for (size_t q = 0; q < vectors.size(); ++q) {
+            out[q].resize(ns[q]);
+            for (uint32_t i = 0; i < ns[q]; ++i) out[q][i] = {ids[q * lim + i], scores[q * lim + i]};
+        }
+        return out;
+    }
+
     // static load(from:metric:dimensions:) (MetalVectorEngine.swift:318-328): the committed blob (may be empty = none
     // committed yet), then the pending embedding mutations as ONE upsert batch (sequential semantics in the library).
     static CUDAVectorEngine *load(const std::vector<uint8_t> *committedBlob, const std::vector<uint64_t> &pendingIds,

@@ -420,6 +420,20 @@ class ShardedVectorEngine:
         d_q = torch.from_numpy(q).to(self.device, non_blocking=False)
         return self.finish(self.search_async(d_q, top_k))
 
+    def search_filtered(self, vector: Sequence[float], top_k: int, allow=None, deny=None) -> List[Tuple[int, float]]:
+        """Filtered search over the whole sharded corpus (collective: same query and ids on every rank).  Needs the
+        fused peer-memory transport: the filter rides in each rank's scan, the exchange is unchanged."""
+        q = np.ascontiguousarray(vector, dtype=np.float32).reshape(-1)
+        if q.size != self.dimensions:
+            from .engine import EncodingError
+            raise EncodingError(f"vector dimension mismatch: expected {self.dimensions}, got {q.size}")
+        if self.total_rows == 0:
+            return []
+        if self.transport != "p2p-fused" or clamp_topk(top_k) > 128:
+            from .engine import InvalidToc
+            raise InvalidToc("sharded filtered search needs the p2p-fused transport and top_k <= 128")
+        return self.engine.shard_search_filtered(q, top_k, allow=allow, deny=deny)
+
     def _search_fused(self, q: np.ndarray, top_k: int) -> List[Tuple[int, float]]:
         """wax_vs_shard_search: host query in, merged host result out; scan + NVLink exchange + merge in one launch."""
         return self.engine.shard_search(q, top_k)
