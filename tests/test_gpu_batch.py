@@ -373,3 +373,30 @@ def test_batch_larger_than_one_launch_of_query_groups(oracle):
         want = eng.search(qs[qi], 5)
         assert [int(i) for i in ids[qi]] == [w[0] for w in want], qi
         assert np.array_equal(scores[qi], np.float32([w[1] for w in want])), qi
+
+
+@pytest.mark.parametrize("metric", [VectorMetric.cosine, VectorMetric.dot])
+@pytest.mark.parametrize("dims,n,b,k", [(384, 150_000, 40, 200), (384, 150_000, 130, 500), (768, 70_000, 9, 1000),
+                                        (128, 70_000, 300, 1024), (384, 100_003, 1100, 160)])
+def test_large_k_batches_take_the_tensor_levels(oracle, metric, dims, n, b, k):
+    """128 < k <= 1024 (the production candidate limit reaches 1 000, UnifiedSearch.swift:1195-1200): level 1 keeps 64
+    nominees per slice and re-scores 1 024 of them exactly -- rarely a proof, but their k-th exact score is a valid
+    threshold for the filter level, which lists EVERY row above it.  Same ids and score bits as the single-query emit +
+    radix-select path, without looping it."""
+    eng = _engine(oracle, metric, n, dims, seed=880 + dims, normalize=(metric is VectorMetric.cosine))
+    qs = oracle.synth_rows(881 + b, 0, b, dims, normalize=True)
+    t0, f0 = eng.batch_stats()
+    got = eng.search_batch(qs, k)
+    t1, f1 = eng.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == b, "the batch did not take the tensor-core levels"
+    assert f1 - f0 <= max(1, b // 20), f"{f1 - f0} of {b} queries fell back to the exact scan"
+    sample = sorted(set(range(0, b, max(1, b // 12))) | {b - 1})
+    eng.set_option("batch_tensor", 0)
+    for qi in sample:
+        assert got[qi] == eng.search(qs[qi], k), (qi,)
+    eng.set_option("batch_tensor", 1)
+    assert all(len(hits) == min(k, n) for hits in got)
+    eng.set_option("batch_large_k", 0)                          # opt-out: the loop answers, same results
+    t2, f2 = eng.batch_stats()
+    assert eng.search_batch(qs[:5], k) == got[:5]
+    assert eng.batch_stats() == (t2, f2)

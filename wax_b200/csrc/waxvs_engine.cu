@@ -131,6 +131,7 @@ struct Tuning {
     int time_overlap = 0;   // wax_vs_debug_time_search: alternate consecutive queries over two streams
     int batch_pair = 0;     // 1: cta_group::2 CTA pairs for the SS shapes (validated; no net gain)
     int batch_ts = 0;       // 1: queries in TMEM + CTA pairs (dims <= 384, dims % 128 == 0)
+    int batch_large_k = 1;  // batches with 128 < k <= 1024 take the tensor-core levels (0: loop the single-query emit + select path)
     int batch_heap = 0;     // 0 auto, 16, 24 (bf16 streamed shape) or 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
     int batch_bf16 = 1;     // 1: nominate from a bf16 shadow of the corpus when HBM allows (kind::f16 MMAs, 2x the TF32 rate; +dims*2 B/row)
@@ -705,7 +706,13 @@ static bool batch_tensor_eligible(const wax_vs_engine *e, uint32_t n_queries, ui
     return e->tune.batch_tensor && n_queries >= min_batch &&
            (e->similarity == WAX_VS_COSINE || e->similarity == WAX_VS_DOT) && e->dims % kBatchKBlock == 0 &&
            e->dims <= 8192 &&        // the proof's accumulation slack (dims * 2^-23) stays far below the operand bound
-           k_eff >= 1 && k_eff <= 128 && e->n_rows >= 1;
+           k_eff >= 1 && e->n_rows >= 1 &&
+           // 128 < k <= 1024 (the production candidate limit reaches 1 000, UnifiedSearch.swift:1195-1200): real batches
+           // only.  Level 1 can rarely PROVE such a k (64 nominees per slice barely cover it) but its exactly re-scored
+           // nominees give the filter level its threshold, and that level is complete by construction.
+           (k_eff <= 128 || (k_eff <= static_cast<uint32_t>(kBatchRescoreMax) && e->tune.batch_large_k &&
+                             n_queries >= static_cast<uint32_t>(std::max(e->tune.batch_min, 4)) &&
+                             e->n_rows >= 64ull * k_eff));   // smaller corpora: too few row slices to nominate k rows
 }
 
 // 1/|v| per row + max |v|, cached per corpus version.  Appends only extend the cache (rows [norms_rows, n_rows) are
@@ -828,7 +835,10 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         bf16 = e->shadow_valid;
     }
     if (used_bf16) *used_bf16 = bf16;
-    const uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
+    // k > 128: the union of the slices' 64-entry heaps must hold k nominees with some room (slices >= 1.15 k / 64), so
+    // fewer query groups share the SMs and a large batch is split into several launches
+    uint32_t max_groups = static_cast<uint32_t>(e->sm_count);
+    if (k_eff > 128u) max_groups = std::max<uint32_t>(1u, max_groups / ((k_eff * 115u / 100u + 63u) / 64u));
     cudaError_t attr_err = cudaSuccess;
     {   // per function and per DEVICE: once per engine
         std::lock_guard<std::mutex> ag(e->attr_mu);
@@ -877,6 +887,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
     uint32_t rescore = static_cast<uint32_t>(kBatchRescore);
     if (e->tune.batch_rescore > 0) rescore = static_cast<uint32_t>(e->tune.batch_rescore);
     else if (bf16) rescore = k_eff <= 16 ? 256u : (k_eff <= 48 ? 512u : 1024u);
+    if (k_eff > 128u) rescore = static_cast<uint32_t>(kBatchRescoreMax);   // the finish kernel writes k re-scored nominees
     rescore = rescore <= 256u ? 256u : (rescore <= 512u ? 512u : static_cast<uint32_t>(kBatchRescoreMax));
 
     for (uint32_t q0 = 0; q0 < n_queries; q0 += max_groups * kBatchM) {
@@ -1648,7 +1659,7 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         CUDA_TRY(cudaStreamSynchronize(c->stream));
         std::vector<uint32_t> unproven;
         for (uint32_t qi = 0; qi < n_queries; ++qi) if (!c->h_ok[qi]) unproven.push_back(qi);
-        if (used_bf16 && unproven.size() * 4 > n_queries) {
+        if (used_bf16 && k_eff <= 128u && unproven.size() * 4 > n_queries) {   // (large k is expected to need the filter level)
             std::lock_guard<std::mutex> pg(e->pool_mu);
             e->bf16_skip_batches = 16;
         }
@@ -2716,6 +2727,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_min")) e->tune.batch_min = v;
     else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;
     else if (!strcmp(key, "batch_heap")) e->tune.batch_heap = v;
+    else if (!strcmp(key, "batch_large_k")) e->tune.batch_large_k = v;
     else if (!strcmp(key, "batch_pair")) e->tune.batch_pair = v;
     else if (!strcmp(key, "batch_ts")) e->tune.batch_ts = v;
     else if (!strcmp(key, "batch_bf16")) { e->tune.batch_bf16 = v; e->shadow_unavailable = false; e->bf16_skip_batches = 0; }
