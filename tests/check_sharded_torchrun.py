@@ -64,6 +64,19 @@ same = same and len(big) == 200 and [b[0] for b in big[:128]] == exp[0, :128, 0]
 ok = ok and same
 if rank == 0:
     print(f"all-gather transport (k=10 and k=200) agrees with the fused exchange: {'OK' if same else 'MISMATCH'}", flush=True)
+# filtered collective search (wax_vs_shard_search_filtered): with the oracle's complete top-128 in hand, denying its first
+# five rows must return rows 5..14, and an allow-list of four of its rows exactly those four, in order
+if eng.transport == "p2p-fused":
+    def bits_of(got):
+        return [g[0] for g in got], [int(np.float32(g[1]).view(np.uint32)) for g in got]
+    got = eng.search_filtered(qs[0], 10, deny=exp[0, :5, 0].astype(np.uint64))
+    same = bits_of(got) == (exp[0, 5:15, 0].tolist(), exp[0, 5:15, 1].tolist())
+    pick = [3, 40, 100, 127]
+    got = eng.search_filtered(qs[0], 10, allow=exp[0, pick, 0].astype(np.uint64))
+    same = same and bits_of(got) == (exp[0, pick, 0].tolist(), exp[0, pick, 1].tolist())
+    ok = ok and same
+    if rank == 0:
+        print(f"filtered collective search (deny the top-5 / allow four rows): {'OK' if same else 'MISMATCH'}", flush=True)
 # many collective searches back to back on one stream (mailbox slot reuse under real NVLink latency)
 ms, launches = eng.time_search(10, 40, warmup=5, n_queries=8, seed=778)
 after = eng.search(qs[0], 10)

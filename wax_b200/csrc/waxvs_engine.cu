@@ -406,7 +406,7 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg, int mode = 0
     int C = 0;
     if (d % 128u == 0) {
         const int c = static_cast<int>(d / 128u);
-        if (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8) C = c;   // unrolled shapes
+        if (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8 || c == 12) C = c;   // unrolled shapes (12: the 1536-dim embeddings)
     }
     if (C == 0 && d < 128) return false;                 // short rows: the direct-load kernel is faster (dims sweep)
     // rows per step / warps per CTA by row length (profiles/dims_sweep_r01_call17.json): keep a step at >= 4-12 KB
@@ -414,6 +414,8 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg, int mode = 0
     int R, warps_default = 8;
     if (C == 0) {                                        // generic shape: run-time chunk count, query in shared memory
         R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d >= 2048 ? 1 : 2);
+    } else if (C == 12) {
+        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : 2;
     } else if (C >= 6) {
         R = e->tune.rows_per_step == 2 || e->tune.rows_per_step == 4 ? e->tune.rows_per_step : 2;
     } else {
@@ -480,6 +482,7 @@ static cudaError_t launch_tma(wax_vs_engine *e, const ScanParams &p, int grid, c
     WAXVS_CASE(1, 4); WAXVS_CASE(1, 8); WAXVS_CASE(2, 4); WAXVS_CASE(2, 8);
     WAXVS_CASE(3, 4); WAXVS_CASE(3, 8); WAXVS_CASE(4, 4); WAXVS_CASE(4, 8);
     WAXVS_CASE(6, 2); WAXVS_CASE(6, 4); WAXVS_CASE(8, 2); WAXVS_CASE(8, 4);
+    WAXVS_CASE(12, 1); WAXVS_CASE(12, 2);
     WAXVS_CASE(0, 1); WAXVS_CASE(0, 2);
 #undef WAXVS_CASE
     return cudaErrorInvalidValue;
