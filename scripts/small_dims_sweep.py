@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Single-query scan at the row lengths where round 1's dims sweep was below the HBM roofline (64, 128, 256, 1000, 1536):
-launch-shape options per dims.  ~8 GB corpus each, CUDA-event time inside the library, one JSON line per (dims, options)."""
+"""Single-query scan across row lengths (round 1's dims sweep was below the HBM roofline at 64 ... 256, 1000, 1536, 2048+):
+the shipped launch shape and the direct-load kernel (variant 2) per dims.  ~8 GB corpus each, CUDA-event time inside the library, one JSON line per (dims, options)."""
 import json
 import sys
 from pathlib import Path
@@ -10,15 +10,8 @@ sys.path.insert(0, str(ROOT))
 from wax_b200 import CUDAVectorEngine, VectorMetric  # noqa: E402
 
 only = [int(a) for a in sys.argv[1:]]
-CASES = {
-    64: [{"variant": 2}, {"variant": 2, "ldg_ctas_per_sm": 8}],
-    128: [{}, {"stages": 3}, {"stages": 4}, {"warps": 8}, {"warps": 8, "stages": 4}, {"rows_per_step": 4}, {"rows_per_step": 4, "stages": 4},
-          {"chunk_steps": 32}, {"chunk_steps": 0}, {"variant": 2}, {"variant": 2, "ldg_ctas_per_sm": 8}],
-    256: [{}, {"stages": 3}, {"warps": 16}, {"warps": 8}, {"rows_per_step": 4}, {"chunk_steps": 32}],
-    1000: [{}, {"stages": 3}, {"rows_per_step": 1}, {"variant": 2}],
-    1536: [{}, {"rows_per_step": 1}, {"stages": 3}, {"rows_per_step": 1, "stages": 3}, {"variant": 2}],
-    768: [{}], 384: [{}], 1024: [{}], 3072: [{}],
-}
+CASES = {d: [{}, {"variant": 2}] for d in (32, 64, 96, 100, 128, 160, 256, 300, 384, 400, 512, 640, 768, 1000, 1024, 1280, 1536, 2048, 2560,
+                                           3072, 3584, 4096, 6144, 8192)}
 for dims, cases in CASES.items():
     if only and dims not in only:
         continue

@@ -408,12 +408,23 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg, int mode = 0
         const int c = static_cast<int>(d / 128u);
         if (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8 || c == 12) C = c;   // unrolled shapes (12: the 1536-dim embeddings)
     }
-    if (C == 0 && d < 128) return false;                 // short rows: the direct-load kernel is faster (dims sweep)
+    if (C == 0 && d < 32) return false;                  // a few floats per row: the direct-load kernel
+    if (C == 0 && d > 3072) return false;                // very long rows: too few warps fit beside two stages; the
+                                                         // direct-load kernel streams them at 6.7-6.8 TB/s (sweep_big_r02j)
     // rows per step / warps per CTA by row length (profiles/dims_sweep_r01_call17.json): keep a step at >= 4-12 KB
     // and give short rows more warps (their bound is per-row instruction latency, not bytes in flight)
     int R, warps_default = 8;
     if (C == 0) {                                        // generic shape: run-time chunk count, query in shared memory
-        R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : (d >= 2048 ? 1 : 2);
+        // keep a step at >= 2-8 KB: short generic rows (dims < 128, 160, 300, 400, ...) take 8 or 4 rows per step and
+        // more warps, like the unrolled C <= 2 shapes (profiles/small_dims_sweep_r02*.jsonl)
+        // (long rows: as many rows as keep a step at <= 32 KB -- the few warps that then fit still hold ~190 KB in flight,
+        // profiles/small_dims_sweep_r02h.jsonl / sweep_big_r02i.jsonl: 1000 dims 6.1 -> 7.3 TB/s, 2048 dims 6.5 -> 7.3)
+        int auto_r = d > 256 ? 4 : 8;
+        if (d > 640) { auto_r = 8; while (auto_r > 1 && static_cast<size_t>(auto_r) * d * 4 > 32768) auto_r >>= 1; }
+        const int want_r = e->tune.rows_per_step;
+        R = (want_r == 1 || want_r == 2 || want_r == 4 || want_r == 8) ? want_r : auto_r;
+        if (R == 8) warps_default = 16;
+        else if (R == 4) warps_default = 12;
     } else if (C == 12) {
         R = e->tune.rows_per_step == 1 || e->tune.rows_per_step == 2 ? e->tune.rows_per_step : 2;
     } else if (C >= 6) {
@@ -483,7 +494,7 @@ static cudaError_t launch_tma(wax_vs_engine *e, const ScanParams &p, int grid, c
     WAXVS_CASE(3, 4); WAXVS_CASE(3, 8); WAXVS_CASE(4, 4); WAXVS_CASE(4, 8);
     WAXVS_CASE(6, 2); WAXVS_CASE(6, 4); WAXVS_CASE(8, 2); WAXVS_CASE(8, 4);
     WAXVS_CASE(12, 1); WAXVS_CASE(12, 2);
-    WAXVS_CASE(0, 1); WAXVS_CASE(0, 2);
+    WAXVS_CASE(0, 1); WAXVS_CASE(0, 2); WAXVS_CASE(0, 4); WAXVS_CASE(0, 8);
 #undef WAXVS_CASE
     return cudaErrorInvalidValue;
 }

@@ -415,6 +415,43 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
         const float4 *tile = reinterpret_cast<const float4 *>(ring + s * STAGE_BYTES);
 
         float sum0[R], sum1[R];
+        if (C == 0 && R >= 2) {
+            // Generic rows (dims < 128 or not one of the unrolled multiples of 128), several rows per step: chunk-outer /
+            // row-inner, so a query chunk is read from shared memory once for the R rows (the row-outer form read it per row:
+            // twice the shared-memory traffic, 5.6 instead of 7.3 TB/s at 2560 dims).  Each row still sees its chunks in ascending
+            // order on its own accumulators: the same operations in the same order as the row-outer loop below.
+            float a[R][4], b[R][4];
+#pragma unroll
+            for (int r = 0; r < R; ++r)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { a[r][j] = 0.f; b[r][j] = 0.f; }
+            for (int c = 0; c < CN; ++c) {
+                if (lane + 32 * c >= D4) break;
+                const float4 qc = qchunk(c);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    const float4 v = tile[r * D4 + lane + 32 * c];
+                    if (METRIC == kL2) {
+                        const float dx = __fsub_rn(qc.x, v.x), dy = __fsub_rn(qc.y, v.y);
+                        const float dz = __fsub_rn(qc.z, v.z), dw = __fsub_rn(qc.w, v.w);
+                        a[r][0] = __fmaf_rn(dx, dx, a[r][0]); a[r][1] = __fmaf_rn(dy, dy, a[r][1]);
+                        a[r][2] = __fmaf_rn(dz, dz, a[r][2]); a[r][3] = __fmaf_rn(dw, dw, a[r][3]);
+                    } else {
+                        a[r][0] = __fmaf_rn(qc.x, v.x, a[r][0]); a[r][1] = __fmaf_rn(qc.y, v.y, a[r][1]);
+                        a[r][2] = __fmaf_rn(qc.z, v.z, a[r][2]); a[r][3] = __fmaf_rn(qc.w, v.w, a[r][3]);
+                        if (METRIC == kCosine) {
+                            b[r][0] = __fmaf_rn(v.x, v.x, b[r][0]); b[r][1] = __fmaf_rn(v.y, v.y, b[r][1]);
+                            b[r][2] = __fmaf_rn(v.z, v.z, b[r][2]); b[r][3] = __fmaf_rn(v.w, v.w, b[r][3]);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                sum0[r] = __fadd_rn(__fadd_rn(a[r][0], a[r][1]), __fadd_rn(a[r][2], a[r][3]));
+                sum1[r] = __fadd_rn(__fadd_rn(b[r][0], b[r][1]), __fadd_rn(b[r][2], b[r][3]));
+            }
+        } else
 #pragma unroll
         for (int r = 0; r < R; ++r) {
             float a0 = 0.f, a1 = 0.f, a2_ = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
