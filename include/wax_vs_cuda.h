@@ -206,6 +206,13 @@ int32_t wax_vs_shard_close(wax_vs_engine *engine);
    wax_vs_search); blocks until the merged result is in the caller's buffers.  out_cap >= clamp(top_k). */
 int32_t wax_vs_shard_search(wax_vs_engine *engine, const float *query, uint32_t query_len, int64_t top_k,
                             uint64_t *out_ids, float *out_scores, uint32_t out_cap, uint32_t *out_n);
+/* Device-side merge for the sharded search_batch: d_gathered = [world][n_queries][k] candidates exactly as an
+   all-gather of the ranks' wax_vs_search_batch_device outputs leaves them (rank-major; every per-query list sorted, padding
+   valid = 0 last); d_out = [n_queries][k_out] (k_out <= k), the k_out best of each query under (distance, GLOBAL row)
+   -- ranks must be ordered by ascending row ranges.  Enqueued on cuda_stream, no synchronisation. */
+int32_t wax_vs_merge_candidates_device(wax_vs_engine *engine, const wax_vs_candidate *d_gathered, uint32_t world,
+                                       uint32_t n_queries, uint32_t k, uint32_t k_out, wax_vs_candidate *d_out,
+                                       void *cuda_stream);
 /* wax_vs_search_filtered over the whole sharded corpus: every rank passes the SAME frame_ids / mode; a rank resolves
    the ids its own shard holds (the rest are unknown to it and ignored), its fused scan applies the row filter below
    the top-k and the in-kernel exchange merges the ranks' lists.  Still one launch per query per rank. */

@@ -15,6 +15,7 @@
 #   launches   ncu launch list of bench.py         ncu-scan   ncu --set full of the fused scan kernel
 #   ncu-batch  ncu --set full of the batched nominate + finish kernels (configs[2] and [4] shapes)
 #   sharded:N  torchrun -N tests/check_sharded_torchrun.py + bench.py --gpus N      (needs gpurun --gpus N)
+#   parity:N   torchrun -N tests/check_sharded_torchrun.py only      batch-sharded:N  scripts/bench_batch_sharded.py (2 and 1 batches in flight)
 #   c4         torchrun -8 tests/check_sharded_torchrun.py 100000000 light          (needs gpurun --gpus 8)
 #   ncu-batch-c5 / ncu-batch-c3  ncu --set full of the nominate + finish kernels of configs[4] / configs[2] (NCU_OPTS="batch_pair=1" ...)
 #   power      clocks + power draw sampled while the batched configs run (is the tensor path power-capped?)
@@ -69,6 +70,10 @@ for step in "$@"; do
     sharded:*) N=${step#sharded:}
            timeout 900 $TR --nproc-per-node $N tests/check_sharded_torchrun.py > $OUT/sharded_parity_${TAG}_n$N.txt 2>&1; tail -12 $OUT/sharded_parity_${TAG}_n$N.txt
            timeout 900 $TR --nproc-per-node $N bench.py --gpus $N 2> $OUT/bench_${TAG}_n$N.err | tail -1 > $OUT/bench_${TAG}_n$N.json; cut -c1-700 $OUT/bench_${TAG}_n$N.json; tail -3 $OUT/bench_${TAG}_n$N.err ;;
+    parity:*) N=${step#parity:}
+           timeout 900 $TR --nproc-per-node $N tests/check_sharded_torchrun.py > $OUT/sharded_parity_${TAG}_n$N.txt 2>&1; tail -14 $OUT/sharded_parity_${TAG}_n$N.txt ;;
+    batch-sharded:*) N=${step#batch-sharded:}
+           for depth in 2 1; do timeout 600 $TR --nproc-per-node $N scripts/bench_batch_sharded.py 20 $depth 2> $OUT/bench_batch_sharded_${TAG}_n${N}_d$depth.err | tail -1 | tee $OUT/bench_batch_sharded_${TAG}_n${N}_d$depth.json | cut -c1-400; tail -2 $OUT/bench_batch_sharded_${TAG}_n${N}_d$depth.err; done ;;
     c4) timeout 1200 $TR --nproc-per-node 8 tests/check_sharded_torchrun.py 100000000 light > $OUT/sharded_parity_${TAG}_c4_100m_n8.txt 2>&1; tail -12 $OUT/sharded_parity_${TAG}_c4_100m_n8.txt ;;
     sass) cuobjdump -sass wax_b200/libwaxvs_cuda.so | python scripts/sass_histogram.py > $OUT/sass_opcodes_$TAG.txt; head -40 $OUT/sass_opcodes_$TAG.txt ;;
     *) echo "unknown step $step" ;;

@@ -202,3 +202,42 @@ def test_sharded_filtered_search_equals_the_single_engine_filtered_search(oracle
     finally:
         grp.close()
         single.close()
+
+
+def test_device_merge_of_gathered_lists_equals_the_host_merge():
+    """wax_vs_merge_candidates_device (the sharded search_batch's merge kernel) against the numpy merge it replaces:
+    random sorted per-rank lists with exact distance ties inside and across ranks, padding (valid = 0) at the tails,
+    ranks owning ascending row ranges -- identical records in identical order, every k_out."""
+    import ctypes as C
+    import torch
+    from wax_b200 import _lib as L
+    rng = np.random.default_rng(77)
+    eng = CUDAVectorEngine(VectorMetric.cosine, 8)
+    try:
+        for world, b, k in [(8, 300, 10), (2, 17, 128), (16, 5, 72), (1, 9, 10), (3, 40, 1)]:
+            cands = np.zeros((world, b, k), sharded.CAND_DTYPE)
+            for r in range(world):
+                for q in range(b):
+                    n_valid = int(rng.integers(0, k + 1)) if rng.random() < 0.3 else k
+                    d = np.round(rng.random(n_valid).astype(np.float32), 2)               # coarse: many exact ties
+                    rows = rng.choice(1000, n_valid, replace=False).astype(np.uint64) + np.uint64(r * 1000)
+                    order = np.lexsort((rows, d))
+                    cands[r, q, :n_valid]["distance"] = d[order]
+                    cands[r, q, :n_valid]["row"] = rows[order]
+                    cands[r, q, :n_valid]["frame_id"] = rows[order] * np.uint64(3)
+                    cands[r, q, :n_valid]["valid"] = 1
+            dev = torch.from_numpy(cands.view(np.uint8).reshape(-1).copy()).cuda()
+            for k_out in sorted({k, max(1, k // 2), 1}):
+                out = torch.zeros(b * k_out * 24, dtype=torch.uint8, device="cuda")
+                rc = L.lib().wax_vs_merge_candidates_device(eng.handle, C.c_void_p(dev.data_ptr()), world, b, k, k_out,
+                                                            C.c_void_p(out.data_ptr()), None)
+                assert rc == 0, L.last_error()
+                torch.cuda.synchronize()
+                got = out.cpu().numpy().view(sharded.CAND_DTYPE).reshape(b, k_out)
+                want, n_valid = sharded.merge_candidates_batch(cands, k_out)
+                for q in range(b):
+                    m = int(n_valid[q])
+                    assert np.array_equal(got[q, :m], want[q, :m]), (world, b, k, k_out, q)
+                    assert not got[q, m:]["valid"].any()
+    finally:
+        eng.close()

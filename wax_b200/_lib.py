@@ -55,6 +55,8 @@ SIGNATURES = {
                                          C.c_void_p]),
     "wax_vs_search_batch_device": (C.c_int32, [_eng, C.c_void_p, C.c_uint32, C.c_int64, C.c_uint64, C.c_void_p,
                                                C.c_void_p]),
+    "wax_vs_merge_candidates_device": (C.c_int32, [_eng, C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.c_void_p, C.c_void_p]),
     "wax_vs_shard_open": (C.c_int32, [_eng, C.c_int32, C.c_int32, C.c_uint64, _u8p]),
     "wax_vs_shard_connect": (C.c_int32, [_eng, _u8p, C.c_int32]),
     "wax_vs_shard_close": (C.c_int32, [_eng]),

@@ -2163,6 +2163,22 @@ int32_t wax_vs_debug_time_shard_search(wax_vs_engine *e, uint32_t n_queries, int
     return WAX_VS_OK;
 }
 
+// Device-side merge of all-gathered per-rank candidate lists (the sharded search_batch): stateless, enqueued on the
+// caller's stream, no synchronisation.
+int32_t wax_vs_merge_candidates_device(wax_vs_engine *e, const wax_vs_candidate *d_gathered, uint32_t world,
+                                       uint32_t n_queries, uint32_t k, uint32_t k_out, wax_vs_candidate *d_out,
+                                       void *cuda_stream) {
+    if (!e || !d_gathered || !d_out) return fail(WAX_VS_ERR_NULL, "NULL argument");
+    if (world == 0 || world > 1024u || k == 0 || k_out == 0 || k_out > k)
+        return fail(WAX_VS_ERR_ARGUMENT, "merge: world %u, k %u, k_out %u", world, k, k_out);
+    if (n_queries == 0) return WAX_VS_OK;
+    DeviceGuard g(e->device);
+    if (!g.ok) return fail(WAX_VS_ERR_CUDA, "failed to select CUDA device %d", e->device);
+    merge_gathered_kernel<<<n_queries, 128, 0, static_cast<cudaStream_t>(cuda_stream)>>>(d_gathered, world, n_queries, k, k_out, d_out);
+    CUDA_TRY(cudaGetLastError());
+    return WAX_VS_OK;
+}
+
 // ---- filtered search -------------------------------------------------------------------
 // The reference filters AFTER the engine call and over-fetches 3 x topK to compensate (UnifiedSearch.swift:58,
 // 371-442, 1195-1200, 1241-1258).  Here the filter is pushed below the top-k: a row bitset consulted only for rows

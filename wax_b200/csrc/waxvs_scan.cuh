@@ -579,9 +579,11 @@ __global__ void __launch_bounds__(256, 4) scan_ldg_kernel(const __grid_constant_
         if (vec4) {
             const float4 *v4 = reinterpret_cast<const float4 *>(v);
             const float4 *q4 = reinterpret_cast<const float4 *>(p.query);
-#pragma unroll 4
+            // the row is read once: streaming loads (evict-first, no L1 residency) leave L1 to the query, which every row
+            // re-reads; eight 16-byte loads in flight per lane
+#pragma unroll 8
             for (uint32_t c = lane; c < d4; c += 32u) {
-                const float4 x = __ldg(v4 + c);
+                const float4 x = __ldcs(v4 + c);
                 const float4 y = __ldg(q4 + c);
                 acc(y.x, x.x, a0, b0); acc(y.y, x.y, a1, b1); acc(y.z, x.z, a2_, b2); acc(y.w, x.w, a3, b3);
             }

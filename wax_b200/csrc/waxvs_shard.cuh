@@ -152,4 +152,39 @@ __global__ void __launch_bounds__(256) shard_exchange_kernel(const ShardParams s
     shard_exchange_cta(sh, local, k, skeys);
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// Batched form of the same merge (sharded search_batch): `gathered` = [world][n_queries][k] candidates as an all-gather
+// of the ranks' per-query lists leaves them (every list sorted, padding valid = 0 last); out = [n_queries][k_out], the
+// k_out best of each query under (distance, GLOBAL row) -- the position rule of shard_exchange_cta, binary searches in
+// global memory.  One CTA per query.  Replaces the host-side numpy merge (7.6 ms per 1024 x 8 x 10 batch, ten times the
+// shard's tensor-core pass at 8 GPUs).
+__device__ __forceinline__ uint32_t cand_dist_key(const wax_vs_candidate &c) {
+    return c.valid ? orderable_u32(c.distance) : WAXVS_UKEY_NONE;
+}
+__global__ void __launch_bounds__(128) merge_gathered_kernel(const wax_vs_candidate *__restrict__ gathered, uint32_t world,
+                                                             uint32_t n_queries, uint32_t k, uint32_t k_out,
+                                                             wax_vs_candidate *__restrict__ out) {
+    const uint32_t q = blockIdx.x;
+    const size_t rank_stride = static_cast<size_t>(n_queries) * k;
+    const wax_vs_candidate *mine = gathered + static_cast<size_t>(q) * k;           // rank 0's list of this query
+    for (uint32_t t = threadIdx.x; t < world * k; t += blockDim.x) {
+        const uint32_t r = t / k, j = t % k;
+        const wax_vs_candidate c = mine[r * rank_stride + j];
+        const uint32_t key = cand_dist_key(c);
+        uint32_t pos = j;
+        for (uint32_t o = 0; o < world; ++o) {
+            if (o == r) continue;
+            const wax_vs_candidate *lst = mine + o * rank_stride;
+            uint32_t lo = 0, hi = k;                 // lower ranks: entries <= key come first; higher ranks: entries < key
+            while (lo < hi) {
+                const uint32_t mid = (lo + hi) >> 1;
+                const uint32_t km = cand_dist_key(lst[mid]);
+                if (o < r ? km <= key : km < key) lo = mid + 1; else hi = mid;
+            }
+            pos += lo;
+        }
+        if (pos < k_out) out[static_cast<size_t>(q) * k_out + pos] = c;
+    }
+}
+
 }  // namespace waxvs

@@ -274,11 +274,27 @@ class ShardedVectorEngine:
             out.append([(int(best["frame_id"][j]), float(scores[j])) for j in range(best.size)])
         return out
 
+    def _merge_on_device(self, gathered, b: int, k: int, k_eff: int, stream):
+        """[world][b][k] gathered candidates (device bytes) -> [b][k_eff] merged candidates on the device, by the library's
+        merge kernel (same (distance, GLOBAL row) rule as the fused exchange); enqueued on `stream`."""
+        from . import _lib as L
+        merged = self._torch.empty(b * k_eff * 24, dtype=self._torch.uint8, device=self.device)
+        rc = L.lib().wax_vs_merge_candidates_device(self.engine.handle, C.c_void_p(gathered.data_ptr()), self.world_size, b, k,
+                                                    k_eff, C.c_void_p(merged.data_ptr()), C.c_void_p(stream.cuda_stream))
+        if rc != 0:
+            raise RuntimeError(f"wax_vs_merge_candidates_device rc={rc}: {L.last_error()}")
+        return merged
+
+    def _unpack_merged(self, host_bytes: np.ndarray, b: int, k_eff: int):
+        best = host_bytes.view(CAND_DTYPE).reshape(b, k_eff)
+        scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
+        return best["frame_id"].astype(np.uint64), scores, (best["valid"] != 0).sum(axis=1).astype(np.uint32)
+
     def search_batch_arrays(self, queries, top_k: int):
         """A batch of independent queries against the sharded corpus: every rank runs the batched tensor-core levels
         (wax_vs_search_batch_device: bf16-shadow nominations -> TF32 retry -> exact scan, results identical to
-        single-query scans) on its shard, ONE all-gather carries batch x k candidates per rank, one vectorised host
-        merge.  `queries`: [batch, dims] host array or device tensor (identical on every rank).  Returns
+        single-query scans) on its shard, ONE all-gather carries batch x k candidates per rank, ONE merge kernel
+        (wax_vs_merge_candidates_device) ranks them on the device.  `queries`: [batch, dims] host array or device tensor (identical on every rank).  Returns
         (ids [batch, k_eff] uint64, scores [batch, k_eff] float32, n_valid [batch] uint32)."""
         torch, dist = self._torch, self._dist
         k = clamp_topk(top_k)
@@ -310,6 +326,9 @@ class ShardedVectorEngine:
             dist.all_gather_into_tensor(gathered, local, group=self.group)
         else:
             gathered = local
+        if self._local_search is None:      # GPU: merge on the device, one D2H of the final batch x k_eff records
+            merged = self._merge_on_device(gathered, b, k, k_eff, torch.cuda.current_stream(self.device))
+            return self._unpack_merged(merged.cpu().numpy(), b, k_eff)
         cands = gathered.cpu().numpy().view(CAND_DTYPE).reshape(self.world_size, b, k)
         best, n_valid = merge_candidates_batch(cands, k_eff)
         scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
@@ -369,11 +388,13 @@ class ShardedVectorEngine:
                     dist.all_gather_into_tensor(gathered, local, group=self.group)
                 else:
                     gathered = local
-                host = torch.empty(gathered.numel(), dtype=torch.uint8, pin_memory=True)
-                host.copy_(gathered, non_blocking=True)
+                k_eff = min(k, self.total_rows) if self.total_rows else k
+                merged = self._merge_on_device(gathered, b, k, k_eff, self._batch_stream) if b and self.total_rows else gathered
+                host = torch.empty(merged.numel(), dtype=torch.uint8, pin_memory=True)
+                host.copy_(merged, non_blocking=True)
                 done = torch.cuda.Event()
                 done.record()
-            return host, done, gathered, d_qs            # keep the device buffers alive until the copy has finished
+            return host, done, (gathered, merged), d_qs  # keep the device buffers alive until the copy has finished
 
         return (self._worker.submit(work), b, k)
 
@@ -386,6 +407,8 @@ class ShardedVectorEngine:
         k_eff = min(k, self.total_rows) if self.total_rows else k
         if b == 0 or self.total_rows == 0:
             return np.zeros((b, 0), np.uint64), np.zeros((b, 0), np.float32), np.zeros(b, np.uint32)
+        if self._local_search is None:      # GPU: the worker already merged on the device
+            return self._unpack_merged(host.numpy(), b, k_eff)
         cands = host.numpy().view(CAND_DTYPE).reshape(self.world_size, b, k)
         best, n_valid = merge_candidates_batch(cands, k_eff)
         scores = score_from_distance(self.metric.to_vec_similarity(), best["distance"])
