@@ -122,6 +122,34 @@ def test_config2_full_size_batch_1024_top10_cosine(oracle, full_engine, c3_queri
                        [ids[i] for i in four], [scores[i] for i in four])
 
 
+def test_full_size_filtered_batch_and_large_k_batch_against_the_oracle_top100(oracle, full_engine, c3_queries, c3_oracle_top100):
+    """At 10 M x 384, against the oracle's COMPLETE top-100 of the sampled queries: (1) one deny-list for the whole
+    1024-query batch (the five best rows of every sampled query): the filtered batch must return, for each sampled query,
+    exactly the oracle list with the denied rows struck out -- ids and score bits; (2) a batch with k = 200 (tensor levels:
+    nominee threshold + filter level) must carry the oracle's top-100 as its first hundred rows."""
+    sample, rows, s = c3_oracle_top100
+    deny = np.unique(np.concatenate([rows[j][:5] for j in range(len(sample))])).astype(np.uint64)   # implicit ids = rows
+    denied = set(deny.tolist())
+    t0, f0 = full_engine.batch_stats()
+    got = full_engine.search_batch_filtered(c3_queries, 10, deny=deny)
+    t1, f1 = full_engine.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == 1024 and f1 - f0 <= 10
+    for j, qi in enumerate(sample):
+        keep = [i for i in range(100) if int(rows[j][i]) not in denied][:10]
+        assert [g[0] for g in got[qi]] == [int(rows[j][i]) for i in keep], qi
+        assert np.array_equal(np.float32([g[1] for g in got[qi]]).view(np.uint32), s[j][keep].view(np.uint32)), qi
+    qs = c3_queries[sample]
+    t0, f0 = full_engine.batch_stats()
+    ids, scores, ns = full_engine.search_batch_arrays(qs, 200)
+    t1, f1 = full_engine.batch_stats()
+    assert (t1 - t0) + (f1 - f0) == len(sample) and f1 - f0 <= 1, "the k = 200 batch did not take the tensor levels"
+    assert ns.tolist() == [200] * len(sample)
+    for j in range(len(sample)):
+        assert ids[j][:100].tolist() == rows[j].tolist(), j
+        assert np.array_equal(scores[j][:100].view(np.uint32), s[j].view(np.uint32)), j
+        assert np.all(scores[j][:-1] >= scores[j][1:])
+
+
 def test_config4_full_size_10m_x_768_batch_256_top100_dot(oracle):
     """BASELINE configs[4] at its stated size: 10 M x 768 fp32 rows that are NOT normalised, batch 256, top-100 under
     the dot metric (USearch ip: d = 1 - q.v, score = q.v - 1, VectorMetric.swift:21-43).  Same three checks."""
