@@ -15,6 +15,7 @@
 #   launches   ncu launch list of bench.py         ncu-scan   ncu --set full of the fused scan kernel
 #   ncu-batch  ncu --set full of the batched nominate + finish kernels (configs[2] and [4] shapes)
 #   sharded:N  torchrun -N tests/check_sharded_torchrun.py + bench.py --gpus N      (needs gpurun --gpus N)
+#   sanitize   compute-sanitizer memcheck over scripts/sanitize_probe.py      ncu-dims  ncu --set full of the scan at 1000 / 1536 dims
 #   parity:N   torchrun -N tests/check_sharded_torchrun.py only      batch-sharded:N  scripts/bench_batch_sharded.py (2 and 1 batches in flight)
 #   c4         torchrun -8 tests/check_sharded_torchrun.py 100000000 light          (needs gpurun --gpus 8)
 #   ncu-batch-c5 / ncu-batch-c3  ncu --set full of the nominate + finish kernels of configs[4] / configs[2] (NCU_OPTS="batch_pair=1" ...)
@@ -70,6 +71,11 @@ for step in "$@"; do
     sharded:*) N=${step#sharded:}
            timeout 900 $TR --nproc-per-node $N tests/check_sharded_torchrun.py > $OUT/sharded_parity_${TAG}_n$N.txt 2>&1; tail -12 $OUT/sharded_parity_${TAG}_n$N.txt
            timeout 900 $TR --nproc-per-node $N bench.py --gpus $N 2> $OUT/bench_${TAG}_n$N.err | tail -1 > $OUT/bench_${TAG}_n$N.json; cut -c1-700 $OUT/bench_${TAG}_n$N.json; tail -3 $OUT/bench_${TAG}_n$N.err ;;
+    sanitize) timeout 1500 compute-sanitizer --tool memcheck --error-exitcode 9 python scripts/sanitize_probe.py > $OUT/sanitizer_memcheck_$TAG.txt 2>&1; echo "rc=$?" >> $OUT/sanitizer_memcheck_$TAG.txt; tail -8 $OUT/sanitizer_memcheck_$TAG.txt ;;
+    ncu-dims) for d in 1000 1536; do
+             timeout 600 ncu --set full --clock-control none --import-source on -k regex:scan_tma -s 4 -c 1 -o $OUT/ncu_scan_d${d}_$TAG -f python scripts/small_dims_sweep.py $d > $OUT/ncu_scan_d${d}_$TAG.log 2>&1
+             ncu -i $OUT/ncu_scan_d${d}_$TAG.ncu-rep --page raw --csv 2>/dev/null | python scripts/ncu_summary.py > $OUT/ncu_scan_d${d}_${TAG}_summary.csv; cut -c1-330 $OUT/ncu_scan_d${d}_${TAG}_summary.csv | tail -1
+             rm -f $OUT/ncu_scan_d${d}_$TAG.ncu-rep; done ;;   # the reports are ~30 MB each: only the summaries travel back
     parity:*) N=${step#parity:}
            timeout 900 $TR --nproc-per-node $N tests/check_sharded_torchrun.py > $OUT/sharded_parity_${TAG}_n$N.txt 2>&1; tail -14 $OUT/sharded_parity_${TAG}_n$N.txt ;;
     batch-sharded:*) N=${step#batch-sharded:}
