@@ -400,3 +400,36 @@ def test_large_k_batches_take_the_tensor_levels(oracle, metric, dims, n, b, k):
     t2, f2 = eng.batch_stats()
     assert eng.search_batch(qs[:5], k) == got[:5]
     assert eng.batch_stats() == (t2, f2)
+
+
+def test_nominee_heap_size_follows_k_and_adapts_to_unproven_queries(oracle):
+    """The bf16 level-1 shape: the nominee heap per (slice, query) is sized from k and the slice count (expected cost of a
+    batch = shape time + P(an unproven query) x one more pass), and the data overrules the model -- a batch that leaves
+    queries unproven bumps the next batches one size up.  Results never depend on the choice."""
+    dims, n = 384, 120_000
+    eng = _engine(oracle, VectorMetric.cosine, n, dims, seed=1500)
+    qs = oracle.synth_rows(1501, 0, 1024, dims, normalize=True)
+    want = {k: _single(eng, qs[:3], k) for k in (10, 72)}
+    heaps = {}
+    for k in (10, 72, 128):
+        got = eng.search_batch(qs, k)
+        heaps[k] = eng.counter("batch_last_heap")
+        if k in want:
+            assert got[:3] == want[k]
+    assert heaps[10] == 16 and heaps[72] in (24, 32) and heaps[128] == 64, heaps      # 8 groups x 18 slices
+    # planted near-duplicates inside one slice: 16-entry heaps cannot prove k = 10 there -> the filter level answers
+    # (same results) and the engine bumps the heap size for the following batches
+    base = oracle.synth_row(1502, 0, dims, True)
+    rng = np.random.default_rng(3)
+    dup = base + rng.standard_normal((40, dims)).astype(np.float32) * np.float32(2e-3)
+    eng.add_batch(list(range(100, 140)), dup)                        # rows 100..139 overwritten: one row slice
+    probe = np.vstack([base[None, :], qs[:129]])
+    eng.set_option("batch_tensor", 0)
+    ref = [eng.search(q, 10) for q in probe[:2]]
+    eng.set_option("batch_tensor", 1)
+    assert eng.counter("batch_heap_bump") == 0
+    got = eng.search_batch(probe, 10)
+    assert got[:2] == ref
+    assert eng.counter("batch_heap_bump") == 1, "an unproven query must bump the nominee heap size"
+    eng.search_batch(probe, 10)
+    assert eng.counter("batch_last_heap") > 16

@@ -61,8 +61,8 @@ __host__ __device__ constexpr uint32_t batch_smem_bytes(int stages, int heap, bo
 // kernel (16 KB each: 6 k-blocks = 96 KB at 384 bf16 dims) and the ring stages carry the corpus only.
 __host__ __device__ constexpr uint32_t batch_ares_stage_bytes(bool pair) { return pair ? kBatchBBytes / 2 : kBatchBBytes; }
 __host__ __device__ constexpr uint32_t batch_ares_smem_bytes(int stages, int heap, bool pair, int ares_kb) {
-    return ares_kb * kBatchABytes + stages * batch_ares_stage_bytes(pair) + 2048 + 256 + kBatchStageSlots * kBatchM * 8 +
-           heap * kBatchM * 8 + 1024;
+    return ares_kb * kBatchABytes + stages * batch_ares_stage_bytes(pair) + 256 + kBatchStageSlots * kBatchM * 8 +
+           heap * kBatchM * 8 + 1024;       // (bf16 only: no epilogue scale area)
 }
 constexpr int kBatchThreads = 192;
 constexpr float kTf32Eps = 1.25f * 0x1p-9f;

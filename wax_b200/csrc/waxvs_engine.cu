@@ -229,6 +229,11 @@ struct wax_vs_engine {
     // Adaptive level choice: when more than a quarter of a batch fails the coarse bf16 bound (tightly clustered
     // neighbours), the next 16 batches nominate in TF32 straight away, then bf16 is probed again.
     uint32_t bf16_skip_batches = 0;
+    // adaptive nominee-heap size (bf16 level 1): a batch that left queries unproven makes the next `heap_bump_ttl` batches
+    // use one size more than the model picks; a failure right after probing back down doubles the time-out
+    uint32_t heap_bump = 0, heap_bump_ttl = 0, heap_backoff = 256;
+    bool heap_probing = false;
+    uint32_t last_heap = 0;
     // Bulk ingest / export staging: two pinned buffers so that the host-side copy of chunk i+1 overlaps
     // the DMA of chunk i, one copy stream, a device staging area for upserts and for the compaction of removes.
     struct Ingest {
@@ -832,6 +837,15 @@ static int ares_stages(bool pair, int heap, uint32_t num_kb, int want) {
     return batch_ares_smem_bytes(st, heap, pair, static_cast<int>(num_kb)) <= 227u * 1024u ? st : 0;
 }
 
+// P(X >= h) for X ~ Poisson(m): the chance that one row slice holds h or more of a query's "threatening" rows.
+static double poisson_tail(double m, int h) {
+    double term = std::exp(-m);                      // P(X = 0)
+    for (int i = 1; i <= h; ++i) term *= m / i;      // P(X = h)
+    double tail = 0.0, t = term;
+    for (int i = h + 1; i < h + 200 && t > 1e-300; ++i) { tail += t; t *= m / i; }
+    return std::min(1.0, tail + t);
+}
+
 // Enqueue the tensor-core nomination + exact finish for n_queries device-resident queries.  d_ok[i] = 1 when
 // query i's result is proven exact; the caller sends the others to the filter level, then to enqueue_search.
 // allow_bf16 = false forces TF32 nominations (adaptive level choice).  *used_bf16 reports what ran; d_tau_star
@@ -840,7 +854,7 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
                                     uint32_t k_eff, uint64_t row_offset, wax_vs_candidate *d_out, uint32_t *d_ok,
                                     const uint64_t *d_ids, cudaStream_t stream, uint64_t *launches,
                                     bool allow_bf16 = true, bool *used_bf16 = nullptr, float *d_tau_star = nullptr,
-                                    const uint32_t *d_mask = nullptr) {
+                                    const uint32_t *d_mask = nullptr, uint32_t *used_heap = nullptr) {
     int32_t rc = ensure_norms(e, stream);
     if (rc) return rc;
     bool bf16 = allow_bf16 && batch_bf16_wanted(e);
@@ -874,6 +888,9 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
             chk(set_smem_attr(batch_nominate_kernel<6, 16, true, true, true>, 227u * 1024u));
             chk(set_smem_attr(batch_nominate_kernel<4, 16, true, true, true>, 227u * 1024u));
             chk(set_smem_attr(batch_nominate_kernel<4, 64, true, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<5, 32, true, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<3, 24, false, true, true>, 227u * 1024u));
+            chk(set_smem_attr(batch_nominate_kernel<5, 32, true, true>, batch_smem_bytes(5, 32, true)));
             chk(set_smem_attr(batch_tf32_ts_kernel<16>, batch_ts_smem_bytes(16)));
             chk(set_smem_attr(batch_tf32_ts_kernel<64>, batch_ts_smem_bytes(64)));
             chk(set_smem_attr(batch_nominate_kernel<4, 16, false, false, false, true>, batch_smem_bytes(4, 16)));
@@ -911,25 +928,66 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         // the corpus tile.  Needs at least two groups; an odd group count is padded with an all-out-of-range group.
         // TS shape: queries in TMEM + CTA pair (dims <= 384, dims % 128 == 0): shared memory carries only the corpus
         const bool ts = !bf16 && !d_mask && e->tune.batch_ts != 0 && groups >= 2 && e->dims <= 384 && e->dims % 128u == 0;
-        const bool pair = ts || (e->tune.batch_pair != 0 && groups >= 2);
-        if (pair) groups = (groups + 1u) & ~1u;
+        bool pair = ts || (e->tune.batch_pair != 0 && groups >= 2);
         const uint32_t tile_rows = ts ? static_cast<uint32_t>(kTsN) : static_cast<uint32_t>(kBatchN);
         const uint32_t tiles_total = static_cast<uint32_t>((e->n_rows + tile_rows - 1) / tile_rows);
-        const uint32_t units = pair ? groups / 2u : groups;                       // clusters (or CTAs) per slice
-        const uint32_t unit_slots = static_cast<uint32_t>(e->sm_count) / (pair ? 2u : 1u);
-        uint32_t slices = std::max<uint32_t>(1, std::min<uint32_t>(unit_slots / units, tiles_total));
-        // kernel shape: 16-entry heaps + more stages when 16 nominees per slice comfortably cover k, else 64-entry heaps
+        auto slices_for = [&](bool pr, uint32_t g) {
+            const uint32_t units = pr ? ((g + 1u) & ~1u) / 2u : g;                   // clusters (or CTAs) per slice
+            const uint32_t unit_slots = static_cast<uint32_t>(e->sm_count) / (pr ? 2u : 1u);
+            return std::max<uint32_t>(1, std::min<uint32_t>(unit_slots / units, tiles_total));
+        };
+        uint32_t slices = slices_for(pair, groups);
+        // Nominee heap size per (slice, query) = kernel shape.  TF32 / TS shapes: 16 entries when 16 nominees per slice
+        // comfortably cover k (16 * slices >= 8 k), else 64.  bf16 shapes (16 / 24 / 32 / 64): level 1 can prove a query
+        // only if no slice holds `heap` rows scoring within the bf16 bound of the k-th result; with the corpus spread over
+        // the slices those "threatening" rows (about 2.2 k of them for the bf16 bound on unit-scale embeddings) fall
+        // ~Poisson(m = 2.2 k / slices) per slice, so the heap must clear m by six standard deviations -- ONE unproven
+        // query costs its whole batch a second pass (k = 72 over 18 slices left 209 of 1024 queries
+        // unproven with 16 entries, none with 24 / 32; 64-entry heaps cost a stage of the ring: 8.9 vs 6.8 ms).
         const bool small_heap = e->tune.batch_heap == 16 || (e->tune.batch_heap == 0 && 16u * slices >= 8u * k_eff);
+        uint32_t kprime = small_heap ? 16u : 64u;
+        if (bf16 && !ts) {
+            uint32_t want = static_cast<uint32_t>(std::max(e->tune.batch_heap, 0));
+            if (k_eff > 128u && want == 0u) want = 64u;       // large k: level 1 only has to NOMINATE k rows (filter level decides)
+            if (want != 16u && want != 24u && want != 32u && want != 64u) {
+                // expected cost of a batch = the shape's relative time + P(some query of the batch is unproven) x one more
+                // pass.  Threatening rows per query: ~2.2 k (cosine, unit rows) / ~2.8 k (dot: the bound scales with the
+                // LARGEST row norm) -- calibrated on profiles/batch_k_sweep_r02p.jsonl and c5_proof_heap16_r02c.jsonl.
+                static const uint32_t ladder[4] = {16u, 24u, 32u, 64u};
+                static const double rel_time[4] = {1.00, 1.02, 1.10, 1.40};
+                const double m = (e->similarity == WAX_VS_DOT ? 2.8 : 2.2) * k_eff / slices;
+                uint32_t bump = 0;
+                { std::lock_guard<std::mutex> pg(e->pool_mu); bump = e->heap_bump; }
+                double best = 1e30;
+                uint32_t pick = 3u;
+                for (uint32_t i = 0; i < 4u; ++i) {
+                    if (ladder[i] == 24u && pair) continue;                     // 24: single-CTA shapes only
+                    if (ladder[i] == 32u && groups < 2u) continue;              // 32: cta_group::2 shapes only
+                    const double p_fail = std::min(1.0, static_cast<double>(nq) * slices * poisson_tail(m, static_cast<int>(ladder[i])));
+                    if (p_fail >= 1.0 && ladder[i] != 64u) continue;             // hopeless: every batch would pay a second pass
+                    const double cost = rel_time[i] + 4.0 * p_fail;              // risk-averse: the model can be off
+                    if (cost < best) { best = cost; pick = i; }
+                }
+                for (; bump > 0u && pick < 3u; --bump) {                         // the data overrules the model (see caller)
+                    ++pick;
+                    if (ladder[pick] == 24u && pair) ++pick;
+                    if (pick < 3u && ladder[pick] == 32u && groups < 2u) ++pick;
+                }
+                want = ladder[std::min(pick, 3u)];
+                if (want == 0u) want = 64u;
+            }
+            if (want == 24u && pair) want = 32u;                       // 24: single-CTA shapes; 32: cta_group::2 shapes
+            if (want == 32u && groups < 2u) want = 64u;
+            if (want == 32u && !pair) { pair = true; slices = slices_for(true, groups); }
+            kprime = want;
+            if (used_heap) *used_heap = std::max(*used_heap, kprime);
+        }
+        if (pair) groups = (groups + 1u) & ~1u;
         // resident queries (bf16) when they leave room for a useful ring: >= 3 corpus stages (pair: >= 4 half-tile stages)
         const uint32_t num_kb16 = e->dims / kBatchKBlockBf16;
-        const int ares_st = (bf16 && !ts && e->tune.batch_ares) ? ares_stages(pair, small_heap ? 16 : 64, num_kb16, pair ? 6 : 3) : 0;
-        const bool ares = bf16 && !ts && ares_st >= (pair ? 4 : 2) && !(pair && !small_heap && ares_st < 4);
-        // 24-entry heaps (streamed-query bf16 shape only, where they fit beside four stages): when k exceeds the slice
-        // count a slice can hold 16 rows within the bf16 bound of the k-th score and the proof fails (1 query in 1 000
-        // on configs[4]); 24 nominees per slice make that a non-event for the cost of 8 KB.
-        const bool mid_heap = bf16 && !ts && !pair && !ares && (e->tune.batch_heap == 24 ||
-                              (e->tune.batch_heap == 0 && small_heap && slices < k_eff));
-        const uint32_t kprime = mid_heap ? 24u : (small_heap ? 16u : 64u);
+        const int ares_want = pair ? (kprime == 32u ? 5 : (kprime == 64u ? 4 : 6)) : (kprime == 64u ? 2 : 3);
+        const int ares_st = (bf16 && !ts && e->tune.batch_ares) ? ares_stages(pair, static_cast<int>(kprime), num_kb16, ares_want) : 0;
+        const bool ares = bf16 && !ts && ares_st >= (pair ? 4 : 2) && !(kprime >= 24u && ares_st < ares_want);
         slices = std::max<uint32_t>(1, std::min<uint32_t>(slices, 16384u / kprime));   // union fits the finish sort
         const uint32_t grid = groups * slices;
         if ((rc = ensure_dev(&c->d_heaps, &c->heaps_cap, static_cast<size_t>(grid) * kBatchM * kprime, "nominee heaps"))) return rc;
@@ -966,28 +1024,29 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
             if (small_heap) { cfg.dynamicSmemBytes = batch_ts_smem_bytes(16); lerr = cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<16>, map_c, qbase, bp); }
             else { cfg.dynamicSmemBytes = batch_ts_smem_bytes(64); lerr = cudaLaunchKernelEx(&cfg, batch_tf32_ts_kernel<64>, map_c, qbase, bp); }
         } else if (bf16) {
-            const uint32_t num_kb = num_kb16;
-            const int heap = small_heap ? 16 : 64;
-            const int st = ares_st;
-            if (ares) {
-                const uint32_t smem = batch_ares_smem_bytes(st, heap, pair, static_cast<int>(num_kb));
-                if (pair) {
-                    if (heap == 64) lerr = launch_nominate(batch_nominate_kernel<4, 64, true, true, true>, grid, batch_ares_smem_bytes(4, 64, true, static_cast<int>(num_kb)), true, stream, map_q, map_c, bp);
-                    else if (st >= 6) lerr = launch_nominate(batch_nominate_kernel<6, 16, true, true, true>, grid, smem, true, stream, map_q, map_c, bp);
-                    else lerr = launch_nominate(batch_nominate_kernel<4, 16, true, true, true>, grid, batch_ares_smem_bytes(4, 16, true, static_cast<int>(num_kb)), true, stream, map_q, map_c, bp);
-                } else {
-                    if (heap == 64) lerr = launch_nominate(batch_nominate_kernel<2, 64, false, true, true>, grid, batch_ares_smem_bytes(2, 64, false, static_cast<int>(num_kb)), false, stream, map_q, map_c, bp);
-                    else if (st >= 3) lerr = launch_nominate(batch_nominate_kernel<3, 16, false, true, true>, grid, smem, false, stream, map_q, map_c, bp);
-                    else lerr = launch_nominate(batch_nominate_kernel<2, 16, false, true, true>, grid, batch_ares_smem_bytes(2, 16, false, static_cast<int>(num_kb)), false, stream, map_q, map_c, bp);
-                }
+            const int kb = static_cast<int>(num_kb16);
+            const bool h16 = kprime == 16u;
+#define WAXVS_NOM(ST, HP, PR, AR, SMEM) lerr = launch_nominate(batch_nominate_kernel<ST, HP, PR, true, AR>, grid, (SMEM), PR, stream, map_q, map_c, bp)
+            if (ares && pair) {
+                if (kprime == 64u) WAXVS_NOM(4, 64, true, true, batch_ares_smem_bytes(4, 64, true, kb));
+                else if (kprime == 32u) WAXVS_NOM(5, 32, true, true, batch_ares_smem_bytes(5, 32, true, kb));
+                else if (ares_st >= 6) WAXVS_NOM(6, 16, true, true, batch_ares_smem_bytes(6, 16, true, kb));
+                else WAXVS_NOM(4, 16, true, true, batch_ares_smem_bytes(4, 16, true, kb));
+            } else if (ares) {
+                if (kprime == 64u) WAXVS_NOM(2, 64, false, true, batch_ares_smem_bytes(2, 64, false, kb));
+                else if (kprime == 24u) WAXVS_NOM(3, 24, false, true, batch_ares_smem_bytes(3, 24, false, kb));
+                else if (ares_st >= 3) WAXVS_NOM(3, 16, false, true, batch_ares_smem_bytes(3, 16, false, kb));
+                else WAXVS_NOM(2, 16, false, true, batch_ares_smem_bytes(2, 16, false, kb));
             } else if (pair) {
-                if (small_heap) lerr = launch_nominate(batch_nominate_kernel<6, 16, true, true>, grid, batch_smem_bytes(6, 16, true), true, stream, map_q, map_c, bp);
-                else lerr = launch_nominate(batch_nominate_kernel<4, 64, true, true>, grid, batch_smem_bytes(4, 64, true), true, stream, map_q, map_c, bp);
+                if (h16) WAXVS_NOM(6, 16, true, false, batch_smem_bytes(6, 16, true));
+                else if (kprime == 32u) WAXVS_NOM(5, 32, true, false, batch_smem_bytes(5, 32, true));
+                else WAXVS_NOM(4, 64, true, false, batch_smem_bytes(4, 64, true));
             } else {
-                if (mid_heap) lerr = launch_nominate(batch_nominate_kernel<4, 24, false, true>, grid, batch_smem_bytes(4, 24) - 2048u, false, stream, map_q, map_c, bp);
-                else if (small_heap) lerr = launch_nominate(batch_nominate_kernel<4, 16, false, true>, grid, batch_smem_bytes(4, 16), false, stream, map_q, map_c, bp);
-                else lerr = launch_nominate(batch_nominate_kernel<3, 64, false, true>, grid, batch_smem_bytes(3, 64), false, stream, map_q, map_c, bp);
+                if (kprime == 24u) WAXVS_NOM(4, 24, false, false, batch_smem_bytes(4, 24) - 2048u);
+                else if (h16) WAXVS_NOM(4, 16, false, false, batch_smem_bytes(4, 16));
+                else WAXVS_NOM(3, 64, false, false, batch_smem_bytes(3, 64));
             }
+#undef WAXVS_NOM
         } else if (pair) {
             if (small_heap) lerr = launch_nominate(batch_nominate_kernel<6, 16, true>, grid, batch_smem_bytes(6, 16, true), true, stream, map_q, map_c, bp);
             else lerr = launch_nominate(batch_nominate_kernel<4, 64, true>, grid, batch_smem_bytes(4, 64, true), true, stream, map_q, map_c, bp);
@@ -1665,8 +1724,9 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         if ((rc = ensure_dev(&c->d_tau_star, &c->tau_star_cap, static_cast<size_t>(n_queries) * 2, "filter thresholds"))) return rc;
         if ((rc = ensure_pinned(&c->h_tau_star, &c->h_tau_star_cap, static_cast<size_t>(n_queries) * 2, "filter threshold staging"))) return rc;
         bool used_bf16 = false;
+        uint32_t used_heap = 0;
         rc = enqueue_batch_tensor(e, c, d_queries, n_queries, k_eff, row_offset, d_out, c->d_ok, d_ids, c->stream, launches,
-                                  allow_bf16, &used_bf16, c->d_tau_star, d_mask);
+                                  allow_bf16, &used_bf16, c->d_tau_star, d_mask, &used_heap);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
         CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CUDA_TRY(cudaMemcpyAsync(c->h_tau_star, c->d_tau_star, 2 * n_queries * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
@@ -1676,6 +1736,27 @@ static int32_t run_queries_on_device(wax_vs_engine *e, SearchCtx *c, const float
         if (used_bf16 && k_eff <= 128u && unproven.size() * 4 > n_queries) {   // (large k is expected to need the filter level)
             std::lock_guard<std::mutex> pg(e->pool_mu);
             e->bf16_skip_batches = 16;
+        }
+        if (used_bf16 && k_eff <= 128u && used_heap != 0u && e->tune.batch_heap == 0) {
+            // the data has the last word on the heap size: unproven queries -> one size up for `ttl` batches; when the
+            // time-out ends one size down is probed again, and a failure during the probe doubles the time-out
+            std::lock_guard<std::mutex> pg(e->pool_mu);
+            e->last_heap = used_heap;
+            if (!unproven.empty()) {
+                if (used_heap < 64u) {
+                    if (e->heap_probing) e->heap_backoff = std::min<uint32_t>(e->heap_backoff * 2u, 1u << 16);
+                    e->heap_bump = std::min<uint32_t>(e->heap_bump + 1u, 3u);
+                    e->heap_bump_ttl = e->heap_backoff;
+                }
+                e->heap_probing = false;
+            } else {
+                e->heap_probing = false;
+                if (e->heap_bump > 0 && e->heap_bump_ttl > 0 && --e->heap_bump_ttl == 0) {
+                    --e->heap_bump;
+                    e->heap_probing = true;
+                    e->heap_bump_ttl = e->heap_bump ? e->heap_backoff : 0;
+                }
+            }
         }
         uint64_t retried = 0, retried_bf16 = 0;
         // Level 2, the filter levels: the unproven queries that have a finite threshold, as one compacted sub-batch, get
@@ -2693,6 +2774,8 @@ int32_t wax_vs_debug_counter(wax_vs_engine *e, const char *name, uint64_t *out) 
     else if (!strcmp(name, "ingest_d2h_bytes")) *out = e->ingest_d2h_bytes;
     else if (!strcmp(name, "norms_rows")) *out = e->norms_rows;       // rows whose cached 1/|v| is valid
     else if (!strcmp(name, "shadow_rows")) *out = e->shadow_rows;     // rows whose bf16 shadow is valid
+    else if (!strcmp(name, "batch_heap_bump")) *out = e->heap_bump;          // sizes above the model's nominee-heap choice (adaptive)
+    else if (!strcmp(name, "batch_last_heap")) *out = e->last_heap;          // nominee heap entries of the last bf16 level-1 launch
     else if (!strcmp(name, "pool_allocs")) *out = e->pool_allocs;
     else if (!strcmp(name, "pool_reuses")) *out = e->pool_reuses;
     else return fail(WAX_VS_ERR_ARGUMENT, "unknown counter '%s'", name);
@@ -2725,8 +2808,11 @@ int32_t wax_vs_debug_time_search_batch(wax_vs_engine *e, uint32_t n_queries, int
     uint64_t launches = 0;
     for (uint32_t it = 0; it < warmup + iters; ++it) {
         if (it == warmup) { launches = 0; CUDA_TRY(cudaEventRecord(c->ev0, c->stream)); }
-        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches);
+        uint32_t used_heap = 0;
+        rc = enqueue_batch_tensor(e, c, c->d_queries, n_queries, k_eff, 0, c->d_out, c->d_ok, nullptr, c->stream, &launches,
+                                  true, nullptr, nullptr, nullptr, &used_heap);
         if (rc) { cudaStreamSynchronize(c->stream); return rc; }
+        if (used_heap) { std::lock_guard<std::mutex> pg(e->pool_mu); e->last_heap = used_heap; }
     }
     CUDA_TRY(cudaEventRecord(c->ev1, c->stream));
     CUDA_TRY(cudaMemcpyAsync(c->h_ok, c->d_ok, n_queries * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
