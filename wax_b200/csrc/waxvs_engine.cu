@@ -132,7 +132,7 @@ struct Tuning {
     int batch_pair = 0;     // 1: cta_group::2 CTA pairs for the SS shapes (validated; no net gain)
     int batch_ts = 0;       // 1: queries in TMEM + CTA pairs (dims <= 384, dims % 128 == 0)
     int batch_large_k = 1;  // batches with 128 < k <= 1024 take the tensor-core levels (0: loop the single-query emit + select path)
-    int batch_heap = 0;     // 0 auto, 16, 24 (bf16 streamed shape) or 64: nominee heap size per (slice, query) = kernel shape
+    int batch_heap = 0;     // 0 auto (cost model + adaptive bump), 16 / 24 / 32 / 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
     int batch_bf16 = 1;     // 1: nominate from a bf16 shadow of the corpus when HBM allows (kind::f16 MMAs, 2x the TF32 rate; +dims*2 B/row)
     int batch_ares = 1;     // with batch_bf16: keep the CTA's queries resident in shared memory when they fit (dims <= 512)
@@ -941,9 +941,9 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
         // comfortably cover k (16 * slices >= 8 k), else 64.  bf16 shapes (16 / 24 / 32 / 64): level 1 can prove a query
         // only if no slice holds `heap` rows scoring within the bf16 bound of the k-th result; with the corpus spread over
         // the slices those "threatening" rows (about 2.2 k of them for the bf16 bound on unit-scale embeddings) fall
-        // ~Poisson(m = 2.2 k / slices) per slice, so the heap must clear m by six standard deviations -- ONE unproven
-        // query costs its whole batch a second pass (k = 72 over 18 slices left 209 of 1024 queries
-        // unproven with 16 entries, none with 24 / 32; 64-entry heaps cost a stage of the ring: 8.9 vs 6.8 ms).
+        // ~Poisson(m = 2.2 k / slices) per slice.  ONE unproven query costs its whole batch a second pass (DESIGN 4.5.2:
+        // k = 72 over 18 slices left 209 of 1024 queries unproven with 16 entries, none with 24 / 32), while 64-entry
+        // heaps cost a stage of the ring (8.6 vs 6.1-6.9 ms): the heap that minimises the expected cost is picked below.
         const bool small_heap = e->tune.batch_heap == 16 || (e->tune.batch_heap == 0 && 16u * slices >= 8u * k_eff);
         uint32_t kprime = small_heap ? 16u : 64u;
         if (bf16 && !ts) {
@@ -974,7 +974,6 @@ static int32_t enqueue_batch_tensor(wax_vs_engine *e, SearchCtx *c, const float 
                     if (pick < 3u && ladder[pick] == 32u && groups < 2u) ++pick;
                 }
                 want = ladder[std::min(pick, 3u)];
-                if (want == 0u) want = 64u;
             }
             if (want == 24u && pair) want = 32u;                       // 24: single-CTA shapes; 32: cta_group::2 shapes
             if (want == 32u && groups < 2u) want = 64u;
