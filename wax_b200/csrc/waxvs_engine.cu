@@ -131,6 +131,7 @@ struct Tuning {
     int time_overlap = 0;   // wax_vs_debug_time_search: alternate consecutive queries over two streams
     int batch_pair = 0;     // 1: cta_group::2 CTA pairs for the SS shapes (validated; no net gain)
     int batch_ts = 0;       // 1: queries in TMEM + CTA pairs (dims <= 384, dims % 128 == 0)
+    uint32_t tma_max_dims = 4096;   // generic TMA shape up to this row length, the direct-load kernel above
     int batch_large_k = 1;  // batches with 128 < k <= 1024 take the tensor-core levels (0: loop the single-query emit + select path)
     int batch_heap = 0;     // 0 auto (cost model + adaptive bump), 16 / 24 / 32 / 64: nominee heap size per (slice, query) = kernel shape
     int batch_noinsert = 0; // instrumentation: GEMM pipeline only (results meaningless)
@@ -414,8 +415,8 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg, int mode = 0
         if (c == 1 || c == 2 || c == 3 || c == 4 || c == 6 || c == 8 || c == 12) C = c;   // unrolled shapes (12: the 1536-dim embeddings)
     }
     if (C == 0 && d < 32) return false;                  // a few floats per row: the direct-load kernel
-    if (C == 0 && d > 3072) return false;                // very long rows: too few warps fit beside two stages; the
-                                                         // direct-load kernel streams them at 6.7-6.8 TB/s (sweep_big_r02j)
+    if (C == 0 && d > e->tune.tma_max_dims) return false;   // very long rows: too few warps fit beside two stages; the
+                                                             // direct-load kernel streams them at 6.9 TB/s (sweep_long_r02t)
     // rows per step / warps per CTA by row length (profiles/dims_sweep_r01_call17.json): keep a step at >= 4-12 KB
     // and give short rows more warps (their bound is per-row instruction latency, not bytes in flight)
     int R, warps_default = 8;
@@ -426,6 +427,7 @@ static bool pick_tma_config(const wax_vs_engine *e, TmaConfig *cfg, int mode = 0
         // profiles/small_dims_sweep_r02h.jsonl / sweep_big_r02i.jsonl: 1000 dims 6.1 -> 7.3 TB/s, 2048 dims 6.5 -> 7.3)
         int auto_r = d > 256 ? 4 : 8;
         if (d > 640) { auto_r = 8; while (auto_r > 1 && static_cast<size_t>(auto_r) * d * 4 > 32768) auto_r >>= 1; }
+        if (d > 3072) auto_r = 1;       // 12-16 KB rows: one per step keeps six warps in flight (3584: 7.36, 4096: 7.24 TB/s)
         const int want_r = e->tune.rows_per_step;
         R = (want_r == 1 || want_r == 2 || want_r == 4 || want_r == 8) ? want_r : auto_r;
         if (R == 8) warps_default = 16;
@@ -2843,6 +2845,7 @@ int32_t wax_vs_debug_set_option(wax_vs_engine *e, const char *key, int64_t value
     else if (!strcmp(key, "batch_noinsert")) e->tune.batch_noinsert = v;
     else if (!strcmp(key, "batch_heap")) e->tune.batch_heap = v;
     else if (!strcmp(key, "batch_large_k")) e->tune.batch_large_k = v;
+    else if (!strcmp(key, "tma_max_dims")) e->tune.tma_max_dims = static_cast<uint32_t>(std::max(v, 0));
     else if (!strcmp(key, "batch_pair")) e->tune.batch_pair = v;
     else if (!strcmp(key, "batch_ts")) e->tune.batch_ts = v;
     else if (!strcmp(key, "batch_bf16")) { e->tune.batch_bf16 = v; e->shadow_unavailable = false; e->bf16_skip_batches = 0; }

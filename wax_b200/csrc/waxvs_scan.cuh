@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
         const float4 *tile = reinterpret_cast<const float4 *>(ring + s * STAGE_BYTES);
 
         float sum0[R], sum1[R];
-        if (C == 0 && R >= 2) {
+        if (C == 0) {
             // Generic rows (dims < 128 or not one of the unrolled multiples of 128), several rows per step: chunk-outer /
             // row-inner, so a query chunk is read from shared memory once for the R rows (the row-outer form read it per row:
             // twice the shared-memory traffic, 5.6 instead of 7.3 TB/s at 2560 dims).  Each row still sees its chunks in ascending
@@ -425,6 +425,8 @@ __global__ void __launch_bounds__(512, 1) scan_tma_kernel(const __grid_constant_
             for (int r = 0; r < R; ++r)
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { a[r][j] = 0.f; b[r][j] = 0.f; }
+            // (a few chunks in flight per lane: with one or two rows per step the loads of consecutive chunks must overlap)
+#pragma unroll (R >= 8 ? 1 : 8 / R)
             for (int c = 0; c < CN; ++c) {
                 if (lane + 32 * c >= D4) break;
                 const float4 qc = qchunk(c);
