@@ -360,7 +360,7 @@ def _batched_line(eng, rows, dims, batch, top_k, metric_name, workload, steps):
     HOST buffers (queries H2D, ids/scores D2H inside the timed region) + which level answered."""
     import torch
     peaks = _tensor_peaks()
-    ms, launches, unproven = eng.time_search_batch(batch, top_k, steps, warmup=2, seed=QUERY_SEED)
+    ms, launches, unproven = eng.time_search_batch(batch, top_k, steps, warmup=4, seed=QUERY_SEED)
     per = ms / steps
     flops = 2.0 * batch * rows * dims
     tf = flops / (per * 1e-3) / 1e12
