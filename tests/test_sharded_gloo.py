@@ -51,6 +51,12 @@ def _worker(rank, world, port, total, dims, k, seed, q, out_dir):
         ids, scores, ns = eng.search_batch_arrays(qs, k)
         assert ids.shape == (3, min(k, total)) and ns.tolist() == [len(b) for b in batch]
         np.save(Path(out_dir) / f"b{rank}.npy", np.array(batch[1], dtype=np.float64))
+        # the filtered collective search exists only on the fused peer-memory transport: a loud error here, not a fallback
+        try:
+            eng.search_filtered(q, k, allow=[1, 2, 3])
+            raise AssertionError("search_filtered must refuse the all-gather transport")
+        except wax_b200.InvalidToc:
+            pass
         # pipelined form: three batches of different sizes in flight on the worker thread -- the all-gathers must
         # line up across the ranks (submission order), and each batch must come back as the synchronous call has it
         handles = [eng.search_batch_submit(qs[:n], k) for n in (3, 1, 2)]
